@@ -1,0 +1,41 @@
+// Host-side helpers shared by every launcher of the C-ABI library:
+// status codes + last-error string, TMA tensor-map encoding through the driver entry point
+// (resolved at run time with cudaGetDriverEntryPoint, so the .so has no link-time dependency
+// on libcuda and can be dlopen'ed on a GPU-less box for the symbol-export test).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mapanything_b200.h"
+
+namespace ma {
+
+void set_last_error(const char* fmt, ...);
+
+#define MA_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ma::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return MA_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define MA_REQUIRE(cond, ...)                  \
+  do {                                         \
+    if (!(cond)) {                             \
+      ma::set_last_error(__VA_ARGS__);         \
+      return MA_ERR_INVALID;                   \
+    }                                          \
+  } while (0)
+
+// Encodes a bf16 tiled tensor map with 128-byte swizzle. dims/strides innermost first;
+// strides_bytes[i] is the stride of dimension i+1 (dimension 0 is contiguous).
+// Returns MA_OK or an error code (message in ma_last_error()).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+int device_sm_count();
+
+}  // namespace ma

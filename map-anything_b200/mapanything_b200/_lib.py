@@ -1,0 +1,79 @@
+"""ctypes binding of the C-ABI CUDA library (include/mapanything_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing or a call fails, the caller gets an
+exception.  Nothing in this package computes on the CPU or through PyTorch library kernels instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("MAPANYTHING_B200_LIB", _HERE / "libmapanything_b200.so"))
+
+MA_OK = 0
+MA_BF16, MA_F32 = 0, 1
+MA_ACT_NONE, MA_ACT_GELU, MA_ACT_RELU = 0, 1, 2
+
+
+class MapAnythingB200Error(RuntimeError):
+    pass
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("out_dtype", C.c_int32),
+        ("act", C.c_int32),
+        ("bias", C.c_void_p),
+        ("colscale", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("residual_dtype", C.c_int32),
+        ("residual_row_mod", C.c_int32),
+        ("out_relu", C.c_void_p),
+        ("ldo_relu", C.c_int64),
+        ("rows_per_group_in", C.c_int32),
+        ("rows_per_group_out", C.c_int32),
+        ("row_offset_out", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/mapanything_b200.h declares.
+_i, _i64, _p, _f = C.c_int, C.c_int64, C.c_void_p, C.c_float
+SIGNATURES = {
+    "ma_last_error": (C.c_char_p, []),
+    "ma_abi_version": (_i, []),
+    "ma_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "ma_gemm_bf16": (_i, [_p, _i64, _p, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the library (once). Raises if it has not been built: there is no other compute path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MapAnythingB200Error(
+            f"{LIB_PATH} not found. Build it with `python map-anything_b200/build.py` "
+            "(nvcc, sm_100a). This package has no CPU / PyTorch fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale / missing a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != MA_OK:
+        msg = load().ma_last_error().decode("utf-8", "replace")
+        raise MapAnythingB200Error(f"{what} failed (status {rc}): {msg}")

@@ -1,0 +1,104 @@
+"""GPU parity tests for the tcgen05 GEMM (ma_gemm_bf16) against a plain fp32 PyTorch matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, bias=None, act=0, colscale=None, residual=None):
+    y = x.float() @ w.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 1:
+        y = torch.nn.functional.gelu(y)
+    elif act == 2:
+        y = torch.relu(y)
+    if colscale is not None:
+        y = y * colscale
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def _check(y, ref, tol=2e-2, what=""):
+    err = (y.float() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, f"{what}: max abs err {err:.4g} vs scale {scale:.4g}"
+
+
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (2740, 1024, 1024), (1369, 96, 1024), (1000, 3072, 640)])
+def test_gemm_plain(bn, shape):
+    from mapanything_b200 import ops
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(x, w, out, block_n=bn)
+    torch.cuda.synchronize()
+    _check(out, _ref(x, w), 2e-3, f"plain {shape} bn={bn}")
+
+
+def test_gemm_epilogues():
+    from mapanything_b200 import ops
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, N, K = 1370 * 2, 1024, 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    res = torch.randn(M, N, device="cuda", generator=g)
+
+    # bias + GELU -> bf16
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out, bias=bias, act=ops.MA_ACT_GELU)
+    _check(out, _ref(x, w, bias, 1), 1e-2, "bias+gelu")
+
+    # bias, layerscale, fp32 residual in place
+    stream = res.clone()
+    ops.gemm(x, w, stream, bias=bias, colscale=gamma, residual=stream)
+    _check(stream, _ref(x, w, bias, 0, gamma, res), 2e-3, "bias+ls+residual(in place)")
+
+    # relu + bf16 residual + second relu output
+    resb = res.bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, w, out, bias=bias, residual=resb, out_relu=out2)
+    ref = _ref(x, w, bias, 0, None, resb)
+    _check(out, ref, 1e-2, "bf16 residual")
+    _check(out2, torch.relu(ref), 1e-2, "relu twin output")
+
+
+def test_gemm_row_remap_and_strides():
+    from mapanything_b200 import ops
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n_img, P, K, N = 3, 1369, 640, 1024
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xfull = torch.randn(n_img * P, K + 64, device="cuda", generator=g).bfloat16()
+    x = xfull[:, :K]  # strided view, ld = K+64
+    w = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    pos = torch.randn(P + 1, N, device="cuda", generator=g)
+    out = torch.zeros(n_img * (P + 1), N, device="cuda")
+    ops.gemm(x, w, out, bias=bias, residual=pos[1:], residual_row_mod=P, rows_per_group_in=P,
+             rows_per_group_out=P + 1, row_offset_out=1)
+    ref = (_ref(x, w, bias).view(n_img, P, N) + pos[1:]).reshape(n_img, P, N)
+    got = out.view(n_img, P + 1, N)
+    _check(got[:, 1:], ref, 2e-3, "row remap")
+    assert got[:, 0].abs().max().item() == 0.0
+
+    # ragged N (scalar store path), N not a multiple of 32 and ldo padded
+    N2 = 6
+    w2 = (torch.randn(N2, 128, device="cuda", generator=g) / 11.0).bfloat16()
+    x2 = torch.randn(777, 128, device="cuda", generator=g).bfloat16()
+    b2 = torch.randn(N2, device="cuda", generator=g)
+    out2 = torch.zeros(777, 8, device="cuda")
+    ops.gemm(x2, w2, out2[:, :N2], bias=b2)
+    _check(out2[:, :N2], _ref(x2, w2, b2), 2e-3, "ragged N")
+    assert out2[:, N2:].abs().max().item() == 0.0
