@@ -78,6 +78,21 @@ typedef struct ma_gemm_epilogue {
 int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                  const ma_gemm_epilogue* epi, int block_n, void* stream);
 
+/* ---- Attention forward (head_dim 64, non-causal) ---------------------------------------------
+ * Replaces the attention of the DINOv2 blocks (reference dinov2/layers/attention.py:53-90,
+ * F.scaled_dot_product_attention / xformers there) and of the info-sharing frame / global blocks
+ * (uniception, invoked at model.py:1532-1542; analog vggt/layers/attention.py:46-76).
+ *
+ * q/k/v are token-major bf16 matrices (typically three column slices of one fused-qkv GEMM output):
+ * head h of q occupies columns [q_col0 + 64 h, q_col0 + 64 h + 64).  Sequence s uses query rows
+ * [s*q_seq_stride, s*q_seq_stride + q_len) and key/value rows [s*kv_seq_stride, ... + kv_len).
+ * out[row, o_col0 + 64 h ...] = softmax(q k^T * softmax_scale) v, bf16.  QK^T and PV run on tcgen05
+ * with accumulators in TMEM; softmax statistics and the output accumulator are fp32. */
+int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
+                     int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                     int o_col0, int num_seqs, int num_heads, int q_len, int kv_len, int64_t q_seq_stride,
+                     int64_t kv_seq_stride, float softmax_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,350 @@
+// Flash-style attention forward for sm_100a (head_dim 64, bf16 in/out, fp32 softmax + accumulate).
+//
+// One CTA = one 128-row query tile of one head of one sequence; two CTAs are resident per SM (<=113 KB
+// smem, 256 TMEM columns each) so that one CTA's softmax overlaps the other's tensor-core work.
+//
+//   warp 0      : TMEM alloc + TMA producer (Q once, K/V tiles through a 2-stage mbarrier ring)
+//   warp 1      : MMA issuer.  S = Q.K^T  (tcgen05.mma 128x128x16, K-major A/B, 4 per tile) into TMEM,
+//                 PV = P.V      (tcgen05.mma 128x64x16, A = P from smem, B = V MN-major, 8 per tile)
+//   warps 2..5  : softmax / accumulate, one query row per thread.  Pass 1 reads S from TMEM for the row
+//                 max, pass 2 re-reads it, exponentiates, writes P (bf16) into the 128B-swizzled smem
+//                 operand buffer.  The PV product of the PREVIOUS tile is folded into the fp32 register
+//                 accumulator (O = O*alpha + PV) while the tensor core works on the current tile.
+//
+// Sequences are contiguous row ranges of a token-major matrix ([tokens][heads*64] slices of the fused
+// qkv GEMM output, so no head permute/copy is ever materialised).  Keys past kv_len are masked to -inf
+// (TMA zero-fills rows beyond the tensor; rows that belong to the next sequence are masked the same way).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ma {
+
+constexpr int ATT_BM = 128;
+constexpr int ATT_BN = 128;
+constexpr int ATT_D = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_STAGES = 2;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q, one K stage, one V stage, half of P
+constexpr int ATT_SMEM_BYTES = ATT_TILE_BYTES * (1 + 2 * ATT_STAGES + 2) + 256;
+constexpr int ATT_TMEM_COLS = 256;            // S: [0,128)  PV0: [128,192)  PV1: [192,256)
+
+struct AttnParams {
+  __nv_bfloat16* out;
+  int64_t ldo;
+  int q_len, kv_len;
+  int64_t q_seq_stride, kv_seq_stride;  // rows between consecutive sequences
+  int q_col0, k_col0, v_col0, o_col0;   // column of head 0 in the respective matrices
+  float scale_log2;                     // softmax scale * log2(e)
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;
+  uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;  // two 16 KB K-major sub-tiles (kv 0..63, 64..127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + ATT_STAGES;
+  uint64_t* v_full = k_empty + ATT_STAGES;
+  uint64_t* v_empty = v_full + ATT_STAGES;
+  uint64_t* s_full = v_empty + ATT_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* p_empty = p_full + 1;
+  uint64_t* pv_full = p_empty + 1;   // [2]
+  uint64_t* pv_empty = pv_full + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  const int q0 = blockIdx.x * ATT_BM;
+  const int head = blockIdx.y;
+  const int seq = blockIdx.z;
+  const int n_kv_tiles = (p.kv_len + ATT_BN - 1) / ATT_BN;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[ma] attention: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_full[i], 1);
+      mbar_init(&pv_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_pv = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int q_row = static_cast<int>(seq * p.q_seq_stride) + q0;
+      const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, kv_row0 + j * ATT_BN);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, kv_row0 + j * ATT_BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t p_addr = smem_u32(sP);
+
+      auto issue_s = [&](int j) {
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(s_empty, (j & 1) ^ 1);  // softmax has drained S of tile j-1
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) {
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                       make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(s_full);
+      };
+
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        if (j + 1 < n_kv_tiles) issue_s(j + 1);
+        const int st = j % ATT_STAGES;
+        const uint32_t ph = (j / ATT_STAGES) & 1;
+        const int buf = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], ph);
+        mbar_wait(&pv_empty[buf], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          const uint64_t adesc = make_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
+          umma_bf16_ss(tmem_pv + buf * ATT_D, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(p_empty);
+        umma_commit(&pv_full[buf]);
+      }
+    }
+  } else {
+    // ---- softmax / accumulate warps: thread <-> query row -------------------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    float o_acc[ATT_D];
+#pragma unroll
+    for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY;  // running max of raw scores
+    float l_run = 0.f;
+    float alpha_prev = 1.f;
+    const uint32_t sw = static_cast<uint32_t>(row & 7);
+    uint8_t* p_row = sP + row * 128;
+
+    auto fold_pv = [&](int j, float alpha) {
+      const int buf = j & 1;
+      mbar_wait(&pv_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < ATT_D; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_base + buf * ATT_D + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o_acc[c + i] = fmaf(o_acc[c + i], alpha, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pv_empty[buf]);
+    };
+
+    for (int j = 0; j < n_kv_tiles; ++j) {
+      const int kv_valid = p.kv_len - j * ATT_BN;  // >= 1; < 128 only on the last tile
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float m_tile = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_base + c, v);
+        tmem_ld_wait();
+        if (kv_valid >= c + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < kv_valid) m_tile = fmaxf(m_tile, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, m_tile);
+      const float alpha = fast_exp2((m_run - m_new) * p.scale_log2);
+      const float m_scaled = m_new * p.scale_log2;
+      m_run = m_new;
+
+      mbar_wait(p_empty, (j & 1) ^ 1);  // PV of tile j-1 has finished reading P
+      // pass 2: probabilities -> bf16 -> swizzled smem operand
+      float l_tile = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < ATT_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_base + c, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
+          if (c + i >= kv_valid) x = 0.f;
+          e[i] = x;
+          l_tile += x;
+        }
+        uint8_t* dst = p_row + (c >> 6) * ATT_TILE_BYTES;
+        const uint32_t chunk0 = static_cast<uint32_t>((c & 63) >> 3);  // 16-byte chunk index inside the 128 B row
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk = make_uint4(pack_bf16x2(e[8 * q + 0], e[8 * q + 1]), pack_bf16x2(e[8 * q + 2], e[8 * q + 3]),
+                                pack_bf16x2(e[8 * q + 4], e[8 * q + 5]), pack_bf16x2(e[8 * q + 6], e[8 * q + 7]));
+          *reinterpret_cast<uint4*>(dst + (((chunk0 + q) ^ sw) << 4)) = pk;
+        }
+      }
+      l_run = l_run * alpha + l_tile;
+      tc_fence_before();        // S reads are complete before the MMA warp may overwrite S
+      fence_proxy_async_smem(); // P writes visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+      // fold the previous tile's PV while the tensor core computes S_{j+1} and PV_j
+      if (j > 0) fold_pv(j - 1, alpha_prev);
+      alpha_prev = alpha;  // O_j = O_{j-1} * alpha_j + PV_j is applied when PV_j is folded (next iteration)
+    }
+    fold_pv(n_kv_tiles - 1, alpha_prev);
+
+    const int q_idx = q0 + row;
+    if (q_idx < p.q_len) {
+      const float inv_l = 1.0f / l_run;
+      __nv_bfloat16* optr = p.out + (static_cast<int64_t>(seq) * p.q_seq_stride + q_idx) * p.ldo + p.o_col0 + head * ATT_D;
+#pragma unroll
+      for (int q = 0; q < ATT_D / 8; ++q) {
+        uint4 pk = make_uint4(pack_bf16x2(o_acc[8 * q + 0] * inv_l, o_acc[8 * q + 1] * inv_l),
+                              pack_bf16x2(o_acc[8 * q + 2] * inv_l, o_acc[8 * q + 3] * inv_l),
+                              pack_bf16x2(o_acc[8 * q + 4] * inv_l, o_acc[8 * q + 5] * inv_l),
+                              pack_bf16x2(o_acc[8 * q + 6] * inv_l, o_acc[8 * q + 7] * inv_l));
+        reinterpret_cast<uint4*>(optr)[q] = pk;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+  }
+}
+
+}  // namespace ma
+
+extern "C" int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
+                                int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
+                                int64_t ldo, int o_col0, int num_seqs, int num_heads, int q_len, int kv_len,
+                                int64_t q_seq_stride, int64_t kv_seq_stride, float softmax_scale, void* stream) {
+  using namespace ma;
+  MA_REQUIRE(q && k && v && out, "ma_attention_fwd: null pointer");
+  MA_REQUIRE(num_seqs > 0 && num_heads > 0 && q_len > 0 && kv_len > 0, "ma_attention_fwd: bad sizes");
+  MA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
+                 v_col0 % 8 == 0 && o_col0 % 8 == 0,
+             "ma_attention_fwd: strides / column offsets must be multiples of 8 elements");
+  MA_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "ma_attention_fwd: out not 16-byte aligned");
+  MA_REQUIRE((int64_t)(num_seqs - 1) * q_seq_stride + q_len <= q_rows && (int64_t)(num_seqs - 1) * kv_seq_stride + kv_len <= kv_rows,
+             "ma_attention_fwd: sequences exceed the q / kv row counts");
+  MA_REQUIRE(q_col0 + num_heads * ATT_D <= ldq && k_col0 + num_heads * ATT_D <= ldk && v_col0 + num_heads * ATT_D <= ldv &&
+                 o_col0 + num_heads * ATT_D <= ldo,
+             "ma_attention_fwd: head columns exceed the row stride");
+
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[2] = {ATT_D, ATT_BM};
+  {
+    uint64_t dims[2] = {(uint64_t)ldq, (uint64_t)q_rows};
+    uint64_t str[1] = {(uint64_t)ldq * 2};
+    int rc = make_tmap_bf16(&tq, q, 2, dims, str, box);
+    if (rc != MA_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ldk, (uint64_t)kv_rows};
+    uint64_t str[1] = {(uint64_t)ldk * 2};
+    int rc = make_tmap_bf16(&tk, k, 2, dims, str, box);
+    if (rc != MA_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)ldv, (uint64_t)kv_rows};
+    uint64_t str[1] = {(uint64_t)ldv * 2};
+    int rc = make_tmap_bf16(&tv, v, 2, dims, str, box);
+    if (rc != MA_OK) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ATT_SMEM_BYTES));
+    configured = true;
+  }
+  AttnParams p;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.q_len = q_len;
+  p.kv_len = kv_len;
+  p.q_seq_stride = q_seq_stride;
+  p.kv_seq_stride = kv_seq_stride;
+  p.q_col0 = q_col0;
+  p.k_col0 = k_col0;
+  p.v_col0 = v_col0;
+  p.o_col0 = o_col0;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  dim3 grid((q_len + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
+  attention_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}

@@ -212,6 +212,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // erf with |abs err| < 1.5e-7 (Abramowitz & Stegun 7.1.26) -- far below bf16 output resolution.
 __device__ __forceinline__ float fast_erf(float x) {
   float ax = fabsf(x);

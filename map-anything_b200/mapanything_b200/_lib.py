@@ -49,6 +49,8 @@ SIGNATURES = {
     "ma_abi_version": (_i, []),
     "ma_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ma_gemm_bf16": (_i, [_p, _i64, _p, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _p]),
+    "ma_attention_fwd": (_i, [_p, _i64, _i64, _i, _p, _i64, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i64,
+                              _i64, _f, _p]),
 }
 
 _lib = None

@@ -98,3 +98,47 @@ def gemm(
     )
     _count()
     return out
+
+
+def attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    num_heads: int,
+    num_seqs: int,
+    q_len: int,
+    kv_len: int,
+    q_seq_stride: Optional[int] = None,
+    kv_seq_stride: Optional[int] = None,
+    scale: Optional[float] = None,
+) -> torch.Tensor:
+    """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
+
+    q/k/v/out are 2-D token-major bf16 views whose rows may be strided column slices of a wider matrix
+    (e.g. qkv[:, :D], qkv[:, D:2D], qkv[:, 2D:]); no head permutation is materialised. See ma_attention_fwd."""
+    for t in (q, k, v, out):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise ValueError("attention operands must be 2-D bf16 with contiguous rows")
+    if q_seq_stride is None:
+        q_seq_stride = q_len
+    if kv_seq_stride is None:
+        kv_seq_stride = kv_len
+    if scale is None:
+        scale = 64 ** -0.5
+    lib = _lib.load()
+    # Column offsets are folded into the base pointers; the tensor map width is the row stride, which
+    # always covers [col0, col0 + heads*64) of the parent matrix when the view is a column slice of it.
+    check(
+        lib.ma_attention_fwd(
+            q.data_ptr(), q.stride(0), q.shape[0], 0,
+            k.data_ptr(), k.stride(0), k.shape[0], 0,
+            v.data_ptr(), v.stride(0), 0,
+            out.data_ptr(), out.stride(0), 0,
+            num_seqs, num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, float(scale), _stream(),
+        ),
+        "ma_attention_fwd",
+    )
+    _count()
+    return out
