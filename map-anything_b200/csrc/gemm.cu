@@ -290,8 +290,9 @@ static int pick_block_n(int M, int N) {
     const int bn = cands[i];
     const int tiles = tiles_m * ((N + bn - 1) / bn);
     const int waves = (tiles + sms - 1) / sms;
-    // per-tile cost ~ BN (MMA time) + fixed overhead; narrower tiles also pay more smem bandwidth
-    const double cost = waves * (bn + (bn == 64 ? 40.0 : (bn == 128 ? 24.0 : 16.0)));
+    // measured on B200 (tools/bench_kernels.py): a 128-wide tile runs at ~75% and a 64-wide tile at ~43% of
+    // the 256-wide tile's MMA rate (smem operand bandwidth), so per-tile cost is not proportional to BN.
+    const double cost = waves * (bn == 256 ? 1.0 : (bn == 128 ? 0.66 : 0.58));
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;

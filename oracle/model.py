@@ -1,0 +1,299 @@
+"""Oracle MapAnything: fp32 PyTorch restatement of the reference model class (test infrastructure only).
+
+Follows /root/reference/mapanything/models/mapanything/model.py:
+  __init__                         :90-214, :224-318, :320-388, :390-588 (only the released configuration:
+                                    alternating attention + intermediate features, dpt+pose heads,
+                                    scene_rep_type "raydirs+depth+pose+confidence+mask")
+  _encode_n_views                  :622-645
+  _compute_pose_..._in_ref_view    :647-751
+  _encode_and_fuse_ray_dirs        :753-825
+  _encode_and_fuse_depths          :827-1010   (sparse-depth branch :912-941 omitted: sparse_depth_prob is 0 in infer)
+  _encode_and_fuse_cam_quats_...   :1012-1131
+  _encode_and_fuse_optional_...    :1133-1261
+  downstream_head                  :1340-1475  (mini-batching :1355-1438 gives identical results; here: fixed chunks)
+  forward                          :1477-1909
+  _configure/_restore_geometric... :1911-1961
+  infer                            :1963-2112
+Sub-module attribute names match the reference so `state_dict()` uses the same key prefixes
+(encoder., ray_dirs_encoder., ..., info_sharing., dpt_feature_head., dpt_regressor_head., dense_head.{0,1}.,
+pose_head., scale_head., fusion_norm_layer., scale_token).
+"""
+from __future__ import annotations
+
+from functools import partial
+from typing import Any, Dict, List
+
+import torch
+import torch.nn as nn
+
+from . import geometry as G
+from . import inference as I
+from . import uniception_modules as U
+from .vit import OracleDinoV2Encoder
+
+
+def _make_encoder(encoder_str: str, **kw):
+    if encoder_str == "dinov2":
+        return OracleDinoV2Encoder(**kw)
+    if encoder_str == "dense_rep_encoder":
+        return U.DenseRepresentationEncoder(**kw)
+    if encoder_str == "global_rep_encoder":
+        return U.GlobalRepresentationEncoder(**kw)
+    raise ValueError(f"unknown encoder_str {encoder_str}")
+
+
+class MapAnythingOracle(nn.Module):
+    def __init__(self, name, encoder_config, info_sharing_config, pred_head_config, geometric_input_config,
+                 fusion_norm_layer=partial(nn.LayerNorm, eps=1e-6), pretrained_checkpoint_path=None,
+                 load_specific_pretrained_submodules=False, specific_pretrained_submodules=None,
+                 torch_hub_force_reload=False):
+        super().__init__()
+        self.name = name
+        self.encoder_config, self.info_sharing_config = encoder_config, info_sharing_config
+        self.pred_head_config, self.geometric_input_config = pred_head_config, geometric_input_config
+        self.info_sharing_type = info_sharing_config["model_type"]
+        self.info_sharing_return_type = info_sharing_config["model_return_type"]
+        self.pred_head_type = pred_head_config["type"]
+        assert self.info_sharing_type == "alternating_attention" and self.info_sharing_return_type == "intermediate_features"
+        assert self.pred_head_type == "dpt+pose"
+        assert pred_head_config["adaptor_type"] == "raydirs+depth+pose+confidence+mask"
+        self.scene_rep_type = "raydirs+depth+pose+confidence+mask"
+
+        enc_cfg = dict(encoder_config)
+        enc_cfg.pop("uses_torch_hub", None)
+        self.encoder = _make_encoder(**enc_cfg)
+        c = self.encoder.enc_embed_dim
+        g = geometric_input_config
+        for key in ("ray_dirs_encoder_config", "depth_encoder_config"):
+            g[key]["enc_embed_dim"], g[key]["patch_size"] = c, self.encoder.patch_size
+        for key in ("scale_encoder_config", "cam_rot_encoder_config", "cam_trans_encoder_config"):
+            g[key]["enc_embed_dim"] = c
+        self.ray_dirs_encoder = _make_encoder(**g["ray_dirs_encoder_config"])
+        self.depth_encoder = _make_encoder(**g["depth_encoder_config"])
+        self.depth_scale_encoder = _make_encoder(**g["scale_encoder_config"])
+        self.cam_rot_encoder = _make_encoder(**g["cam_rot_encoder_config"])
+        self.cam_trans_encoder = _make_encoder(**g["cam_trans_encoder_config"])
+        self.cam_trans_scale_encoder = _make_encoder(**g["scale_encoder_config"])
+        self.fusion_norm_layer = fusion_norm_layer(c)
+        self.scale_token = nn.Parameter(torch.zeros(c))
+        torch.nn.init.trunc_normal_(self.scale_token, std=0.02)
+
+        info_sharing_config["module_args"]["input_embed_dim"] = c
+        info_sharing_config["module_args"]["custom_positional_encoding"] = None
+        self.info_sharing = U.MultiViewAlternatingAttentionTransformerIFR(**info_sharing_config["module_args"])
+        assert len(self.info_sharing.indices) == 2
+        self.use_encoder_features_for_dpt = True
+
+        d = self.info_sharing.dim
+        ph = pred_head_config
+        ph["feature_head"]["patch_size"] = self.encoder.patch_size
+        ph["feature_head"]["input_feature_dims"] = [c] + [d] * 3
+        ph["regressor_head"]["input_feature_dim"] = ph["feature_head"]["feature_dim"]
+        ph["pose_head"]["patch_size"] = self.encoder.patch_size
+        ph["pose_head"]["input_feature_dim"] = d
+        ph["scale_head"]["input_feature_dim"] = d
+        self.dpt_feature_head = U.DPTFeature(**ph["feature_head"])
+        self.dpt_regressor_head = U.DPTRegressionProcessor(**ph["regressor_head"])
+        self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)  # aliases, for key parity
+        self.pose_head = U.PoseHead(**ph["pose_head"])
+        self.scale_head = U.MLPHead(**ph["scale_head"])
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # ---------------------------------------------------------------------------------- geometric inputs
+    def _ref_view_poses(self, views, v, device, dtype, b, cam_mask):
+        q_non, t_non, q_ref, t_ref = [], [], [], []
+        for i in range(v):
+            m = cam_mask[i * b : (i + 1) * b]
+            if "camera_pose_quats" in views[i] and "camera_pose_trans" in views[i] and m.any():
+                q_non.append(views[i]["camera_pose_quats"][m])
+                t_non.append(views[i]["camera_pose_trans"][m])
+                q_ref.append(views[0]["camera_pose_quats"][m])
+                t_ref.append(views[0]["camera_pose_trans"][m])
+            else:
+                cam_mask[i * b : (i + 1) * b] = False
+        quats = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=dtype, device=device).repeat(b * v, 1)
+        trans = torch.zeros((b * v, 3), dtype=dtype, device=device)
+        if q_non:
+            q_rel, t_rel = G.relative_pose_2_to_1(torch.cat(q_ref), torch.cat(t_ref), torch.cat(q_non), torch.cat(t_non))
+            quats[cam_mask] = q_rel.to(dtype)
+            trans[cam_mask] = t_rel.to(dtype)
+        return quats, trans, cam_mask
+
+    def _fuse_ray_dirs(self, views, v, b, feats, mask):
+        _, _, h, w = views[0]["img"].shape
+        rays = []
+        for i in range(v):
+            m = mask[i * b : (i + 1) * b]
+            r = torch.zeros((b, h, w, 3), dtype=feats.dtype, device=feats.device)
+            if "ray_directions_cam" in views[i] and m.any():
+                r[m] = views[i]["ray_directions_cam"][m]
+            else:
+                mask[i * b : (i + 1) * b] = False
+            rays.append(r)
+        rays = torch.cat(rays, 0).permute(0, 3, 1, 2).contiguous()
+        f = self.ray_dirs_encoder(rays)
+        return feats + f * mask.view(-1, 1, 1, 1)
+
+    def _fuse_depths(self, views, v, b, feats, mask):
+        device = feats.device
+        _, _, h, w = views[0]["img"].shape
+        assert not (torch.rand(1) < self.geometric_input_config["sparse_depth_prob"]), "sparse depth is training-only"
+        depths, factors, metric = [], [], []
+        for i in range(v):
+            m = mask[i * b : (i + 1) * b]
+            d = torch.zeros((b, h, w, 1), dtype=feats.dtype, device=device)
+            f = torch.zeros((b,), dtype=feats.dtype, device=device)
+            ms = torch.zeros((b,), dtype=torch.bool, device=device)
+            if "depth_along_ray" in views[i] and m.any():
+                din = views[i]["depth_along_ray"][m]
+                if "is_metric_scale" in views[i]:
+                    mm = views[i]["is_metric_scale"][m].clone()
+                else:
+                    mm = torch.zeros(din.shape[0], dtype=torch.bool, device=device)
+                drop = torch.rand(mm.shape[0]) < self.geometric_input_config["depth_scale_norm_all_prob"]
+                if drop.any():
+                    mm[drop.to(device)] = False
+                ms[m] = mm
+                dn, fac = G.normalize_depth_nonzero(din)
+                d[m] = dn
+                f[m] = fac
+            else:
+                mask[i * b : (i + 1) * b] = False
+            depths.append(d)
+            factors.append(f)
+            metric.append(ms)
+        depths = G.log_of_norm(torch.cat(depths, 0)).permute(0, 3, 1, 2).contiguous()
+        dfeat = self.depth_encoder(depths) * mask.view(-1, 1, 1, 1)
+        logf = torch.log(torch.cat(factors, 0) + 1e-8)
+        sfeat = self.depth_scale_encoder(logf.unsqueeze(-1)) * mask.unsqueeze(-1)
+        sfeat = sfeat * torch.cat(metric, 0).unsqueeze(-1)
+        return feats + dfeat + sfeat.unsqueeze(-1).unsqueeze(-1)
+
+    def _fuse_cams(self, views, v, b, feats, quats, trans, cam_mask):
+        device = feats.device
+        qfeat = self.cam_rot_encoder(quats) * cam_mask.unsqueeze(-1)
+        metric = torch.zeros((b * v,), dtype=torch.bool, device=device)
+        for i in range(v):
+            if "is_metric_scale" in views[i]:
+                metric[i * b : (i + 1) * b] = views[i]["is_metric_scale"]
+        drop = torch.rand(b * v) < self.geometric_input_config["pose_scale_norm_all_prob"]
+        if drop.any():
+            metric[drop.to(device)] = False
+        t_bv = torch.stack(torch.split(trans, b, dim=0), dim=1)  # (B, V, 3)
+        t_scaled, factor = G.normalize_pose_translations(t_bv)
+        t_scaled = torch.cat(t_scaled.unbind(dim=1), dim=0)  # back to view-major (V*B, 3)
+        factor_all = factor.unsqueeze(-1).repeat(v, 1)
+        tfeat = self.cam_trans_encoder(t_scaled) * cam_mask.unsqueeze(-1)
+        sfeat = self.cam_trans_scale_encoder(torch.log(factor_all + 1e-8)) * cam_mask.unsqueeze(-1)
+        sfeat = sfeat * metric.unsqueeze(-1)
+        return feats + (qfeat + tfeat + sfeat).unsqueeze(-1).unsqueeze(-1)
+
+    def _encode_and_fuse(self, views, feats_list):
+        v = len(views)
+        b = views[0]["img"].shape[0]
+        device, dtype = feats_list[0].device, feats_list[0].dtype
+        feats = torch.cat(feats_list, dim=0)
+        g = self.geometric_input_config
+        overall = (torch.rand(b, device=device) < g["overall_prob"]).repeat(v)
+        per_sample = (torch.rand(b * v, device=device) < (1 - g["dropout_prob"])) & overall
+        ray_mask = (torch.rand(b, device=device) < g["ray_dirs_prob"]).repeat(v) & per_sample
+        depth_mask = (torch.rand(b, device=device) < g["depth_prob"]).repeat(v) & per_sample
+        cam_mask = (torch.rand(b, device=device) < g["cam_prob"]).repeat(v) & per_sample
+        quats, trans, cam_mask = self._ref_view_poses(views, v, device, dtype, b, cam_mask)
+        feats = self._fuse_ray_dirs(views, v, b, feats, ray_mask)
+        feats = self._fuse_depths(views, v, b, feats, depth_mask)
+        feats = self._fuse_cams(views, v, b, feats, quats, trans, cam_mask)
+        feats = self.fusion_norm_layer(feats.permute(0, 2, 3, 1).contiguous()).permute(0, 3, 1, 2).contiguous()
+        return feats.chunk(v, dim=0)
+
+    # ---------------------------------------------------------------------------------- forward
+    def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False, return_internals: bool = False):
+        b, _, h, w = views[0]["img"].shape
+        v = len(views)
+        norm_type = views[0]["data_norm_type"][0]
+        enc = self.encoder(torch.cat([vw["img"] for vw in views], dim=0), norm_type).chunk(v, dim=0)
+        fused = self._encode_and_fuse(views, enc)
+        token = self.scale_token.unsqueeze(0).unsqueeze(-1).repeat(b, 1, 1)
+        final_feats, final_extra, inter = self.info_sharing(list(fused), token)
+        dpt_in = [torch.cat(fused, 0), torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(final_feats, 0)]
+
+        n = dpt_in[0].shape[0]
+        chunk = 2 if memory_efficient_inference else n
+        dense_raw, pose_raw = [], []
+        for s in range(0, n, chunk):
+            sl = [x[s : s + chunk] for x in dpt_in]
+            dense_raw.append(self.dpt_regressor_head(self.dpt_feature_head(sl), (h, w)))
+            pose_raw.append(self.pose_head(sl[-1]))
+        dense_raw, pose_raw = torch.cat(dense_raw, 0), torch.cat(pose_raw, 0)
+        value, conf, mask, logits = U.dense_adaptor_raydirs_depth_conf_mask(dense_raw)
+        pose = U.pose_adaptor_trans_quats(pose_raw)
+        scale = U.scale_adaptor_exp(self.scale_head(final_extra)).squeeze(-1)  # (B, 1)
+
+        dense = value.permute(0, 2, 3, 1).contiguous()
+        rays, depth = dense.split([3, 1], dim=-1)
+        trans, quats = pose.split([3, 4], dim=-1)
+        pts = G.pointmap_from_rays_depth_pose(rays, depth, trans, quats)
+        pts_cam = rays * depth
+        conf = conf.permute(0, 2, 3, 1).squeeze(-1).contiguous()
+        nam = mask.permute(0, 2, 3, 1).squeeze(-1).contiguous() > 0.5
+        logits = logits.permute(0, 2, 3, 1).squeeze(-1).contiguous()
+        s4 = scale.unsqueeze(-1).unsqueeze(-1)
+        res = []
+        for i in range(v):
+            sl = slice(i * b, (i + 1) * b)
+            res.append(
+                {
+                    "pts3d": pts[sl] * s4, "pts3d_cam": pts_cam[sl] * s4, "ray_directions": rays[sl],
+                    "depth_along_ray": depth[sl] * s4, "cam_trans": trans[sl] * scale, "cam_quats": quats[sl],
+                    "metric_scaling_factor": scale, "conf": conf[sl], "non_ambiguous_mask": nam[sl],
+                    "non_ambiguous_mask_logits": logits[sl],
+                }
+            )
+        if return_internals:
+            internals = {"enc": torch.cat(enc, 0), "fused": dpt_in[0], "tap1": dpt_in[1], "tap2": dpt_in[2],
+                         "final": dpt_in[3], "scale_token_feat": final_extra, "dense_raw": dense_raw, "pose_raw": pose_raw}
+            return res, internals
+        return res
+
+    # ---------------------------------------------------------------------------------- infer
+    def _configure_geometric_input_config(self, use_calibration, use_depth, use_pose, use_depth_scale, use_pose_scale):
+        if not hasattr(self, "_original_geometric_config"):
+            self._original_geometric_config = dict(self.geometric_input_config)
+        if not (use_calibration or use_depth or use_pose):
+            upd = {"overall_prob": 0.0, "dropout_prob": 1.0, "ray_dirs_prob": 0.0, "depth_prob": 0.0, "cam_prob": 0.0,
+                   "sparse_depth_prob": 0.0, "depth_scale_norm_all_prob": 0.0, "pose_scale_norm_all_prob": 0.0}
+        else:
+            upd = {"overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0 if use_calibration else 0.0,
+                   "depth_prob": 1.0 if use_depth else 0.0, "cam_prob": 1.0 if use_pose else 0.0, "sparse_depth_prob": 0.0,
+                   "depth_scale_norm_all_prob": 0.0 if use_depth_scale else 1.0,
+                   "pose_scale_norm_all_prob": 0.0 if use_pose_scale else 1.0}
+        self.geometric_input_config.update(upd)
+
+    def _restore_original_geometric_input_config(self):
+        if hasattr(self, "_original_geometric_config"):
+            self.geometric_input_config.update(self._original_geometric_config)
+
+    @torch.inference_mode()
+    def infer(self, views, memory_efficient_inference=False, use_amp=True, amp_dtype="bf16", apply_mask=True,
+              mask_edges=True, edge_normal_threshold=5.0, edge_depth_threshold=0.03, apply_confidence_mask=False,
+              confidence_percentile=10, ignore_calibration_inputs=False, ignore_depth_inputs=False,
+              ignore_pose_inputs=False, ignore_depth_scale_inputs=False, ignore_pose_scale_inputs=False):
+        """The oracle always computes in fp32 (use_amp / amp_dtype accepted for signature parity)."""
+        views = I.validate_views(views)
+        for view in views:
+            for k in view:
+                if k not in ("instance", "idx", "true_shape", "data_norm_type"):
+                    view[k] = view[k].to(self.device)
+        processed = I.preprocess_views(views)
+        self._configure_geometric_input_config(not ignore_calibration_inputs, not ignore_depth_inputs,
+                                               not ignore_pose_inputs, not ignore_depth_scale_inputs,
+                                               not ignore_pose_scale_inputs)
+        try:
+            preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference)
+        finally:
+            self._restore_original_geometric_input_config()
+        return I.postprocess_outputs(preds, processed, apply_mask, mask_edges, edge_normal_threshold,
+                                     edge_depth_threshold, apply_confidence_mask, confidence_percentile)

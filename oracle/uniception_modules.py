@@ -1,0 +1,312 @@
+"""Oracle restatement of the `uniception` modules MapAnything instantiates (test infrastructure only).
+
+PARITY UNPINNED: `uniception` (pyproject.toml:26 of the reference, no version pin) is not vendored in
+/root/reference, not installed and not downloadable in this environment, and the reference ships no tests
+or golden vectors for it.  These modules therefore follow
+  * the call contracts visible in /root/reference/mapanything/models/mapanything/model.py
+    (:157-193 encoders, :299-301 info sharing, :374-388 heads, :478-483/:588 adaptors, :637-645, :812-825,
+    :972-1008, :1038-1129, :1302-1338, :1449-1469, :1532-1542),
+  * the hyper-parameters in /root/reference/configs/model/{encoder/dinov2_large, info_sharing/aat_ifr_24_layers,
+    pred_head/dpt_pose_scale, pred_head/adaptor_config/raydirs_depth_pose_confidence_mask_scale, task/default}.yaml,
+  * the vendored structural analogs /root/reference/mapanything/models/external/vggt/{models/aggregator.py:229-360,
+    layers/attention.py:46-76, heads/dpt_head.py:427-567},
+  * and the published UniCeption design as recorded in SURVEY.md Appendix A (A.2 - A.7), including the
+    state-dict sub-key names of A.7 so that a real checkpoint maps onto these modules.
+Every assumption that a real checkpoint could falsify is a constructor argument.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .vit import OracleBlock
+
+
+# ------------------------------------------------------------------------------------------------
+# A.2 geometric-input encoders
+# ------------------------------------------------------------------------------------------------
+class ResidualBlock(nn.Module):
+    """conv3x3 -> GELU -> conv3x3, + shortcut (identity or conv1x1), -> GELU."""
+
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.shortcut = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
+
+    def forward(self, x):
+        y = self.conv2(F.gelu(self.conv1(x)))
+        return F.gelu(y + self.shortcut(x))
+
+
+class DenseRepresentationEncoder(nn.Module):
+    """`dense_rep_encoder` (ray directions 3ch / depth 1ch): PixelUnshuffle(patch) -> conv3x3 -> 2 residual blocks ->
+    conv1x1 -> token LayerNorm; output (B, C, H/p, W/p)."""
+
+    def __init__(self, name: str, in_chans: int, enc_embed_dim: int, patch_size: int, apply_pe: bool = False,
+                 intermediate_dims: Sequence[int] = (588, 768, 1024), encoder_str: str = "dense_rep_encoder", **_):
+        super().__init__()
+        assert not apply_pe, "apply_pe is false for every MapAnything task config (configs/model/task/default.yaml)"
+        self.name, self.patch_size, self.enc_embed_dim = name, patch_size, enc_embed_dim
+        d0, d1, d2 = intermediate_dims
+        self.unshuffle = nn.PixelUnshuffle(patch_size)
+        self.conv_in = nn.Conv2d(in_chans * patch_size * patch_size, d0, 3, padding=1)
+        self.encoder = nn.Sequential(ResidualBlock(d0, d1), ResidualBlock(d1, d2), nn.Conv2d(d2, enc_embed_dim, 1))
+        self.norm_layer = nn.LayerNorm(enc_embed_dim, eps=1e-6)
+
+    def forward(self, data: torch.Tensor) -> torch.Tensor:
+        x = self.encoder(self.conv_in(self.unshuffle(data)))
+        b, c, h, w = x.shape
+        tok = self.norm_layer(x.flatten(2).transpose(1, 2))
+        return tok.transpose(1, 2).reshape(b, c, h, w).contiguous()
+
+
+class GlobalRepresentationEncoder(nn.Module):
+    """`global_rep_encoder` (quats 4 / trans 3 / log-scale 1): MLP in -> 128 -> 256 -> 512 -> C with GELU, LayerNorm."""
+
+    def __init__(self, name: str, in_chans: int, enc_embed_dim: int, intermediate_dims: Sequence[int] = (128, 256, 512),
+                 encoder_str: str = "global_rep_encoder", **_):
+        super().__init__()
+        self.name, self.enc_embed_dim = name, enc_embed_dim
+        dims = [in_chans, *intermediate_dims, enc_embed_dim]
+        layers: List[nn.Module] = []
+        for i in range(len(dims) - 1):
+            layers.append(nn.Linear(dims[i], dims[i + 1]))
+            if i < len(dims) - 2:
+                layers.append(nn.GELU())
+        self.encoder = nn.Sequential(*layers)
+        self.norm_layer = nn.LayerNorm(enc_embed_dim, eps=1e-6)
+
+    def forward(self, data: torch.Tensor) -> torch.Tensor:
+        return self.norm_layer(self.encoder(data))
+
+
+# ------------------------------------------------------------------------------------------------
+# A.3 alternating-attention multi-view transformer with intermediate feature return
+# ------------------------------------------------------------------------------------------------
+def sinusoid_table(n_rows: int, dim: int, base: float = 10000.0) -> torch.Tensor:
+    pos = torch.arange(n_rows, dtype=torch.float64)[:, None]
+    j = torch.arange(dim, dtype=torch.float64)[None, :]
+    angle = pos / torch.pow(torch.tensor(base, dtype=torch.float64), 2 * torch.div(j, 2, rounding_mode="floor") / dim)
+    table = torch.where((torch.arange(dim) % 2 == 0)[None, :], torch.sin(angle), torch.cos(angle))
+    return table.float()
+
+
+class MultiViewAlternatingAttentionTransformerIFR(nn.Module):
+    """Even blocks attend globally over all V*N + T tokens, odd blocks per view over N tokens (extra tokens bypass
+    them).  Returns the final normed features plus normed snapshots after the blocks in `indices`."""
+
+    def __init__(self, name: str, input_embed_dim: int, indices: Sequence[int] = (11, 17), norm_intermediate: bool = True,
+                 size: Optional[str] = None, depth: int = 24, dim: int = 768, num_heads: int = 12, mlp_ratio: float = 4.0,
+                 distinguish_ref_and_non_ref_views: bool = True, use_pe_for_non_reference_views: bool = False,
+                 max_num_views_for_pe: int = 1000, gradient_checkpointing: bool = False,
+                 custom_positional_encoding=None, **_):
+        super().__init__()
+        assert custom_positional_encoding is None and not use_pe_for_non_reference_views
+        self.name, self.dim, self.depth, self.num_heads = name, dim, depth, num_heads
+        self.indices = list(indices)
+        self.norm_intermediate = norm_intermediate
+        self.distinguish_ref_and_non_ref_views = distinguish_ref_and_non_ref_views
+        self.proj_embed = nn.Linear(input_embed_dim, dim) if input_embed_dim != dim else nn.Identity()
+        self.self_attention_blocks = nn.ModuleList(
+            [OracleBlock(dim, num_heads, mlp_ratio, layer_scale=False) for _ in range(depth)]
+        )
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+        # fixed (non-learned, non-persistent) view positional table; only row 0 (reference view) is used here
+        self.register_buffer("view_pos_table", sinusoid_table(max_num_views_for_pe, dim), persistent=False)
+
+    def forward(self, features: List[torch.Tensor], additional_input_tokens: Optional[torch.Tensor] = None):
+        """features: V x (B, C, h, w); additional_input_tokens: (B, C, T).
+        Returns (final_feats V x (B, D, h, w), final_extra (B, D, T), [ (feats list, extra) per index ])."""
+        v = len(features)
+        b, c, h, w = features[0].shape
+        n = h * w
+        x = torch.cat([f.flatten(2).transpose(1, 2) for f in features], dim=1)  # (B, V*N, C), view-major
+        t = 0
+        if additional_input_tokens is not None:
+            t = additional_input_tokens.shape[2]
+            x = torch.cat([x, additional_input_tokens.transpose(1, 2)], dim=1)
+        x = self.proj_embed(x)
+        if self.distinguish_ref_and_non_ref_views:
+            pe = self.view_pos_table[0].to(x.dtype).view(1, 1, -1)
+            x = torch.cat([x[:, :n] + pe, x[:, n:]], dim=1)
+
+        def snapshot(y):
+            y = self.norm(y)
+            feats = [y[:, i * n : (i + 1) * n].transpose(1, 2).reshape(b, self.dim, h, w).contiguous() for i in range(v)]
+            extra = y[:, v * n :].transpose(1, 2).contiguous() if t else None
+            return feats, extra
+
+        inter = []
+        for i, blk in enumerate(self.self_attention_blocks):
+            if i % 2 == 0:
+                x = blk(x)
+            else:
+                frames = blk(x[:, : v * n].reshape(b * v, n, self.dim)).reshape(b, v * n, self.dim)
+                x = torch.cat([frames, x[:, v * n :]], dim=1) if t else frames
+            if i in self.indices:
+                if self.norm_intermediate:
+                    inter.append(snapshot(x))
+                else:
+                    feats = [x[:, k * n : (k + 1) * n].transpose(1, 2).reshape(b, self.dim, h, w) for k in range(v)]
+                    inter.append((feats, x[:, v * n :].transpose(1, 2) if t else None))
+        final_feats, final_extra = snapshot(x)
+        return final_feats, final_extra, inter
+
+
+# ------------------------------------------------------------------------------------------------
+# A.4 DPT feature head + regression processor
+# ------------------------------------------------------------------------------------------------
+class ResidualConvUnit(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(ch, ch, 3, padding=1)
+        self.conv2 = nn.Conv2d(ch, ch, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv2(F.relu(self.conv1(F.relu(x)))) + x
+
+
+class FeatureFusionBlock(nn.Module):
+    def __init__(self, ch: int):
+        super().__init__()
+        self.resConfUnit1 = ResidualConvUnit(ch)
+        self.resConfUnit2 = ResidualConvUnit(ch)
+        self.out_conv = nn.Conv2d(ch, ch, 1)
+
+    def forward(self, x0, x1=None):
+        out = x0 if x1 is None else x0 + self.resConfUnit1(x1)
+        out = self.resConfUnit2(out)
+        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+        return self.out_conv(out)
+
+
+class _Scratch(nn.Module):
+    def __init__(self, layer_dims, feature_dim):
+        super().__init__()
+        self.layer_rn = nn.ModuleList([nn.Conv2d(d, feature_dim, 3, padding=1, bias=False) for d in layer_dims])
+        self.refinenet1 = FeatureFusionBlock(feature_dim)
+        self.refinenet2 = FeatureFusionBlock(feature_dim)
+        self.refinenet3 = FeatureFusionBlock(feature_dim)
+        self.refinenet4 = FeatureFusionBlock(feature_dim)
+
+
+class DPTFeature(nn.Module):
+    def __init__(self, patch_size: int, input_feature_dims: Sequence[int], feature_dim: int = 256,
+                 hooks: Sequence[int] = (0, 1, 2, 3), layer_dims: Sequence[int] = (96, 192, 384, 768), **_):
+        super().__init__()
+        assert patch_size in (14, 16)
+        self.hooks = list(hooks)
+        d, ld = list(input_feature_dims), list(layer_dims)
+        self.act_postprocess = nn.ModuleList(
+            [
+                nn.Sequential(nn.Conv2d(d[0], ld[0], 1), nn.ConvTranspose2d(ld[0], ld[0], 4, stride=4)),
+                nn.Sequential(nn.Conv2d(d[1], ld[1], 1), nn.ConvTranspose2d(ld[1], ld[1], 2, stride=2)),
+                nn.Sequential(nn.Conv2d(d[2], ld[2], 1)),
+                nn.Sequential(nn.Conv2d(d[3], ld[3], 1), nn.Conv2d(ld[3], ld[3], 3, stride=2, padding=1)),
+            ]
+        )
+        self.scratch = _Scratch(ld, feature_dim)
+
+    def forward(self, list_features: List[torch.Tensor]) -> torch.Tensor:
+        layers = [self.act_postprocess[i](list_features[hk]) for i, hk in enumerate(self.hooks)]
+        layers = [self.scratch.layer_rn[i](l) for i, l in enumerate(layers)]
+        p4 = self.scratch.refinenet4(layers[3])[:, :, : layers[2].shape[2], : layers[2].shape[3]]
+        p3 = self.scratch.refinenet3(p4, layers[2])
+        p2 = self.scratch.refinenet2(p3, layers[1])
+        return self.scratch.refinenet1(p2, layers[0])
+
+
+class DPTRegressionProcessor(nn.Module):
+    def __init__(self, input_feature_dim: int, output_dim: int, hidden_dims: Optional[Sequence[int]] = None, **_):
+        super().__init__()
+        hidden_dims = list(hidden_dims) if hidden_dims is not None else [input_feature_dim // 2, input_feature_dim // 2]
+        self.conv1 = nn.Conv2d(input_feature_dim, hidden_dims[0], 3, padding=1)
+        self.conv2 = nn.Sequential(
+            nn.Conv2d(hidden_dims[0], hidden_dims[1], 3, padding=1), nn.ReLU(), nn.Conv2d(hidden_dims[1], output_dim, 1)
+        )
+
+    def forward(self, x: torch.Tensor, target_output_shape: Tuple[int, int]) -> torch.Tensor:
+        x = self.conv1(x)
+        x = F.interpolate(x, size=tuple(target_output_shape), mode="bilinear", align_corners=True)
+        return self.conv2(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# A.6 pose head, scale head
+# ------------------------------------------------------------------------------------------------
+class ResConvBlock(nn.Module):
+    def __init__(self, cin: int, cout: int):
+        super().__init__()
+        self.head_skip = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
+        self.res_conv1 = nn.Conv2d(cin, cout, 1)
+        self.res_conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.res_conv3 = nn.Conv2d(cout, cout, 1)
+
+    def forward(self, x):
+        y = F.relu(self.res_conv1(x))
+        y = F.relu(self.res_conv2(y))
+        y = self.res_conv3(y)
+        return F.relu(self.head_skip(x) + y)
+
+
+class PoseHead(nn.Module):
+    def __init__(self, patch_size: int, input_feature_dim: int, num_resconv_block: int = 2,
+                 rot_representation_dim: int = 4, **_):
+        super().__init__()
+        c = input_feature_dim
+        self.res_conv = nn.ModuleList([ResConvBlock(c, c) for _ in range(num_resconv_block)])
+        self.more_mlps = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c), nn.ReLU())
+        self.fc_t = nn.Linear(c, 3)
+        self.fc_rot = nn.Linear(c, rot_representation_dim)
+
+    def forward(self, feat: torch.Tensor) -> torch.Tensor:
+        for blk in self.res_conv:
+            feat = blk(feat)
+        g = self.more_mlps(feat.mean(dim=(2, 3)))
+        return torch.cat([self.fc_t(g), self.fc_rot(g)], dim=-1)  # (n, 7): trans | quat
+
+
+class MLPHead(nn.Module):
+    def __init__(self, input_feature_dim: int, output_dim: int, num_mlp_layers: int = 2, hidden_dim: Optional[int] = None, **_):
+        super().__init__()
+        hidden_dim = hidden_dim or input_feature_dim
+        layers: List[nn.Module] = []
+        d = input_feature_dim
+        for _ in range(num_mlp_layers):
+            layers += [nn.Linear(d, hidden_dim), nn.ReLU()]
+            d = hidden_dim
+        layers.append(nn.Linear(d, output_dim))
+        self.mlp = nn.Sequential(*layers)
+
+    def forward(self, tokens: torch.Tensor) -> torch.Tensor:
+        """(B, D, T) -> (B, out, T)."""
+        return self.mlp(tokens.transpose(1, 2)).transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# A.5 / A.6 adaptors (parameter-free)
+# ------------------------------------------------------------------------------------------------
+def dense_adaptor_raydirs_depth_conf_mask(x: torch.Tensor):
+    """x (n, 6, H, W): [ray(3) | depth logit | confidence logit | mask logit] ->
+    value (n,4,H,W) = [unit ray | exp(depth)], confidence (n,1,H,W) = 1 + exp, mask = sigmoid(logits), logits."""
+    ray = x[:, 0:3]
+    ray = ray / ray.norm(dim=1, keepdim=True)
+    depth = torch.exp(x[:, 3:4]).clamp(min=0.0)
+    conf = 1.0 + torch.exp(x[:, 4:5])
+    logits = x[:, 5:6]
+    return torch.cat([ray, depth], dim=1), conf, torch.sigmoid(logits), logits
+
+
+def pose_adaptor_trans_quats(x: torch.Tensor) -> torch.Tensor:
+    """(n, 7) -> [trans (linear) | quats normalised]."""
+    q = x[:, 3:7]
+    return torch.cat([x[:, 0:3], q / q.norm(dim=1, keepdim=True)], dim=1)
+
+
+def scale_adaptor_exp(x: torch.Tensor) -> torch.Tensor:
+    """(B, 1, T) -> exp, clamped to [1e-8, inf)."""
+    return torch.exp(x).clamp(min=1e-8)

@@ -1,0 +1,172 @@
+"""CPU tests: the oracle restatement vs golden vectors produced by the REFERENCE's own code (oracle/make_golden.py).
+
+These pin the oracle for everything the reference ships source for: the DINOv2 ViT, the geometry math and the
+infer() pre/post-processing.  (The uniception modules have no pin -- see oracle/__init__.py.)
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = Path(__file__).parent / "golden"
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def geo():
+    return np.load(GOLD / "geometry.npz")
+
+
+def test_rays_and_intrinsics(geo):
+    from oracle import geometry as G
+
+    rays = G.rays_from_intrinsics(_t(geo["K"]), 56, 70)
+    assert torch.equal(rays, _t(geo["rays"]))
+    assert torch.allclose(G.intrinsics_from_rays(_t(geo["rays"])), _t(geo["K_rec"]), atol=1e-4)
+    # round trip recovers the true intrinsics (f=500 -> 499.9997)
+    assert torch.allclose(_t(geo["K_rec"]), _t(geo["K"]), atol=5e-2)
+    big = G.rays_from_intrinsics(torch.tensor([[[900.0, 0, 640.0], [0, 905.0, 400.0], [0, 0, 1]]]), 800, 1300)
+    assert torch.allclose(G.intrinsics_from_rays(big), _t(geo["K_rec_big"]), atol=1e-3)
+
+
+def test_quaternions(geo):
+    from oracle import geometry as G
+
+    q, q2, t1, t2 = (_t(geo[k]) for k in ("q", "q2", "t1", "t2"))
+    assert torch.equal(G.quat_to_rotmat(q), _t(geo["rotmat"]))
+    assert torch.equal(G.rotmat_to_quat(_t(geo["rotmat"])), _t(geo["q_back"]))
+    assert torch.equal(G.quat_inverse(q), _t(geo["q_inv"]))
+    assert torch.equal(G.quat_multiply(q, q2), _t(geo["q_mul"]))
+    qn, q2n = q / q.norm(dim=1, keepdim=True), q2 / q2.norm(dim=1, keepdim=True)
+    rq, rt = G.relative_pose_2_to_1(qn, t1, q2n, t2)
+    assert torch.allclose(rq, _t(geo["rel_q"]), atol=1e-6) and torch.allclose(rt, _t(geo["rel_t"]), atol=1e-6)
+    # known answers: identity, and q (x) q^-1 = identity
+    eye = G.quat_to_rotmat(torch.tensor([0.0, 0.0, 0.0, 1.0]))
+    assert torch.equal(eye, torch.eye(3))
+    ident = G.quat_multiply(qn, G.quat_inverse(qn))
+    assert torch.allclose(ident, torch.tensor([0.0, 0.0, 0.0, 1.0]).expand_as(ident), atol=1e-6)
+    # rotmat -> quat -> rotmat round trip, w >= 0
+    qb = G.rotmat_to_quat(G.quat_to_rotmat(q))
+    assert (qb[:, 3] >= 0).all()
+    assert torch.allclose(G.quat_to_rotmat(qb), G.quat_to_rotmat(q), atol=1e-5)
+
+
+def test_pointmap_and_normalisers(geo):
+    from oracle import geometry as G
+
+    pts = G.pointmap_from_rays_depth_pose(_t(geo["rays"]), _t(geo["depth"]), _t(geo["t1"])[:2], _t(geo["q"])[:2])
+    assert torch.allclose(pts, _t(geo["pts_world"]), atol=1e-6)
+    dn, df = G.normalize_depth_nonzero(_t(geo["depth_sparse"]))
+    assert torch.equal(dn, _t(geo["depth_norm"])) and torch.equal(df, _t(geo["depth_factor"]))
+    tn, tf = G.normalize_pose_translations(_t(geo["trans_views"]))
+    assert torch.equal(tn, _t(geo["trans_norm"])) and torch.equal(tf, _t(geo["trans_factor"]))
+    assert torch.equal(G.log_of_norm(_t(geo["depth_sparse"])), _t(geo["depth_log"]))
+    # empty (all-zero) depth: factor clips to 1e-8, output stays finite
+    z = torch.zeros(1, 4, 4, 1)
+    zn, zf = G.normalize_depth_nonzero(z)
+    assert torch.isfinite(zn).all() and zf.item() == pytest.approx(1e-8)
+
+
+def test_edge_masks_bit_exact(geo):
+    from oracle import geometry as G
+
+    n, nm = G.points_to_normals(geo["edge_pts"], geo["edge_mask"])
+    assert np.array_equal(nm, geo["edge_nmask"])
+    assert np.allclose(n, geo["edge_normals"], atol=1e-7)
+    assert np.array_equal(G.normals_edge(geo["edge_normals"], 5.0, geo["edge_nmask"]), geo["edge_ne"])
+    dz = geo["edge_pts"][..., 2]
+    assert np.array_equal(G.depth_edge(dz, 0.03, geo["edge_mask"]), geo["edge_de"])
+    assert geo["edge_ne"].sum() > 0 and geo["edge_de"].sum() > 0  # the fixture actually exercises both
+
+
+def test_preprocess_matches_reference():
+    from oracle import inference as I
+
+    g = np.load(GOLD / "inference.npz")
+    img, k, dz, pose, q, rays = (_t(g[n]) for n in ("pre_img", "pre_K", "pre_depth_z", "pre_pose", "pre_q", "pre_rays_in"))
+    views = [
+        {"img": img, "data_norm_type": ["dinov2"], "intrinsics": k, "depth_z": dz, "camera_poses": pose},
+        {"img": img, "data_norm_type": ["dinov2"], "ray_directions": rays,
+         "camera_poses": (q, torch.tensor([[0.5, 0.5, 0.5]])), "is_metric_scale": torch.tensor([False])},
+    ]
+    out = I.preprocess_views(I.validate_views(views))
+    for i in range(2):
+        for key in ("ray_directions_cam", "depth_along_ray", "camera_pose_quats", "camera_pose_trans", "is_metric_scale"):
+            name = f"pre{i}_{key}"
+            if name in g.files:
+                assert torch.allclose(out[i][key].float(), _t(g[name]).float(), atol=1e-6), name
+    assert "depth_along_ray" not in out[1] and "intrinsics" not in out[0] and "camera_poses" not in out[0]
+
+
+@pytest.mark.parametrize("tag,kw", [("default", {}), ("conf", {"apply_confidence_mask": True, "confidence_percentile": 25}),
+                                    ("noedge", {"mask_edges": False})])
+def test_postprocess_matches_reference(tag, kw):
+    from oracle import inference as I
+
+    g = np.load(GOLD / "inference.npz")
+    raw = {k[4:]: _t(g[k]) for k in g.files if k.startswith("raw_") and k != "raw_img"}
+    out = I.postprocess_outputs([raw], [{"img": _t(g["raw_img"]), "data_norm_type": ["dinov2"]}], **kw)[0]
+    keys = [k[len(f"post_{tag}_"):] for k in g.files if k.startswith(f"post_{tag}_")]
+    assert set(keys) == set(out.keys())
+    for key in keys:
+        ref = _t(g[f"post_{tag}_{key}"])
+        if ref.dtype == torch.bool:
+            assert torch.equal(out[key], ref), key
+        else:
+            assert torch.allclose(out[key], ref, atol=1e-3 if key == "intrinsics" else 1e-6), key
+    m = out["mask"]
+    assert 0 < m.sum() < m.numel()
+
+
+def test_validate_errors():
+    from oracle import inference as I
+
+    img = torch.zeros(1, 3, 14, 14)
+    base = {"img": img, "data_norm_type": ["dinov2"]}
+    with pytest.raises(ValueError, match="At least one view"):
+        I.validate_views([])
+    with pytest.raises(ValueError, match="invalid keys"):
+        I.validate_views([{**base, "bogus": 1}])
+    with pytest.raises(ValueError, match="missing required"):
+        I.validate_views([{"img": img}])
+    with pytest.raises(ValueError, match="conflicting"):
+        I.validate_views([{**base, "intrinsics": torch.eye(3)[None], "ray_directions": torch.zeros(1, 14, 14, 3)}])
+    with pytest.raises(ValueError, match="depth constraint"):
+        I.validate_views([{**base, "depth_z": torch.zeros(1, 14, 14, 1)}])
+    with pytest.raises(ValueError, match="reference view"):
+        I.validate_views([base, {**base, "camera_poses": torch.eye(4)[None]}])
+
+
+def test_small_vit_matches_reference_square_and_rect():
+    from oracle.vit import OracleDinoV2
+    from oracle.weights import synth_state_dict
+
+    g = np.load(GOLD / "vit.npz")
+    m = OracleDinoV2(img_size=70, embed_dim=128, depth=2, num_heads=2).eval()
+    m.load_state_dict(synth_state_dict(m, seed=3))
+    with torch.no_grad():
+        for tag in ("sq", "rect"):
+            out = m.forward_patch_tokens(_t(g[f"small_{tag}_in"]))
+            assert torch.allclose(out, _t(g[f"small_{tag}_out"]), atol=2e-5), tag
+
+
+def test_vit_large_matches_reference_518():
+    """Full ViT-L/14 at 518 px on one view (~5 s on 8 cores): checks sampled tokens against the reference run."""
+    from oracle.vit import OracleDinoV2
+    from oracle.weights import synth_state_dict
+
+    g = np.load(GOLD / "vit.npz")
+    m = OracleDinoV2().eval()
+    m.load_state_dict(synth_state_dict(m, seed=0))
+    gen = torch.Generator().manual_seed(1234)
+    img = torch.randn(1, 3, 518, 518, generator=gen)
+    with torch.no_grad():
+        out = m.forward_patch_tokens(img)
+    rows = g["vitl_rows"].tolist()
+    assert torch.allclose(out[0, rows], _t(g["vitl_tokens"]), atol=5e-4)
+    assert torch.allclose(out[0].mean(0), _t(g["vitl_col_mean"]), atol=5e-4)
+    assert out.abs().mean().item() == pytest.approx(float(g["vitl_mean_abs"]), rel=1e-3)
