@@ -52,6 +52,7 @@ int ma_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * Epilogue, applied per element in this order:
  *    v = acc + bias[n];  v = act(v);  v *= colscale[n];  v += residual[res_row, n]
  *    out[out_row, n] = v;  out_relu[out_row, n] = max(v, 0)   (optional second output, bf16)
+ * (`flags` can move the activation after the residual add, or take out_relu before it.)
  * Row mapping (token assembly without copy kernels): when rows_per_group_in > 0,
  *    out_row = (m / rows_per_group_in) * rows_per_group_out + row_offset_out + m % rows_per_group_in
  * else out_row = m.  res_row = m % residual_row_mod when residual_row_mod > 0, else out_row. */
@@ -71,8 +72,14 @@ typedef struct ma_gemm_epilogue {
   int32_t rows_per_group_in;
   int32_t rows_per_group_out;
   int32_t row_offset_out;
-  int32_t reserved;
+  int32_t flags; /* MA_GEMM_* bits */
 } ma_gemm_epilogue;
+
+/* act is applied after the residual add instead of before the column scale (ResConvBlock: relu(skip + y)). */
+#define MA_GEMM_ACT_AFTER_RESIDUAL 1
+/* out_relu receives relu(value BEFORE colscale/residual) instead of relu(final value) (DPT: the conv input
+ * relu(x1) and the fused skip x0 + x1 come out of one launch). */
+#define MA_GEMM_RELU_OUT_BEFORE_RESIDUAL 2
 
 /* block_n: 0 = choose automatically, else one of 64 / 128 / 256. */
 int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
@@ -92,6 +99,78 @@ int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, con
                      int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
                      int o_col0, int num_seqs, int num_heads, int q_len, int kv_len, int64_t q_seq_stride,
                      int64_t kv_seq_stride, float softmax_scale, void* stream);
+
+/* ---- HBM-bound stage kernels ------------------------------------------------------------------ */
+
+/* DINOv2 PatchEmbed im2col (reference dinov2/layers/patch_embed.py:65-87, Conv2d k=s=patch): fp32 NCHW image
+ * (n,3,H,W) -> bf16 [n*(H/p)*(W/p)][kpad], k = c*p*p + ky*p + kx, zero padded to kpad (multiple of 8). */
+int ma_patchify(const float* img, void* out, int n, int H, int W, int patch, int kpad, void* stream);
+
+/* nn.LayerNorm over the last dim (reference: every norm1/norm2/norm of dinov2/layers/block.py:93-119, the
+ * fusion_norm_layer model.py:1245-1254, the info-sharing norms).  in/out dtype are ma_dtype; the optional row
+ * remap row(r) = (r / rows_per_group) * group_stride + row_offset + r % rows_per_group (separately for in and
+ * out; rows_per_group = 0 -> identity) drops the cls token / skips the scale token without a copy. */
+int ma_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out,
+                 const float* gamma, const float* beta, int rows, int C, float eps, int rows_per_group,
+                 int64_t in_group_stride, int64_t in_row_offset, int64_t out_group_stride, int64_t out_row_offset,
+                 void* stream);
+
+/* dst[g*group_stride + row_offset][0:C] = a[0:C] + b[0:C] (b may be NULL) for g in [0, groups): cls token +
+ * pos_embed[0] (reference vision_transformer.py:252-253), scale token row (model.py:1524-1535). fp32. */
+int ma_set_rows(float* dst, int64_t ld, int groups, int64_t group_stride, int64_t row_offset, const float* a,
+                const float* b, int C, void* stream);
+
+/* im2col of a 3x3 / pad 1 / stride {1,2} convolution over NHWC bf16 (n,H,W,C): out[(i,yo,xo)][(ky*3+kx)*C + c].
+ * With ma_gemm_bf16 this replaces the cuDNN convs of the DPT / pose heads (reference model.py:1302-1338). */
+int ma_im2col3x3(const void* in, void* out, int n, int H, int W, int C, int stride, void* stream);
+
+/* ConvTranspose2d with kernel == stride == s as GEMM + this permutation: in[(i,y,x)][(ky*s+kx)*C + c] ->
+ * NHWC out[(i, y*s+ky, x*s+kx)][c]  (DPT act_postprocess). bf16. */
+int ma_pixel_shuffle(const void* in, void* out, int n, int h, int w, int C, int s, void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=True) over NHWC bf16.  (Hv,Wv) is the full output size that
+ * defines the scale; only the top-left (Ho,Wo) window is written (refinenet4 crop 38 -> 37). */
+int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win, int C, int Hv, int Wv, int Ho, int Wo,
+                              void* stream);
+
+/* AdaptiveAvgPool2d(1) over tokens: bf16 [n][T][C] -> bf16 [n][C] (pose head). */
+int ma_token_mean(const void* in, void* out, int n, int T, int C, void* stream);
+
+/* Fused dense adaptor + pose/scale adaptors + factored-geometry decode + output packaging (reference
+ * model.py:1683-1741, :1874-1907; geometry.py:855-907): raw [n*HW][ld_raw] fp32 = (ray xyz, depth logit,
+ * confidence logit, mask logit); pose_raw [n][7] = (t, q xyzw); scale_raw [1] (log metric scale).
+ * Writes pts3d, pts3d_cam, rays [n*HW][3]; depth, conf, logits [n*HW]; mask [n*HW] (1 byte bool);
+ * cam_trans [n][3] (scaled), cam_quats [n][4] (unit), scale_out [1]. */
+int ma_decode_dense(const float* raw, int ld_raw, const float* pose_raw, const float* scale_raw, int n, int HW,
+                    float* pts3d, float* pts3d_cam, float* rays, float* depth, float* conf, float* logits, uint8_t* mask,
+                    float* cam_trans, float* cam_quats, float* scale_out, void* stream);
+
+/* ---- infer() post-processing (reference mapanything/utils/inference.py:294-480, host numpy there) ---- */
+
+/* img_no_norm: clip(img * std + mean, 0, 1), (n,3,H,W) -> (n,H,W,3) fp32 (image.py:93-131). mean/std: 3 HOST floats. */
+int ma_denorm_image(const float* img, float* out, int n, int H, int W, const float* mean_host, const float* std_host,
+                    void* stream);
+
+/* Pinhole intrinsics (n,3,3) from unit ray directions (n,H,W,3) (geometry.py:304-447): 2x2 least squares over
+ * the sampled grid for <= 1 MP images, five-pixel closed form above. */
+int ma_intrinsics_from_rays(const float* rays, float* K, int n, int H, int W, void* stream);
+
+/* camera_poses (n,4,4) from quats (n,4, xyzw) and translations (n,3) (inference.py:364-379). */
+int ma_pose_matrices(const float* quats, const float* trans, float* out, int n, void* stream);
+
+/* Edge mask (inference.py:418-454 + geometry.py:1717-1780, :2031-2072, :2129-2188), float32-exact with numpy:
+ * mask_out = mask_in & ~(depth_edge & normal_edge).  depth_z is read with an element stride (pass pts3d_cam + 2,
+ * stride 3).  Workspaces per pixel: ws_normals 3 floats, ws_nmask 1 byte, ws_angle 1 float, ws_depth_edge 1 byte. */
+int ma_edge_mask(const float* pts3d, const float* depth_z, int depth_stride, const uint8_t* mask_in, uint8_t* mask_out,
+                 float* ws_normals, uint8_t* ws_nmask, float* ws_angle, uint8_t* ws_depth_edge, int n, int H, int W,
+                 float normal_tol_deg, float depth_rtol, void* stream);
+
+/* out[px, c] = in[px*in_stride + in_offset + c] * mask[px], c < width (inference.py:457-476). */
+int ma_apply_mask(const float* in, int in_stride, int in_offset, const uint8_t* mask, float* out, int64_t pixels, int width,
+                  void* stream);
+
+/* out = a & b over n bool bytes. */
+int ma_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,408 @@
+// HBM-bound kernels of the MapAnything hot path: coalesced, 16-byte vectorised, warp-primitive reductions.
+// Everything between the tensor-core kernels lives here so that no permute().contiguous(), torch.cat or
+// separate bias/activation pass is ever materialised (reference: model.py:1245-1259, :1549-1572, :1683-1741).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ma {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// patchify: (n,3,H,W) fp32 NCHW image -> [n*hp*wp][kpad] bf16 rows, k = c*p*p + ky*p + kx (the Conv2d weight
+// order of DINOv2's PatchEmbed, dinov2/layers/patch_embed.py:65-67), zero padded to kpad.
+// ----------------------------------------------------------------------------------------------
+__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int H, int W, int hp,
+                                int wp, int p, int kpad) {
+  const int patch = blockIdx.x;  // n*hp*wp
+  const int i = patch / (hp * wp);
+  const int rem = patch - i * hp * wp;
+  const int py = rem / wp, px = rem - py * wp;
+  const int kk = 3 * p * p;
+  for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+    float v = 0.f;
+    if (k < kk) {
+      const int c = k / (p * p);
+      const int r = k - c * p * p;
+      const int ky = r / p, kx = r - ky * p;
+      v = __ldg(img + (((size_t)i * 3 + c) * H + (py * p + ky)) * W + px * p + kx);
+    }
+    out[(size_t)patch * kpad + k] = __float2bfloat16(v);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps inside the sqrt, biased variance -- nn.LayerNorm), one warp per row.
+// Row remap on both sides lets one launch drop the cls token / skip the scale token / scatter view-major
+// rows into the info-sharing layout:   row(r) = (r / rpg) * group_stride + row_offset + r % rpg.
+// ----------------------------------------------------------------------------------------------
+struct LnParams {
+  const void* in;
+  void* out;
+  const float* gamma;
+  const float* beta;
+  int64_t ld_in, ld_out;
+  int rows, C;
+  int rpg;  // rows per group (0 = identity mapping)
+  int64_t in_group_stride, in_row_offset, out_group_stride, out_row_offset;
+  float eps;
+};
+
+template <typename TIn, typename TOut>
+__global__ void layernorm_kernel(const LnParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  int64_t rin = r, rout = r;
+  if (p.rpg > 0) {
+    const int g = r / p.rpg, o = r - g * p.rpg;
+    rin = (int64_t)g * p.in_group_stride + p.in_row_offset + o;
+    rout = (int64_t)g * p.out_group_stride + p.out_row_offset + o;
+  }
+  const TIn* x = static_cast<const TIn*>(p.in) + rin * p.ld_in;
+  TOut* y = static_cast<TOut*>(p.out) + rout * p.ld_out;
+  const int C = p.C;
+
+  auto load4 = [&](int c, float (&v)[4]) {
+    if constexpr (sizeof(TIn) == 4) {
+      float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + c);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+      uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(x) + c);
+      v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+    }
+  };
+
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float v[4];
+    load4(c, v);
+    s += (v[0] + v[1]) + (v[2] + v[3]);
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    float v[4];
+    load4(c, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float d = v[i] - mean;
+      ss = fmaf(d, d, ss);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / C + p.eps);
+  for (int c = lane * 4; c < C; c += 128) {
+    float v[4];
+    load4(c, v);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    const float o0 = (v[0] - mean) * rstd * g.x + b.x, o1 = (v[1] - mean) * rstd * g.y + b.y;
+    const float o2 = (v[2] - mean) * rstd * g.z + b.z, o3 = (v[3] - mean) * rstd * g.w + b.w;
+    if constexpr (sizeof(TOut) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + c) = make_float4(o0, o1, o2, o3);
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// set_rows: dst[g*group_stride + row_offset][:] = a[:] (+ b[:]), fp32.  (cls token + pos_embed[0]; scale token.)
+// ----------------------------------------------------------------------------------------------
+__global__ void set_rows_kernel(float* __restrict__ dst, int64_t ld, int64_t group_stride, int64_t row_offset,
+                                const float* __restrict__ a, const float* __restrict__ b, int C) {
+  float* d = dst + ((int64_t)blockIdx.x * group_stride + row_offset) * ld;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) d[c] = a[c] + (b ? b[c] : 0.f);
+}
+
+// ----------------------------------------------------------------------------------------------
+// im2col for 3x3 / pad 1 / stride s convolutions over NHWC bf16: out[(i,yo,xo)][tap*C + c], tap = ky*3+kx.
+// One thread moves 8 channels (16 B); consecutive threads walk channels then taps -> coalesced both ways.
+// ----------------------------------------------------------------------------------------------
+__global__ void im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int H,
+                                 int W, int C, int Ho, int Wo, int stride) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)n * Ho * Wo * 9 * c8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = static_cast<int>(idx % c8);
+    int64_t t = idx / c8;
+    const int tap = static_cast<int>(t % 9);
+    t /= 9;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const int i = static_cast<int>(t / Ho);
+    const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && x >= 0 && x < W)
+      v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)i * H + y) * W + x) * C) + cc);
+    reinterpret_cast<uint4*>(out)[idx] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// pixel_shuffle: GEMM output of a ConvTranspose2d with kernel == stride == s,
+//   in[(i,y,x)][(ky*s+kx)*C + c]  ->  out NHWC [(i, y*s+ky, x*s+kx)][c]       (bias already added by the GEMM)
+// ----------------------------------------------------------------------------------------------
+__global__ void pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int h,
+                                     int w, int C, int s) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)n * h * w * s * s * c8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = static_cast<int>(idx % c8);
+    int64_t t = idx / c8;
+    const int kk = static_cast<int>(t % (s * s));
+    t /= (s * s);
+    const int x = static_cast<int>(t % w);
+    t /= w;
+    const int y = static_cast<int>(t % h);
+    const int i = static_cast<int>(t / h);
+    const int ky = kk / s, kx = kk - ky * s;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in) + idx);
+    reinterpret_cast<uint4*>(out + (((size_t)i * h * s + (y * s + ky)) * (w * s) + (x * s + kx)) * C)[cc] = v;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=True, NHWC bf16.  The scale is defined by the VIRTUAL output size (Hv, Wv);
+// only the top-left (Ho, Wo) window is produced (refinenet4: 19 -> 38, cropped to 37).
+// ----------------------------------------------------------------------------------------------
+__global__ void bilinear_ac_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int Hin,
+                                   int Win, int C, int Hv, int Wv, int Ho, int Wo) {
+  const int c8 = C >> 3;
+  const int64_t total = (int64_t)n * Ho * Wo * c8;
+  const float sy = Hv > 1 ? (float)(Hin - 1) / (float)(Hv - 1) : 0.f;
+  const float sx = Wv > 1 ? (float)(Win - 1) / (float)(Wv - 1) : 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cc = static_cast<int>(idx % c8);
+    int64_t t = idx / c8;
+    const int xo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int yo = static_cast<int>(t % Ho);
+    const int i = static_cast<int>(t / Ho);
+    const float fy = yo * sy, fx = xo * sx;
+    const int y0 = min((int)fy, Hin - 1), x0 = min((int)fx, Win - 1);
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float wy = fy - y0, wx = fx - x0;
+    const __nv_bfloat16* base = in + (size_t)i * Hin * Win * C;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * Win + x0) * C) + cc);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * Win + x1) * C) + cc);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * Win + x0) * C) + cc);
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * Win + x1) * C) + cc);
+    const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t0 = bf16_lo(aa[j]) + wx * (bf16_lo(bb[j]) - bf16_lo(aa[j]));
+      const float b0 = bf16_lo(cw[j]) + wx * (bf16_lo(dd[j]) - bf16_lo(cw[j]));
+      const float t1 = bf16_hi(aa[j]) + wx * (bf16_hi(bb[j]) - bf16_hi(aa[j]));
+      const float b1 = bf16_hi(cw[j]) + wx * (bf16_hi(dd[j]) - bf16_hi(cw[j]));
+      o[j] = pack_bf16x2(t0 + wy * (b0 - t0), t1 + wy * (b1 - t1));
+    }
+    reinterpret_cast<uint4*>(out)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// token mean: [n][T][C] bf16 -> [n][C] bf16 (AdaptiveAvgPool2d(1) of the pose head).  grid (C/64, n), block 256.
+// ----------------------------------------------------------------------------------------------
+__global__ void token_mean_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int T, int C) {
+  __shared__ float red[8][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;  // 0..3
+  const __nv_bfloat16* base = in + (size_t)blockIdx.y * T * C;
+  float s = 0.f;
+  if (c < C)
+    for (int t = rl; t < T; t += 4) s += __bfloat162float(base[(size_t)t * C + c]);
+  red[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const float tot = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    out[(size_t)blockIdx.y * C + c] = __float2bfloat16(tot / T);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fused dense adaptor + factored-geometry decode + packaging (reference model.py:1683-1741, :1874-1907,
+// geometry.py:855-907, adaptor semantics SURVEY App. A.5/A.6):
+//   raw[pixel][0:3] ray (linear) -> /|ray| ; raw[3] -> depth = exp ; raw[4] -> conf = 1 + exp ; raw[5] -> mask logits
+//   pose_raw[view] = (t, q) -> q/|q| -> R ; scale = clamp(exp(scale_raw), 1e-8)
+//   pts3d_cam = ray*depth ; pts3d = R pts3d_cam + t ; metric scale on pts3d, pts3d_cam, depth, cam_trans.
+// ----------------------------------------------------------------------------------------------
+struct DecodeParams {
+  const float* raw;  // [n*HW][ld_raw]
+  int ld_raw;
+  const float* pose_raw;   // [n][7]
+  const float* scale_raw;  // [1]
+  float* pts3d;            // [n*HW][3]
+  float* pts3d_cam;        // [n*HW][3]
+  float* rays;             // [n*HW][3]
+  float* depth;            // [n*HW]
+  float* conf;             // [n*HW]
+  float* logits;           // [n*HW]
+  uint8_t* mask;           // [n*HW] (bool)
+  float* cam_trans;        // [n][3]
+  float* cam_quats;        // [n][4]
+  float* scale_out;        // [1]
+  int n, HW;
+};
+
+__global__ void decode_dense_kernel(const DecodeParams p) {
+  const int view = blockIdx.y;
+  const float* pr = p.pose_raw + view * 7;
+  const float scale = fmaxf(expf(p.scale_raw[0]), 1e-8f);
+  float qx = pr[3], qy = pr[4], qz = pr[5], qw = pr[6];
+  {
+    // pose adaptor: q / |q|  (then geometry.py:883 and :621 re-normalise; idempotent up to rounding)
+    const float inv = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx *= inv; qy *= inv; qz *= inv; qw *= inv;
+  }
+  const float tx = pr[0], ty = pr[1], tz = pr[2];
+  const float r00 = 1 - 2 * (qy * qy + qz * qz), r01 = 2 * (qx * qy - qw * qz), r02 = 2 * (qx * qz + qw * qy);
+  const float r10 = 2 * (qx * qy + qw * qz), r11 = 1 - 2 * (qx * qx + qz * qz), r12 = 2 * (qy * qz - qw * qx);
+  const float r20 = 2 * (qx * qz - qw * qy), r21 = 2 * (qy * qz + qw * qx), r22 = 1 - 2 * (qx * qx + qy * qy);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.cam_trans[view * 3 + 0] = tx * scale;
+    p.cam_trans[view * 3 + 1] = ty * scale;
+    p.cam_trans[view * 3 + 2] = tz * scale;
+    p.cam_quats[view * 4 + 0] = qx;
+    p.cam_quats[view * 4 + 1] = qy;
+    p.cam_quats[view * 4 + 2] = qz;
+    p.cam_quats[view * 4 + 3] = qw;
+    if (view == 0) p.scale_out[0] = scale;
+  }
+  for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < p.HW; px += gridDim.x * blockDim.x) {
+    const size_t g = (size_t)view * p.HW + px;
+    const float* r = p.raw + g * p.ld_raw;
+    float a[6];
+    if ((p.ld_raw & 3) == 0) {
+      const float4 v0 = *reinterpret_cast<const float4*>(r);
+      const float2 v1 = *reinterpret_cast<const float2*>(r + 4);
+      a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a[i] = r[i];
+    }
+    const float inv = 1.0f / sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const float dx = a[0] * inv, dy = a[1] * inv, dz = a[2] * inv;
+    const float depth = expf(a[3]);
+    const float cx = dx * depth, cy = dy * depth, cz = dz * depth;
+    const float wx = r00 * cx + r01 * cy + r02 * cz + tx;
+    const float wy = r10 * cx + r11 * cy + r12 * cz + ty;
+    const float wz = r20 * cx + r21 * cy + r22 * cz + tz;
+    p.rays[g * 3 + 0] = dx; p.rays[g * 3 + 1] = dy; p.rays[g * 3 + 2] = dz;
+    p.pts3d_cam[g * 3 + 0] = cx * scale; p.pts3d_cam[g * 3 + 1] = cy * scale; p.pts3d_cam[g * 3 + 2] = cz * scale;
+    p.pts3d[g * 3 + 0] = wx * scale; p.pts3d[g * 3 + 1] = wy * scale; p.pts3d[g * 3 + 2] = wz * scale;
+    p.depth[g] = depth * scale;
+    p.conf[g] = 1.0f + expf(a[4]);
+    p.logits[g] = a[5];
+    p.mask[g] = (1.0f / (1.0f + expf(-a[5]))) > 0.5f ? 1 : 0;
+  }
+}
+
+static inline int grid_for(int64_t total, int block, int max_blocks) {
+  int64_t g = (total + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" int ma_patchify(const float* img, void* out, int n, int H, int W, int patch, int kpad, void* stream) {
+  MA_REQUIRE(img && out && n > 0 && patch > 0 && H % patch == 0 && W % patch == 0 && kpad >= 3 * patch * patch && kpad % 8 == 0,
+             "ma_patchify: bad arguments (H=%d W=%d patch=%d kpad=%d)", H, W, patch, kpad);
+  const int hp = H / patch, wp = W / patch;
+  patchify_kernel<<<n * hp * wp, 128, 0, static_cast<cudaStream_t>(stream)>>>(img, static_cast<__nv_bfloat16*>(out), H, W,
+                                                                               hp, wp, patch, kpad);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out_dtype, int64_t ld_out,
+                            const float* gamma, const float* beta, int rows, int C, float eps, int rows_per_group,
+                            int64_t in_group_stride, int64_t in_row_offset, int64_t out_group_stride,
+                            int64_t out_row_offset, void* stream) {
+  MA_REQUIRE(in && out && gamma && beta && rows > 0 && C > 0 && C % 4 == 0, "ma_layernorm: bad arguments (rows=%d C=%d)", rows, C);
+  MA_REQUIRE(ld_in % 4 == 0 && ld_out % 4 == 0, "ma_layernorm: row strides must be multiples of 4 elements");
+  LnParams p{in, out, gamma, beta, ld_in, ld_out, rows, C, rows_per_group, in_group_stride, in_row_offset,
+             out_group_stride, out_row_offset, eps};
+  const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (in_dtype == MA_F32 && out_dtype == MA_BF16) layernorm_kernel<float, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
+  else if (in_dtype == MA_F32 && out_dtype == MA_F32) layernorm_kernel<float, float><<<grid, wpb * 32, 0, s>>>(p);
+  else if (in_dtype == MA_BF16 && out_dtype == MA_BF16) layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
+  else if (in_dtype == MA_BF16 && out_dtype == MA_F32) layernorm_kernel<__nv_bfloat16, float><<<grid, wpb * 32, 0, s>>>(p);
+  else MA_REQUIRE(false, "ma_layernorm: unsupported dtypes %d -> %d", in_dtype, out_dtype);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_set_rows(float* dst, int64_t ld, int groups, int64_t group_stride, int64_t row_offset, const float* a,
+                           const float* b, int C, void* stream) {
+  MA_REQUIRE(dst && a && groups > 0 && C > 0, "ma_set_rows: bad arguments");
+  set_rows_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, ld, group_stride, row_offset, a, b, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_im2col3x3(const void* in, void* out, int n, int H, int W, int C, int stride, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && C % 8 == 0 && (stride == 1 || stride == 2), "ma_im2col3x3: bad arguments (C=%d stride=%d)", C, stride);
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int64_t total = (int64_t)n * Ho * Wo * 9 * (C / 8);
+  im2col3x3_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, H, W, C, Ho, Wo, stride);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_pixel_shuffle(const void* in, void* out, int n, int h, int w, int C, int s, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && C % 8 == 0 && s > 0, "ma_pixel_shuffle: bad arguments");
+  const int64_t total = (int64_t)n * h * w * s * s * (C / 8);
+  pixel_shuffle_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, h, w, C, s);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win, int C, int Hv, int Wv, int Ho,
+                                         int Wo, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && C % 8 == 0 && Ho <= Hv && Wo <= Wv && Hin > 0 && Win > 0, "ma_bilinear_align_corners: bad arguments");
+  const int64_t total = (int64_t)n * Ho * Wo * (C / 8);
+  bilinear_ac_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, Hin, Win, C, Hv, Wv, Ho, Wo);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_token_mean(const void* in, void* out, int n, int T, int C, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && T > 0 && C > 0, "ma_token_mean: bad arguments");
+  dim3 grid((C + 63) / 64, n);
+  token_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                         static_cast<__nv_bfloat16*>(out), T, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_decode_dense(const float* raw, int ld_raw, const float* pose_raw, const float* scale_raw, int n, int HW,
+                               float* pts3d, float* pts3d_cam, float* rays, float* depth, float* conf, float* logits,
+                               uint8_t* mask, float* cam_trans, float* cam_quats, float* scale_out, void* stream) {
+  MA_REQUIRE(raw && pose_raw && scale_raw && pts3d && pts3d_cam && rays && depth && conf && logits && mask && cam_trans &&
+                 cam_quats && scale_out && n > 0 && HW > 0 && ld_raw >= 6,
+             "ma_decode_dense: bad arguments");
+  DecodeParams p{raw, ld_raw, pose_raw, scale_raw, pts3d, pts3d_cam, rays, depth, conf, logits, mask, cam_trans, cam_quats,
+                 scale_out, n, HW};
+  dim3 grid(grid_for(HW, 256, 1024), n);
+  decode_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}

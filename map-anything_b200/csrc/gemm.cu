@@ -54,12 +54,26 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     }
-    if (ep.act == MA_ACT_GELU) {
+    const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
+    const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
+    if (!act_late) {
+      if (ep.act == MA_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else if (ep.act == MA_ACT_RELU) {
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (ep.act == MA_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+    }
+    if (ep.out_relu && relu_early) {
+      uint4* o4 =
+          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
     }
     if (ep.colscale) {
       const float4* s4 = reinterpret_cast<const float4*>(ep.colscale + col0);
@@ -91,6 +105,15 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
         }
       }
     }
+    if (act_late) {
+      if (ep.act == MA_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (ep.act == MA_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+    }
     if (ep.out_dtype == MA_F32) {
       float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (size_t)out_row * ep.ldo + col0);
 #pragma unroll
@@ -102,7 +125,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
         o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
     }
-    if (ep.out_relu) {
+    if (ep.out_relu && !relu_early) {
       uint4* o4 =
           reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
 #pragma unroll
@@ -119,17 +142,27 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
       if (j >= nvalid) continue;
       const int n = col0 + j;
       float x = v[j];
+      const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
+      const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
       if (ep.bias) x += __ldg(ep.bias + n);
-      if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
-      else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
+      if (!act_late) {
+        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
+        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
+      }
+      if (ep.out_relu && relu_early)
+        static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
       if (ep.colscale) x *= __ldg(ep.colscale + n);
       if (ep.residual) {
         if (ep.residual_dtype == MA_F32) x += static_cast<const float*>(ep.residual)[(size_t)res_row * ep.ldr + n];
         else x += __bfloat162float(static_cast<const __nv_bfloat16*>(ep.residual)[(size_t)res_row * ep.ldr + n]);
       }
+      if (act_late) {
+        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
+        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
+      }
       if (ep.out_dtype == MA_F32) static_cast<float*>(ep.out)[(size_t)out_row * ep.ldo + n] = x;
       else static_cast<__nv_bfloat16*>(ep.out)[(size_t)out_row * ep.ldo + n] = __float2bfloat16(x);
-      if (ep.out_relu)
+      if (ep.out_relu && !relu_early)
         static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
     }
   }

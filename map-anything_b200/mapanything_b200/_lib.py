@@ -15,6 +15,7 @@ LIB_PATH = Path(os.environ.get("MAPANYTHING_B200_LIB", _HERE / "libmapanything_b
 MA_OK = 0
 MA_BF16, MA_F32 = 0, 1
 MA_ACT_NONE, MA_ACT_GELU, MA_ACT_RELU = 0, 1, 2
+MA_GEMM_ACT_AFTER_RESIDUAL, MA_GEMM_RELU_OUT_BEFORE_RESIDUAL = 1, 2
 
 
 class MapAnythingB200Error(RuntimeError):
@@ -38,7 +39,7 @@ class GemmEpilogue(C.Structure):
         ("rows_per_group_in", C.c_int32),
         ("rows_per_group_out", C.c_int32),
         ("row_offset_out", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -51,6 +52,20 @@ SIGNATURES = {
     "ma_gemm_bf16": (_i, [_p, _i64, _p, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _p]),
     "ma_attention_fwd": (_i, [_p, _i64, _i64, _i, _p, _i64, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i64,
                               _i64, _f, _p]),
+    "ma_patchify": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ma_layernorm": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i, _i, _f, _i, _i64, _i64, _i64, _i64, _p]),
+    "ma_set_rows": (_i, [_p, _i64, _i, _i64, _i64, _p, _p, _i, _p]),
+    "ma_im2col3x3": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ma_pixel_shuffle": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ma_bilinear_align_corners": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ma_token_mean": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_decode_dense": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ma_denorm_image": (_i, [_p, _p, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p]),
+    "ma_intrinsics_from_rays": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_pose_matrices": (_i, [_p, _p, _p, _i, _p]),
+    "ma_edge_mask": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
+    "ma_apply_mask": (_i, [_p, _i, _i, _p, _p, _i64, _i, _p]),
+    "ma_mask_and": (_i, [_p, _p, _p, _i64, _p]),
 }
 
 _lib = None

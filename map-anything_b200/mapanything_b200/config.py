@@ -1,0 +1,79 @@
+"""The reference's Hydra composition for the released model, as plain dicts (what `configs/model/mapanything.yaml` composes to).
+
+Mirrors /root/reference/configs/model/mapanything.yaml:1-18 with
+  encoder:      configs/model/encoder/dinov2_large.yaml
+  info_sharing: configs/model/info_sharing/aat_ifr_24_layers.yaml
+  pred_head:    configs/model/pred_head/dpt_pose_scale.yaml (+ adaptor_config/raydirs_depth_pose_confidence_mask_scale.yaml)
+  task:         configs/model/task/images_only.yaml (defaults: task/default.yaml)
+"""
+from __future__ import annotations
+
+import copy
+
+INF = float("inf")
+
+
+def mapanything_config(**overrides) -> dict:
+    cfg = {
+        "name": "mapanything",
+        "encoder_config": {
+            "encoder_str": "dinov2", "name": "dinov2_large", "data_norm_type": "dinov2", "size": "large",
+            "with_registers": False, "uses_torch_hub": True, "gradient_checkpointing": False,
+        },
+        "info_sharing_config": {
+            "model_type": "alternating_attention", "model_return_type": "intermediate_features",
+            "custom_positional_encoding": None,
+            "module_args": {
+                "name": "aat_24_layers_ifr", "indices": [11, 17], "norm_intermediate": True, "size": "24_layers",
+                "depth": 24, "distinguish_ref_and_non_ref_views": True, "gradient_checkpointing": False,
+            },
+        },
+        "pred_head_config": {
+            "type": "dpt+pose",
+            "feature_head": {"feature_dim": 256, "hooks": [0, 1, 2, 3], "checkpoint_gradient": False},
+            "regressor_head": {"output_dim": 6, "checkpoint_gradient": False},
+            "pose_head": {"num_resconv_block": 2, "rot_representation_dim": 4},
+            "scale_head": {"output_dim": 1},
+            "adaptor_type": "raydirs+depth+pose+confidence+mask",
+            "dpt_adaptor": {
+                "name": "raydirs+depth+pose+confidence+mask+scale", "ray_directions_mode": "linear",
+                "ray_directions_normalize_to_unit_sphere": True, "ray_directions_normalize_to_unit_image_plane": False,
+                "ray_directions_vmin": -INF, "ray_directions_vmax": INF, "ray_directions_clamp_min_of_z_dir": False,
+                "ray_directions_z_dir_min": -INF, "depth_mode": "exp", "depth_vmin": 0, "depth_vmax": INF,
+                "confidence_type": "exp", "confidence_vmin": 1, "confidence_vmax": INF,
+            },
+            "pose_adaptor": {
+                "name": "raydirs+depth+pose+confidence+mask+scale", "cam_trans_mode": "linear", "cam_trans_vmin": -INF,
+                "cam_trans_vmax": INF, "quaternions_mode": "linear", "quaternions_normalize": True,
+                "quaternions_vmin": -INF, "quaternions_vmax": INF,
+            },
+            "scale_adaptor": {"name": "raydirs+depth+pose+confidence+mask+scale", "mode": "exp", "vmin": 1e-08, "vmax": INF},
+            "gradient_checkpointing": False,
+        },
+        "geometric_input_config": {
+            "ray_dirs_encoder_config": {"name": "ray_dirs_encoder", "in_chans": 3, "encoder_str": "dense_rep_encoder", "apply_pe": False},
+            "depth_encoder_config": {"name": "depth_encoder", "in_chans": 1, "encoder_str": "dense_rep_encoder", "apply_pe": False},
+            "cam_rot_encoder_config": {"name": "cam_rot_quats_encoder", "in_chans": 4, "encoder_str": "global_rep_encoder"},
+            "cam_trans_encoder_config": {"name": "cam_trans_encoder", "in_chans": 3, "encoder_str": "global_rep_encoder"},
+            "scale_encoder_config": {"name": "scale_encoder", "in_chans": 1, "encoder_str": "global_rep_encoder"},
+            "overall_prob": 0, "dropout_prob": 1, "ray_dirs_prob": 0, "depth_prob": 0, "cam_prob": 0,
+            "sparse_depth_prob": 0, "sparsification_removal_percent": 0, "depth_scale_norm_all_prob": 0,
+            "pose_scale_norm_all_prob": 0,
+        },
+    }
+    cfg = copy.deepcopy(cfg)
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg
+
+
+def tiny_config(img_size: int = 70, enc_dim: int = 128, enc_depth: int = 2, enc_heads: int = 2, info_dim: int = 128,
+                info_heads: int = 2, info_depth: int = 4, indices=(1, 2)) -> dict:
+    """Same wiring at toy width/depth, for fast CPU tests of the host logic and of oracle-vs-CUDA parity."""
+    cfg = mapanything_config()
+    cfg["encoder_config"]["vit_kwargs"] = {
+        "img_size": img_size, "patch_size": 14, "embed_dim": enc_dim, "depth": enc_depth, "num_heads": enc_heads,
+    }
+    ma = cfg["info_sharing_config"]["module_args"]
+    ma.update({"depth": info_depth, "indices": list(indices), "dim": info_dim, "num_heads": info_heads})
+    return cfg

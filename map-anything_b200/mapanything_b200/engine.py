@@ -1,0 +1,347 @@
+"""Execution engine: packs the parameter tree into kernel-ready device buffers and drives the CUDA kernels.
+
+Data layout in HBM (B200-first, no NCHW anywhere inside):
+  * activations are TOKEN-MAJOR / NHWC: row = (view, y, x), channels contiguous -- the ViT token layout, the
+    GEMM row-major A operand, and the im2col-free layout of the DPT convolutions are the same thing, so the
+    reference's permute().contiguous() and torch.cat copies (model.py:1245-1259, :1549-1572) never happen;
+  * the residual streams of both transformers are fp32 (what the reference's bf16 autocast keeps them in),
+    every GEMM/attention operand is bf16, accumulation is fp32 in TMEM;
+  * weights are packed once: Linear/conv1x1 as [N][K] bf16, conv3x3 as [Cout][(ky,kx),Cin],
+    ConvTranspose(k=s) as [(ky,kx),Cout][Cin]; biases / LayerNorm / LayerScale vectors stay fp32.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+class Lin:
+    """Packed y = x W^T + b."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], kpad: int = 0):
+        w2 = w.detach().reshape(w.shape[0], -1)
+        if kpad and kpad > w2.shape[1]:
+            w2 = torch.cat([w2, w2.new_zeros(w2.shape[0], kpad - w2.shape[1])], dim=1)
+        self.w = _bf16(w2)
+        self.b = _f32(b) if b is not None else None
+        self.n, self.k = self.w.shape
+
+
+def _conv3x3(conv: nn.Conv2d) -> Lin:
+    return Lin(conv.weight.detach().permute(0, 2, 3, 1), conv.bias)  # [Cout][ky][kx][Cin]
+
+
+def _conv1x1(conv: nn.Conv2d) -> Lin:
+    return Lin(conv.weight, conv.bias)
+
+
+def _convT(conv: nn.ConvTranspose2d) -> Lin:
+    cin, cout, k, _ = conv.weight.shape
+    w = conv.weight.detach().permute(2, 3, 1, 0).reshape(k * k * cout, cin)  # [(ky,kx,co)][ci]
+    b = conv.bias.detach().repeat(k * k) if conv.bias is not None else None
+    return Lin(w, b)
+
+
+class BlockW:
+    def __init__(self, blk):
+        self.n1w, self.n1b = _f32(blk.norm1.weight), _f32(blk.norm1.bias)
+        self.n2w, self.n2b = _f32(blk.norm2.weight), _f32(blk.norm2.bias)
+        self.qkv = Lin(blk.attn.qkv.weight, blk.attn.qkv.bias)
+        self.proj = Lin(blk.attn.proj.weight, blk.attn.proj.bias)
+        self.fc1 = Lin(blk.mlp.fc1.weight, blk.mlp.fc1.bias)
+        self.fc2 = Lin(blk.mlp.fc2.weight, blk.mlp.fc2.bias)
+        self.ls1 = _f32(blk.ls1.gamma) if hasattr(blk.ls1, "gamma") else None
+        self.ls2 = _f32(blk.ls2.gamma) if hasattr(blk.ls2, "gamma") else None
+
+
+class Engine:
+    """Owns the packed weights of one MapAnything module on one CUDA device."""
+
+    def __init__(self, model: nn.Module):
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("mapanything_b200 has no CPU path: move the module to a CUDA (sm_100a) device first")
+        enc = model.encoder.model
+        self.patch = enc.patch_size
+        self.C = enc.embed_dim
+        self.enc_heads = enc.num_heads
+        self.kpad = (3 * self.patch * self.patch + 63) // 64 * 64
+        self.patch_embed = Lin(enc.patch_embed.proj.weight, enc.patch_embed.proj.bias, kpad=self.kpad)
+        self.cls = _f32(enc.cls_token.reshape(-1))
+        self.pos_embed_param = enc.pos_embed.detach()
+        self.interp_offset = enc.interpolate_offset
+        self._pos_cache: Dict = {}
+        self.enc_blocks = [BlockW(b) for b in enc.blocks]
+        self.enc_nw, self.enc_nb = _f32(enc.norm.weight), _f32(enc.norm.bias)
+        self.fus_w, self.fus_b = _f32(model.fusion_norm_layer.weight), _f32(model.fusion_norm_layer.bias)
+        self.fus_eps = float(model.fusion_norm_layer.eps)
+
+        isx = model.info_sharing
+        self.D, self.is_heads, self.indices = isx.dim, isx.num_heads, list(isx.indices)
+        self.norm_intermediate = isx.norm_intermediate
+        if isinstance(isx.proj_embed, nn.Linear):
+            self.proj_embed = Lin(isx.proj_embed.weight, isx.proj_embed.bias)
+        else:  # identity projection when dims match: expressed as an identity GEMM to keep one code path
+            self.proj_embed = Lin(torch.eye(self.D, device=self.device), None)
+        self.is_blocks = [BlockW(b) for b in isx.self_attention_blocks]
+        self.is_nw, self.is_nb = _f32(isx.norm.weight), _f32(isx.norm.bias)
+        self.use_ref_pe = isx.distinguish_ref_and_non_ref_views
+        # sinusoid row 0 (position 0): sin(0)=0 on even channels, cos(0)=1 on odd channels
+        pe0 = torch.zeros(1, self.D, device=self.device)
+        pe0[0, 1::2] = 1.0
+        self.pe0 = pe0
+        # projected scale token is input independent: computed once with our own GEMM
+        tok = _bf16(model.scale_token.reshape(1, -1))
+        self.scale_tok_proj = torch.empty(1, self.D, device=self.device, dtype=torch.float32)
+        ops.gemm(tok, self.proj_embed.w, self.scale_tok_proj, bias=self.proj_embed.b)
+
+        dpt = model.dpt_feature_head
+        ap = dpt.act_postprocess
+        self.feat = dpt.feature_dim
+        self.ap0a, self.ap0b = _conv1x1(ap[0][0]), _convT(ap[0][1])
+        self.ap1a, self.ap1b = _conv1x1(ap[1][0]), _convT(ap[1][1])
+        self.ap2a = _conv1x1(ap[2][0])
+        self.ap3a, self.ap3b = _conv1x1(ap[3][0]), _conv3x3(ap[3][1])
+        self.ap0_s, self.ap1_s = ap[0][1].stride[0], ap[1][1].stride[0]
+        self.layer_rn = [_conv3x3(c) for c in dpt.scratch.layer_rn]
+        self.refine = []
+        for name in ("refinenet1", "refinenet2", "refinenet3", "refinenet4"):
+            r = getattr(dpt.scratch, name)
+            self.refine.append({
+                "r1c1": _conv3x3(r.resConfUnit1.conv1), "r1c2": _conv3x3(r.resConfUnit1.conv2),
+                "r2c1": _conv3x3(r.resConfUnit2.conv1), "r2c2": _conv3x3(r.resConfUnit2.conv2),
+                "out": _conv1x1(r.out_conv),
+            })
+        reg = model.dpt_regressor_head
+        self.reg1, self.reg2, self.reg3 = _conv3x3(reg.conv1), _conv3x3(reg.conv2[0]), _conv1x1(reg.conv2[2])
+
+        ph = model.pose_head
+        self.pose_blocks = []
+        for rb in ph.res_conv:
+            if not isinstance(rb.head_skip, nn.Identity):
+                raise ValueError("pose head with a projecting skip is not part of the released config")
+            self.pose_blocks.append((_conv1x1(rb.res_conv1), _conv3x3(rb.res_conv2), _conv1x1(rb.res_conv3)))
+        self.pose_mlp = [Lin(ph.more_mlps[0].weight, ph.more_mlps[0].bias), Lin(ph.more_mlps[2].weight, ph.more_mlps[2].bias)]
+        self.pose_out = Lin(torch.cat([ph.fc_t.weight, ph.fc_rot.weight], 0), torch.cat([ph.fc_t.bias, ph.fc_rot.bias], 0))
+        self.scale_mlp = [Lin(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
+        self.dpt_chunk = 4  # views per DPT pass (bounds the im2col scratch: ~0.62 GB per view at 518 px)
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _empty(self, *shape, dtype=torch.bfloat16):
+        return torch.empty(*shape, device=self.device, dtype=dtype)
+
+    def _lin(self, x, lin: Lin, out=None, *, act=MA_ACT_NONE, out_dtype=torch.bfloat16, **kw):
+        if out is None:
+            out = self._empty(x.shape[0], lin.n, dtype=out_dtype)
+        return ops.gemm(x, lin.w, out, bias=lin.b, act=act, **kw)
+
+    def _conv3(self, x, lin: Lin, stride=1, *, act=MA_ACT_NONE, **kw):
+        """x NHWC bf16 (n,H,W,C) -> (n,Ho,Wo,N) via explicit im2col + tcgen05 GEMM."""
+        n, H, W, C = x.shape
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        col = self._empty(n * Ho * Wo, 9 * C)
+        ops.im2col3x3(x, col, stride)
+        out = self._empty(n * Ho * Wo, lin.n)
+        ops.gemm(col, lin.w, out, bias=lin.b, act=act, **kw)
+        return out.view(n, Ho, Wo, lin.n)
+
+    def _pos_embed(self, hp: int, wp: int, H: int, W: int) -> torch.Tensor:
+        """pos_embed (1+hp*wp, C) fp32 for this resolution.  Interpolating the learned table for a non-native /
+        non-square input (reference vision_transformer.py:208-242) is WEIGHT preparation: it is input independent,
+        done once per resolution with torch's bicubic resampler and cached."""
+        key = (hp, wp)
+        if key in self._pos_cache:
+            return self._pos_cache[key]
+        pe = self.pos_embed_param.float()
+        n0 = pe.shape[1] - 1
+        if hp * wp == n0 and H == W:
+            out = pe[0].contiguous()
+        else:
+            m = int(math.sqrt(n0))
+            # the reference passes (w, h) = (x.shape[2], x.shape[3]) = (H, W): first grid axis follows image rows
+            kw = {}
+            if self.interp_offset:
+                kw["scale_factor"] = (float(hp + self.interp_offset) / m, float(wp + self.interp_offset) / m)
+            else:
+                kw["size"] = (hp, wp)
+            grid = torch.nn.functional.interpolate(pe[:, 1:].reshape(1, m, m, -1).permute(0, 3, 1, 2), mode="bicubic",
+                                                   antialias=False, **kw)
+            assert grid.shape[-2:] == (hp, wp)
+            out = torch.cat([pe[0, :1], grid.permute(0, 2, 3, 1).reshape(hp * wp, -1)], 0).contiguous()
+        self._pos_cache[key] = out
+        return out
+
+    def _block(self, x, bw: BlockW, rows: int, heads: int, num_seqs: int, seq_len: int, seq_stride: int):
+        """One pre-LN transformer block, in place on the fp32 residual stream x[:rows]."""
+        dim = x.shape[1]
+        xr = x[:rows]
+        h = self._empty(rows, dim)
+        ops.layernorm(xr, h, bw.n1w, bw.n1b)
+        qkv = self._lin(h, bw.qkv)
+        a = self._empty(rows, dim)
+        ops.attention(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, num_heads=heads, num_seqs=num_seqs,
+                      q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride)
+        ops.gemm(a, bw.proj.w, xr, bias=bw.proj.b, colscale=bw.ls1, residual=xr)
+        ops.layernorm(xr, h, bw.n2w, bw.n2b)
+        f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
+        ops.gemm(f, bw.fc2.w, xr, bias=bw.fc2.b, colscale=bw.ls2, residual=xr)
+
+    # ------------------------------------------------------------------------------------------ stage 1
+    def encode(self, imgs: torch.Tensor) -> torch.Tensor:
+        """(n,3,H,W) fp32 normalised images -> DINOv2 x_norm_patchtokens, fp32 [n*N][C] token-major."""
+        n, _, H, W = imgs.shape
+        p = self.patch
+        hp, wp = H // p, W // p
+        N = hp * wp
+        pos = self._pos_embed(hp, wp, H, W)
+        a = self._empty(n * N, self.kpad)
+        ops.patchify(imgs.contiguous(), a, p)
+        x = self._empty(n * (N + 1), self.C, dtype=torch.float32)
+        ops.gemm(a, self.patch_embed.w, x, bias=self.patch_embed.b, residual=pos[1:], residual_row_mod=N,
+                 rows_per_group_in=N, rows_per_group_out=N + 1, row_offset_out=1)
+        ops.set_rows(x, self.cls, pos[0].contiguous(), groups=n, group_stride=N + 1, row_offset=0)
+        for bw in self.enc_blocks:
+            self._block(x, bw, n * (N + 1), self.enc_heads, n, N + 1, N + 1)
+        feat = self._empty(n * N, self.C, dtype=torch.float32)
+        ops.layernorm(x, feat, self.enc_nw, self.enc_nb, rows=n * N, rows_per_group=N, in_group_stride=N + 1,
+                      in_row_offset=1, out_group_stride=N, out_row_offset=0)
+        return feat
+
+    # ------------------------------------------------------------------------------------------ stage 2
+    def fuse_norm(self, feat: torch.Tensor) -> torch.Tensor:
+        """fusion LayerNorm over channels (model.py:1245-1254): fp32 [n*N][C] -> bf16 (DPT tap 0 and proj_embed input)."""
+        out = self._empty(*feat.shape)
+        ops.layernorm(feat, out, self.fus_w, self.fus_b, eps=self.fus_eps)
+        return out
+
+    def info_sharing(self, fused: torch.Tensor, V: int, N: int):
+        """fused bf16 [V*N][C] -> taps (bf16 [V*N][D]) after blocks `indices`, final (bf16 [V*N][D]), scale-token feature."""
+        D, T = self.D, V * N + 1
+        y = self._empty(T, D, dtype=torch.float32)
+        if self.use_ref_pe:
+            ops.gemm(fused[:N], self.proj_embed.w, y[:N], bias=self.proj_embed.b, residual=self.pe0, residual_row_mod=1)
+            if V > 1:
+                ops.gemm(fused[N:], self.proj_embed.w, y[N:V * N], bias=self.proj_embed.b)
+        else:
+            ops.gemm(fused, self.proj_embed.w, y[:V * N], bias=self.proj_embed.b)
+        ops.set_rows(y, self.scale_tok_proj.reshape(-1), None, groups=1, group_stride=0, row_offset=V * N)
+        taps: List[torch.Tensor] = []
+        for i, bw in enumerate(self.is_blocks):
+            if i % 2 == 0:
+                self._block(y, bw, T, self.is_heads, 1, T, T)  # global: every token of every view + scale token
+            else:
+                self._block(y, bw, V * N, self.is_heads, V, N, N)  # frame: per view, scale token bypasses the block
+            if i in self.indices:
+                tap = self._empty(V * N, D)
+                if self.norm_intermediate:
+                    ops.layernorm(y, tap, self.is_nw, self.is_nb, rows=V * N)
+                else:
+                    raise NotImplementedError("norm_intermediate=False is not part of the released config")
+                taps.append(tap)
+        final = self._empty(T, D)
+        ops.layernorm(y, final, self.is_nw, self.is_nb)
+        return taps, final[:V * N], final[V * N:]
+
+    # ------------------------------------------------------------------------------------------ stage 3
+    def _rcu(self, x_relu, x_skip, r, c1: str, c2: str, *, want_relu: bool):
+        """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + skip; returns (out, relu(out) or None)."""
+        t = self._conv3(x_relu, r[c1], act=MA_ACT_RELU)
+        n, H, W, _ = t.shape
+        col = self._empty(n * H * W, 9 * t.shape[3])
+        ops.im2col3x3(t, col, 1)
+        out = self._empty(n * H * W, r[c2].n)
+        out_relu = self._empty(n * H * W, r[c2].n) if want_relu else None
+        ops.gemm(col, r[c2].w, out, bias=r[c2].b, residual=x_skip.reshape(n * H * W, -1), out_relu=out_relu)
+        return out.view(n, H, W, -1), (out_relu.view(n, H, W, -1) if want_relu else None)
+
+    def _fusion(self, r, x0, lay_in, rn: Lin, up_virtual, up_out):
+        """FeatureFusionBlock on NHWC bf16. x0: previous path (or None for refinenet4); lay_in: act_postprocess output."""
+        n, H, W, _ = lay_in.shape
+        M = n * H * W
+        col = self._empty(M, 9 * lay_in.shape[3])
+        ops.im2col3x3(lay_in, col, 1)
+        lay = self._empty(M, rn.n)
+        lay_relu = self._empty(M, rn.n)
+        if x0 is None:
+            ops.gemm(col, rn.w, lay, out_relu=lay_relu)  # l4 and relu(l4)
+            y, y_relu = lay.view(n, H, W, -1), lay_relu.view(n, H, W, -1)
+        else:
+            # one launch: lay = x0 + layer_rn(x)  (skip for RCU1's output),  lay_relu = relu(layer_rn(x))  (RCU1 input)
+            ops.gemm(col, rn.w, lay, residual=x0.reshape(M, -1), out_relu=lay_relu, relu_out_before_residual=True)
+            y, y_relu = self._rcu(lay_relu.view(n, H, W, -1), lay.view(n, H, W, -1), r, "r1c1", "r1c2", want_relu=True)
+        z, _ = self._rcu(y_relu, y, r, "r2c1", "r2c2", want_relu=False)
+        # out_conv (1x1) commutes with the bilinear upsample (both linear, interpolation weights sum to 1):
+        # apply it at the low resolution (4x fewer FLOPs), then upsample.
+        o = self._lin(z.reshape(M, -1), r["out"]).view(n, H, W, -1)
+        up = self._empty(n, up_out[0], up_out[1], o.shape[3])
+        ops.bilinear_ac(o, up, virtual_hw=up_virtual)
+        return up
+
+    def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int):
+        """taps4: 4 x bf16 [V*N][C_i] -> raw dense fp32 [V*H*W][8] (6 used), pose_raw fp32 [V][7]."""
+        N = hp * wp
+        raw = self._empty(V * H * W, 8, dtype=torch.float32)
+        pose_raw = self._empty(V, 7, dtype=torch.float32)
+        for s in range(0, V, self.dpt_chunk):
+            n = min(self.dpt_chunk, V - s)
+            t = [x[s * N:(s + n) * N] for x in taps4]
+            r1, r2, r3, r4 = self.refine
+            # act_postprocess
+            a0 = self._lin(self._lin(t[0], self.ap0a), self.ap0b)
+            s0 = self.ap0_s
+            l0 = self._empty(n, hp * s0, wp * s0, self.ap0a.n)
+            ops.pixel_shuffle(a0, l0, n, hp, wp, self.ap0a.n, s0)
+            a1 = self._lin(self._lin(t[1], self.ap1a), self.ap1b)
+            s1 = self.ap1_s
+            l1 = self._empty(n, hp * s1, wp * s1, self.ap1a.n)
+            ops.pixel_shuffle(a1, l1, n, hp, wp, self.ap1a.n, s1)
+            l2 = self._lin(t[2], self.ap2a).view(n, hp, wp, -1)
+            l3 = self._conv3(self._lin(t[3], self.ap3a).view(n, hp, wp, -1), self.ap3b, stride=2)
+            h3, w3 = l3.shape[1], l3.shape[2]
+            # refinenets, bottom-up.  refinenet4 output is upsampled x2 then cropped to layer 3's grid.
+            p4 = self._fusion(r4, None, l3, self.layer_rn[3], (2 * h3, 2 * w3), (hp, wp))
+            p3 = self._fusion(r3, p4, l2, self.layer_rn[2], (2 * hp, 2 * wp), (2 * hp, 2 * wp))
+            p2 = self._fusion(r2, p3, l1, self.layer_rn[1], (4 * hp, 4 * wp), (4 * hp, 4 * wp))
+            p1 = self._fusion(r1, p2, l0, self.layer_rn[0], (8 * hp, 8 * wp), (8 * hp, 8 * wp))
+            # regressor: conv3x3 -> bilinear to the image size -> conv3x3 + ReLU -> conv1x1 (fp32 out)
+            g1 = self._conv3(p1, self.reg1)
+            g1u = self._empty(n, H, W, g1.shape[3])
+            ops.bilinear_ac(g1, g1u)
+            g2 = self._conv3(g1u, self.reg2, act=MA_ACT_RELU)
+            ops.gemm(g2.reshape(n * H * W, -1), self.reg3.w, raw[s * H * W:(s + n) * H * W, :self.reg3.n], bias=self.reg3.b)
+            # pose head on the final info-sharing features
+            x = t[3]
+            for c1, c2, c3 in self.pose_blocks:
+                u = self._lin(x, c1, act=MA_ACT_RELU).view(n, hp, wp, -1)
+                u = self._conv3(u, c2, act=MA_ACT_RELU).reshape(n * N, -1)
+                xn = self._empty(n * N, c3.n)
+                ops.gemm(u, c3.w, xn, bias=c3.b, residual=x, act=MA_ACT_RELU, act_after_residual=True)
+                x = xn
+            pooled = self._empty(n, x.shape[1])
+            ops.token_mean(x.view(n, N, -1), pooled)
+            g = self._lin(self._lin(pooled, self.pose_mlp[0], act=MA_ACT_RELU), self.pose_mlp[1], act=MA_ACT_RELU)
+            ops.gemm(g, self.pose_out.w, pose_raw[s:s + n], bias=self.pose_out.b)
+        return raw, pose_raw
+
+    def scale_head(self, tok_feat: torch.Tensor) -> torch.Tensor:
+        """scale-token feature bf16 [1][D] -> log metric scale fp32 [1]."""
+        x = tok_feat
+        for lin in self.scale_mlp[:-1]:
+            x = self._lin(x, lin, act=MA_ACT_RELU)
+        out = self._empty(1, self.scale_mlp[-1].n, dtype=torch.float32)
+        ops.gemm(x, self.scale_mlp[-1].w, out, bias=self.scale_mlp[-1].b)
+        return out.reshape(-1)[:1].contiguous()

@@ -1,0 +1,333 @@
+"""Drop-in `MapAnything` for the feed-forward inference path of etola/map-anything, running on the sm_100a kernels.
+
+Boundary mirrored (reference mapanything/models/mapanything/model.py):
+  class MapAnything(nn.Module, PyTorchModelHubMixin)  :87     same constructor kwargs (:90-104), the ctor mutates the
+                                                              passed config dicts the same way (:153-193, :260-265, :338-366)
+  forward(views, memory_efficient_inference=False)    :1477   same inputs / per-view output dicts (:1727-1741, :1874-1907)
+  infer(views, ...)                                   :1964   same kwargs, validation errors, in-place device move of the
+                                                              caller's view dicts, temporary geometric_input_config mutation
+  device / dtype properties                           :216-222
+  state_dict key prefixes                             :157-202, :299, :374-388 (dense_head.{0,1} aliases included)
+Only the released configuration is implemented (alternating attention + intermediate features, "dpt+pose" heads,
+"raydirs+depth+pose+confidence+mask" adaptor); anything else raises ValueError at construction like the reference does
+for unknown types.
+"""
+from __future__ import annotations
+
+import warnings
+from functools import partial
+from typing import Any, Callable, Dict, List, Type, Union
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import params as P
+from .engine import Engine
+from .inference import (
+    postprocess_model_outputs_for_inference,
+    validate_input_views_for_inference,
+)
+
+try:  # the reference mixes in huggingface_hub's PyTorchModelHubMixin (from_pretrained / config.json + model.safetensors)
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover
+
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+
+class MapAnything(nn.Module, PyTorchModelHubMixin):
+    "B200-native MapAnything (images + optional geometric inputs -> pointmaps, poses, masks, confidence, metric scale)."
+
+    def __init__(
+        self,
+        name: str,
+        encoder_config: Dict,
+        info_sharing_config: Dict,
+        pred_head_config: Dict,
+        geometric_input_config: Dict,
+        fusion_norm_layer: Union[Type[nn.Module], Callable[..., nn.Module]] = partial(nn.LayerNorm, eps=1e-6),
+        pretrained_checkpoint_path: str = None,
+        load_specific_pretrained_submodules: bool = False,
+        specific_pretrained_submodules: list = None,
+        torch_hub_force_reload: bool = False,
+    ):
+        super().__init__()
+        self.name = name
+        self.encoder_config = encoder_config
+        self.info_sharing_config = info_sharing_config
+        self.pred_head_config = pred_head_config
+        self.geometric_input_config = geometric_input_config
+        self.pretrained_checkpoint_path = pretrained_checkpoint_path
+        self.load_specific_pretrained_submodules = load_specific_pretrained_submodules
+        self.specific_pretrained_submodules = specific_pretrained_submodules
+        self.torch_hub_force_reload = torch_hub_force_reload
+        self.class_init_args = {
+            "name": name, "encoder_config": encoder_config, "info_sharing_config": info_sharing_config,
+            "pred_head_config": pred_head_config, "geometric_input_config": geometric_input_config,
+            "pretrained_checkpoint_path": pretrained_checkpoint_path,
+            "load_specific_pretrained_submodules": load_specific_pretrained_submodules,
+            "specific_pretrained_submodules": specific_pretrained_submodules,
+            "torch_hub_force_reload": torch_hub_force_reload,
+        }
+        self.info_sharing_type = info_sharing_config["model_type"]
+        self.info_sharing_return_type = info_sharing_config["model_return_type"]
+        self.pred_head_type = pred_head_config["type"]
+
+        if self.encoder_config.get("uses_torch_hub", False):
+            self.encoder_config["torch_hub_force_reload"] = torch_hub_force_reload
+        enc_cfg = self.encoder_config.copy()
+        enc_cfg.pop("uses_torch_hub", None)
+        self.encoder = P.encoder_factory(**enc_cfg)
+        c = self.encoder.enc_embed_dim
+
+        g = self.geometric_input_config
+        for key in ("ray_dirs_encoder_config", "depth_encoder_config"):
+            g[key]["enc_embed_dim"] = c
+            g[key]["patch_size"] = self.encoder.patch_size
+        for key in ("scale_encoder_config", "cam_rot_encoder_config", "cam_trans_encoder_config"):
+            g[key]["enc_embed_dim"] = c
+        self.ray_dirs_encoder = P.encoder_factory(**g["ray_dirs_encoder_config"])
+        self.depth_encoder = P.encoder_factory(**g["depth_encoder_config"])
+        self.depth_scale_encoder = P.encoder_factory(**g["scale_encoder_config"])
+        self.cam_rot_encoder = P.encoder_factory(**g["cam_rot_encoder_config"])
+        self.cam_trans_encoder = P.encoder_factory(**g["cam_trans_encoder_config"])
+        self.cam_trans_scale_encoder = P.encoder_factory(**g["scale_encoder_config"])
+        self.fusion_norm_layer = fusion_norm_layer(c)
+        self.scale_token = nn.Parameter(torch.zeros(c))
+        torch.nn.init.trunc_normal_(self.scale_token, std=0.02)
+
+        self._initialize_info_sharing(info_sharing_config)
+        self._initialize_prediction_heads(pred_head_config)
+        self._initialize_adaptors(pred_head_config)
+        self._load_pretrained_weights()
+        self._engine = None
+
+    # ------------------------------------------------------------------------------------------ construction
+    def _initialize_info_sharing(self, cfg):
+        if cfg["custom_positional_encoding"] is not None:
+            raise ValueError(
+                f"Invalid custom_positional_encoding: {cfg['custom_positional_encoding']}. None implemented."
+            )
+        self.custom_positional_encoding = None
+        cfg["module_args"]["input_embed_dim"] = self.encoder.enc_embed_dim
+        cfg["module_args"]["custom_positional_encoding"] = None
+        if self.info_sharing_return_type != "intermediate_features" or self.info_sharing_type != "alternating_attention":
+            raise ValueError(
+                f"mapanything_b200 implements info_sharing model_type='alternating_attention' with "
+                f"model_return_type='intermediate_features' (got {self.info_sharing_type!r}, {self.info_sharing_return_type!r})"
+            )
+        self.info_sharing = P.AlternatingAttentionIFR(**cfg["module_args"])
+        if len(self.info_sharing.indices) == 2:
+            self.use_encoder_features_for_dpt = True
+        else:
+            raise ValueError(
+                "Invalid number of indices provided for info sharing feature returner. This build supports 2 indices "
+                "(encoder features + 2 intermediate + final for the DPT head)."
+            )
+
+    def _initialize_prediction_heads(self, cfg):
+        if self.pred_head_type != "dpt+pose":
+            raise ValueError(f"Invalid pred_head_type: {self.pred_head_type}. This build supports 'dpt+pose'.")
+        cfg["feature_head"]["patch_size"] = self.encoder.patch_size
+        cfg["feature_head"]["input_feature_dims"] = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+        cfg["regressor_head"]["input_feature_dim"] = cfg["feature_head"]["feature_dim"]
+        cfg["pose_head"]["patch_size"] = self.encoder.patch_size
+        cfg["pose_head"]["input_feature_dim"] = self.info_sharing.dim
+        cfg["scale_head"]["input_feature_dim"] = self.info_sharing.dim
+        self.dpt_feature_head = P.DPTFeature(**cfg["feature_head"])
+        self.dpt_regressor_head = P.DPTRegressionProcessor(**cfg["regressor_head"])
+        self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)
+        self.pose_head = P.PoseHead(**cfg["pose_head"])
+        self.scale_head = P.MLPHead(**cfg["scale_head"])
+
+    def _initialize_adaptors(self, cfg):
+        if cfg["adaptor_type"] != "raydirs+depth+pose+confidence+mask":
+            raise ValueError(
+                f"Invalid adaptor_type: {cfg['adaptor_type']}. This build supports 'raydirs+depth+pose+confidence+mask'."
+            )
+        a = cfg.get("dpt_adaptor", {})
+        ok = (a.get("ray_directions_mode", "linear") == "linear" and a.get("ray_directions_normalize_to_unit_sphere", True)
+              and a.get("depth_mode", "exp") == "exp" and a.get("confidence_type", "exp") == "exp"
+              and float(a.get("confidence_vmin", 1)) == 1.0 and float(a.get("depth_vmin", 0)) == 0.0)
+        if not ok:
+            raise ValueError("the fused decode kernel implements the released dense adaptor parameters only")
+        self.scene_rep_type = "raydirs+depth+pose+confidence+mask"
+
+    def _load_pretrained_weights(self):
+        if self.pretrained_checkpoint_path is None:
+            return
+        ckpt = torch.load(self.pretrained_checkpoint_path, weights_only=False)
+        if not self.load_specific_pretrained_submodules:
+            print(f"Loading pretrained MapAnything weights from {self.pretrained_checkpoint_path} ...")
+            print(self.load_state_dict(ckpt["model"]))
+        else:
+            print(
+                f"Loading pretrained MapAnything weights from {self.pretrained_checkpoint_path} for specific submodules: "
+                f"{self.specific_pretrained_submodules} ..."
+            )
+            filtered = {k: v for k, v in ckpt["model"].items()
+                        if any(k.startswith(s) for s in self.specific_pretrained_submodules)}
+            print(self.load_state_dict(filtered, strict=False))
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.parameters()).dtype
+
+    # ------------------------------------------------------------------------------------------ engine plumbing
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def engine(self) -> Engine:
+        """Packs the parameters for the kernels (once per weight/device change)."""
+        if self._engine is None or self._engine.device != self.device:
+            self._engine = Engine(self)
+        return self._engine
+
+    def _geometric_inputs_active(self, views) -> bool:
+        """With p in {0,1} (always the case inside infer) the masks of model.py:1155-1201 are deterministic: a modality is
+        fused iff overall_prob and (1 - dropout_prob) and its own prob are all 1 and a view provides it.  When nothing
+        is active the reference still runs all five encoders on zeros and multiplies by 0; the result is
+        exactly LayerNorm(encoder features), which is what this path computes directly."""
+        g = self.geometric_input_config
+        for name in ("overall_prob", "dropout_prob", "ray_dirs_prob", "depth_prob", "cam_prob"):
+            if g[name] not in (0, 1, 0.0, 1.0):
+                raise ValueError(
+                    f"geometric_input_config[{name!r}]={g[name]}: stochastic input dropout is a training feature; "
+                    "inference needs probabilities in {0, 1}"
+                )
+        if not (g["overall_prob"] == 1 and g["dropout_prob"] == 0):
+            return False
+        keys = []
+        if g["ray_dirs_prob"] == 1:
+            keys.append("ray_directions_cam")
+        if g["depth_prob"] == 1:
+            keys.append("depth_along_ray")
+        if g["cam_prob"] == 1:
+            keys += ["camera_pose_quats"]
+        return any(k in v for v in views for k in keys)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False) -> List[Dict[str, torch.Tensor]]:
+        """Same contract as the reference forward (model.py:1477-1909). Runs under no_grad: this is an inference engine."""
+        batch_size_per_view, _, height, width = views[0]["img"].shape
+        num_views = len(views)
+        data_norm_type = views[0]["data_norm_type"][0]
+        if data_norm_type != self.encoder.data_norm_type:
+            raise AssertionError(
+                f"Input data_norm_type {data_norm_type} does not match the encoder's {self.encoder.data_norm_type}"
+            )
+        p = self.encoder.patch_size
+        if height % p or width % p:
+            raise AssertionError(f"Input image size ({height}, {width}) must be a multiple of the patch size {p}")
+        if self._geometric_inputs_active(views):
+            raise NotImplementedError(
+                "geometric-input fusion (ray directions / depth / pose encoders, SURVEY 8a rows a8-a11) is scheduled after "
+                "the image-only path; call infer(..., ignore_calibration_inputs=True, ignore_depth_inputs=True, "
+                "ignore_pose_inputs=True) or pass image-only views"
+            )
+        eng = self.engine()
+        eng.dpt_chunk = 2 if memory_efficient_inference else 4
+        hp, wp = height // p, width // p
+        N = hp * wp
+        per_scene = []
+        with torch.no_grad():
+            for b in range(batch_size_per_view):
+                imgs = torch.cat([v["img"][b:b + 1] for v in views], dim=0).to(self.device, torch.float32)
+                feat = eng.encode(imgs)                       # fp32 [V*N][C]   DINOv2 x_norm_patchtokens
+                fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
+                taps, final, tok = eng.info_sharing(fused, num_views, N)
+                raw, pose_raw = eng.dpt_and_pose([fused, taps[0], taps[1], final], num_views, hp, wp, height, width)
+                scale_raw = eng.scale_head(tok)
+                per_scene.append(ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width))
+        res = []
+        for i in range(num_views):
+            d = {}
+            for key in ("pts3d", "pts3d_cam", "ray_directions", "depth_along_ray", "cam_trans", "cam_quats", "conf",
+                        "non_ambiguous_mask", "non_ambiguous_mask_logits"):
+                parts = [s[key][i:i + 1] for s in per_scene]
+                d[key] = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+            scales = [s["metric_scaling_factor"] for s in per_scene]
+            d["metric_scaling_factor"] = scales[0] if len(scales) == 1 else torch.cat(scales, dim=0)
+            res.append(d)
+        return res
+
+    # ------------------------------------------------------------------------------------------ infer
+    def _configure_geometric_input_config(self, use_calibration: bool, use_depth: bool, use_pose: bool,
+                                          use_depth_scale: bool, use_pose_scale: bool):
+        if not hasattr(self, "_original_geometric_config"):
+            self._original_geometric_config = dict(self.geometric_input_config)
+        if not (use_calibration or use_depth or use_pose):
+            self.geometric_input_config.update({
+                "overall_prob": 0.0, "dropout_prob": 1.0, "ray_dirs_prob": 0.0, "depth_prob": 0.0, "cam_prob": 0.0,
+                "sparse_depth_prob": 0.0, "depth_scale_norm_all_prob": 0.0, "pose_scale_norm_all_prob": 0.0,
+            })
+        else:
+            self.geometric_input_config.update({
+                "overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0 if use_calibration else 0.0,
+                "depth_prob": 1.0 if use_depth else 0.0, "cam_prob": 1.0 if use_pose else 0.0, "sparse_depth_prob": 0.0,
+                "depth_scale_norm_all_prob": 0.0 if use_depth_scale else 1.0,
+                "pose_scale_norm_all_prob": 0.0 if use_pose_scale else 1.0,
+            })
+
+    def _restore_original_geometric_input_config(self):
+        if hasattr(self, "_original_geometric_config"):
+            self.geometric_input_config.update(self._original_geometric_config)
+
+    @torch.inference_mode()
+    def infer(
+        self,
+        views: List[Dict[str, Any]],
+        memory_efficient_inference: bool = False,
+        use_amp: bool = True,
+        amp_dtype: str = "bf16",
+        apply_mask: bool = True,
+        mask_edges: bool = True,
+        edge_normal_threshold: float = 5.0,
+        edge_depth_threshold: float = 0.03,
+        apply_confidence_mask: bool = False,
+        confidence_percentile: float = 10,
+        ignore_calibration_inputs: bool = False,
+        ignore_depth_inputs: bool = False,
+        ignore_pose_inputs: bool = False,
+        ignore_depth_scale_inputs: bool = False,
+        ignore_pose_scale_inputs: bool = False,
+    ) -> List[Dict[str, torch.Tensor]]:
+        """Same surface as the reference infer (model.py:1964-2112).  The kernels always compute with bf16 tensor-core
+        operands, fp32 accumulation and fp32 residual streams -- the reference's `use_amp=True, amp_dtype="bf16"` mode."""
+        if not use_amp or amp_dtype not in ("bf16",):
+            warnings.warn("mapanything_b200 always computes in bf16 (fp32 accumulate); use_amp/amp_dtype are ignored")
+        validated = validate_input_views_for_inference(views)
+        ignore_keys = {"instance", "idx", "true_shape", "data_norm_type"}
+        for view in validated:
+            for key in view.keys():
+                if key in ignore_keys:
+                    continue
+                view[key] = view[key].to(self.device, non_blocking=True)
+        from .preprocess import preprocess_input_views_for_inference
+
+        processed = preprocess_input_views_for_inference(validated)
+        self._configure_geometric_input_config(
+            use_calibration=not ignore_calibration_inputs, use_depth=not ignore_depth_inputs,
+            use_pose=not ignore_pose_inputs, use_depth_scale=not ignore_depth_scale_inputs,
+            use_pose_scale=not ignore_pose_scale_inputs,
+        )
+        try:
+            preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference)
+        finally:
+            self._restore_original_geometric_input_config()
+        return postprocess_model_outputs_for_inference(
+            raw_outputs=preds, input_views=processed, apply_mask=apply_mask, mask_edges=mask_edges,
+            edge_normal_threshold=edge_normal_threshold, edge_depth_threshold=edge_depth_threshold,
+            apply_confidence_mask=apply_confidence_mask, confidence_percentile=confidence_percentile,
+        )

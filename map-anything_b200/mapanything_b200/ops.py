@@ -61,6 +61,8 @@ def gemm(
     rows_per_group_out: int = 0,
     row_offset_out: int = 0,
     block_n: int = 0,
+    act_after_residual: bool = False,
+    relu_out_before_residual: bool = False,
 ) -> torch.Tensor:
     """out = epilogue(x @ w.T); x [M,K] bf16, w [N,K] bf16 (row strides may exceed K). See ma_gemm_bf16."""
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
@@ -91,6 +93,7 @@ def gemm(
     ep.rows_per_group_in = rows_per_group_in
     ep.rows_per_group_out = rows_per_group_out
     ep.row_offset_out = row_offset_out
+    ep.flags = (1 if act_after_residual else 0) | (2 if relu_out_before_residual else 0)
     lib = _lib.load()
     check(
         lib.ma_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), block_n, _stream()),
@@ -142,3 +145,139 @@ def attention(
     )
     _count()
     return out
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA {dtype} tensor")
+    return t
+
+
+def patchify(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
+    """(n,3,H,W) fp32 -> out [n*hp*wp, kpad] bf16 (ma_patchify)."""
+    _req(img, torch.float32, "img")
+    _req(out, torch.bfloat16, "out")
+    n, c, H, W = img.shape
+    assert c == 3 and out.shape[0] == n * (H // patch) * (W // patch)
+    check(_lib.load().ma_patchify(img.data_ptr(), out.data_ptr(), n, H, W, patch, out.shape[1], _stream()), "ma_patchify")
+    _count()
+    return out
+
+
+def layernorm(
+    x: torch.Tensor,
+    out: torch.Tensor,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    *,
+    rows: Optional[int] = None,
+    eps: float = 1e-6,
+    rows_per_group: int = 0,
+    in_group_stride: int = 0,
+    in_row_offset: int = 0,
+    out_group_stride: int = 0,
+    out_row_offset: int = 0,
+) -> torch.Tensor:
+    """LayerNorm over the last dim of 2-D row-major x -> out, with optional row remapping (ma_layernorm)."""
+    C = x.shape[-1]
+    if rows is None:
+        rows = x.shape[0]
+    if x.stride(-1) != 1 or out.stride(-1) != 1 or out.shape[-1] != C:
+        raise ValueError("layernorm: rows must be contiguous and widths must match")
+    _f32c(gamma, C, "gamma")
+    _f32c(beta, C, "beta")
+    check(
+        _lib.load().ma_layernorm(
+            x.data_ptr(), _dt(x), x.stride(-2), out.data_ptr(), _dt(out), out.stride(-2), gamma.data_ptr(), beta.data_ptr(),
+            rows, C, float(eps), rows_per_group, in_group_stride, in_row_offset, out_group_stride, out_row_offset, _stream(),
+        ),
+        "ma_layernorm",
+    )
+    _count()
+    return out
+
+
+def set_rows(dst: torch.Tensor, a: torch.Tensor, b: Optional[torch.Tensor], *, groups: int, group_stride: int,
+             row_offset: int) -> torch.Tensor:
+    C = dst.shape[-1]
+    if dst.dtype != torch.float32 or dst.stride(-1) != 1:
+        raise ValueError("set_rows: dst must be fp32 with contiguous rows")
+    _f32c(a, C, "a")
+    _f32c(b, C, "b")
+    check(_lib.load().ma_set_rows(dst.data_ptr(), dst.stride(-2), groups, group_stride, row_offset, a.data_ptr(), _ptr(b), C,
+                                  _stream()), "ma_set_rows")
+    _count()
+    return dst
+
+
+def im2col3x3(x: torch.Tensor, out: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    """NHWC bf16 (n,H,W,C) -> out [n*Ho*Wo, 9*C] (ma_im2col3x3)."""
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    n, H, W, C = x.shape
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    assert out.numel() == n * Ho * Wo * 9 * C, "im2col3x3: bad output size"
+    check(_lib.load().ma_im2col3x3(x.data_ptr(), out.data_ptr(), n, H, W, C, stride, _stream()), "ma_im2col3x3")
+    _count()
+    return out
+
+
+def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C: int, s: int) -> torch.Tensor:
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    assert x.numel() == n * h * w * s * s * C == out.numel()
+    check(_lib.load().ma_pixel_shuffle(x.data_ptr(), out.data_ptr(), n, h, w, C, s, _stream()), "ma_pixel_shuffle")
+    _count()
+    return out
+
+
+def bilinear_ac(x: torch.Tensor, out: torch.Tensor, virtual_hw=None) -> torch.Tensor:
+    """NHWC bf16 bilinear resize with align_corners=True; out (n,Ho,Wo,C); virtual_hw = uncropped output size."""
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    n, Hin, Win, C = x.shape
+    _, Ho, Wo, _ = out.shape
+    Hv, Wv = virtual_hw if virtual_hw is not None else (Ho, Wo)
+    check(_lib.load().ma_bilinear_align_corners(x.data_ptr(), out.data_ptr(), n, Hin, Win, C, Hv, Wv, Ho, Wo, _stream()),
+          "ma_bilinear_align_corners")
+    _count()
+    return out
+
+
+def token_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """bf16 (n,T,C) -> (n,C)."""
+    _req(x, torch.bfloat16, "x")
+    _req(out, torch.bfloat16, "out")
+    n, T, C = x.shape
+    check(_lib.load().ma_token_mean(x.data_ptr(), out.data_ptr(), n, T, C, _stream()), "ma_token_mean")
+    _count()
+    return out
+
+
+def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Tensor, n: int, H: int, W: int):
+    """Fused adaptor + decode (ma_decode_dense). raw fp32 [n*H*W, ld>=6]; returns the dict of forward() tensors."""
+    if raw.dtype != torch.float32 or raw.stride(-1) != 1:
+        raise ValueError("decode_dense: raw must be fp32 with contiguous rows")
+    _req(pose_raw, torch.float32, "pose_raw")
+    _req(scale_raw, torch.float32, "scale_raw")
+    dev = raw.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    o = {
+        "pts3d": torch.empty(n, H, W, 3, **f32), "pts3d_cam": torch.empty(n, H, W, 3, **f32),
+        "ray_directions": torch.empty(n, H, W, 3, **f32), "depth_along_ray": torch.empty(n, H, W, 1, **f32),
+        "conf": torch.empty(n, H, W, **f32), "non_ambiguous_mask_logits": torch.empty(n, H, W, **f32),
+        "non_ambiguous_mask": torch.empty(n, H, W, device=dev, dtype=torch.bool),
+        "cam_trans": torch.empty(n, 3, **f32), "cam_quats": torch.empty(n, 4, **f32),
+        "metric_scaling_factor": torch.empty(1, 1, **f32),
+    }
+    check(
+        _lib.load().ma_decode_dense(
+            raw.data_ptr(), raw.stride(0), pose_raw.data_ptr(), scale_raw.data_ptr(), n, H * W, o["pts3d"].data_ptr(),
+            o["pts3d_cam"].data_ptr(), o["ray_directions"].data_ptr(), o["depth_along_ray"].data_ptr(), o["conf"].data_ptr(),
+            o["non_ambiguous_mask_logits"].data_ptr(), o["non_ambiguous_mask"].data_ptr(), o["cam_trans"].data_ptr(),
+            o["cam_quats"].data_ptr(), o["metric_scaling_factor"].data_ptr(), _stream(),
+        ),
+        "ma_decode_dense",
+    )
+    _count()
+    return o
