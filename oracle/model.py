@@ -210,14 +210,28 @@ class MapAnythingOracle(nn.Module):
         return feats.chunk(v, dim=0)
 
     # ---------------------------------------------------------------------------------- forward
-    def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False, return_internals: bool = False):
+    def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False, return_internals: bool = False,
+                amp_bf16: bool = False):
+        """amp_bf16=True reproduces the reference's infer(use_amp=True, amp_dtype="bf16") numerics on the CPU: encoder and
+        info sharing under bf16 autocast (model.py:2092-2095), input fusion and every head with autocast disabled
+        (model.py:1516, :1599).  It is the yardstick for how far ANY bf16 path sits from the fp32 result."""
+        import contextlib
+
+        def amp():
+            return torch.autocast("cpu", dtype=torch.bfloat16) if amp_bf16 else contextlib.nullcontext()
+
         b, _, h, w = views[0]["img"].shape
         v = len(views)
         norm_type = views[0]["data_norm_type"][0]
-        enc = self.encoder(torch.cat([vw["img"] for vw in views], dim=0), norm_type).chunk(v, dim=0)
+        with amp():
+            enc = self.encoder(torch.cat([vw["img"] for vw in views], dim=0), norm_type).float().chunk(v, dim=0)
         fused = self._encode_and_fuse(views, enc)
         token = self.scale_token.unsqueeze(0).unsqueeze(-1).repeat(b, 1, 1)
-        final_feats, final_extra, inter = self.info_sharing(list(fused), token)
+        with amp():
+            final_feats, final_extra, inter = self.info_sharing(list(fused), token)
+        final_feats = [f.float() for f in final_feats]
+        final_extra = final_extra.float()
+        inter = [([f.float() for f in fs], ex) for fs, ex in inter]
         dpt_in = [torch.cat(fused, 0), torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(final_feats, 0)]
 
         n = dpt_in[0].shape[0]

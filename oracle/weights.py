@@ -69,3 +69,38 @@ def canonical_key(key: str) -> str:
 def load_synthetic(model: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
     model.load_state_dict(synth_state_dict(model, seed), strict=True)
     return model
+
+
+@torch.no_grad()
+def init_reference_style(model: torch.nn.Module, seed: int = 0) -> torch.nn.Module:
+    """"Random-init weights of that architecture" as the reference would have them without a checkpoint:
+    DINOv2's own init (vision_transformer.py:203-207, :384-389: trunc-normal(0.02) Linear weights, zero biases,
+    pos_embed trunc-normal(0.02), cls_token N(0, 1e-6), LayerScale gamma = init_values = 1.0 per hub/backbones.py:25),
+    the same timm-style init for the multi-view transformer, scale_token trunc-normal(0.02) (model.py:201-202), and
+    PyTorch's default reset_parameters() for every conv / linear of the heads and geometric encoders."""
+    torch.manual_seed(seed)
+    nn = torch.nn
+    for name, mod in model.named_modules():
+        vit_like = name.startswith("encoder.model") or name.startswith("info_sharing")
+        if isinstance(mod, nn.Linear):
+            if vit_like:
+                nn.init.trunc_normal_(mod.weight, std=0.02)
+                if mod.bias is not None:
+                    nn.init.zeros_(mod.bias)
+            else:
+                mod.reset_parameters()
+        elif isinstance(mod, (nn.Conv2d, nn.ConvTranspose2d)):
+            mod.reset_parameters()
+        elif isinstance(mod, nn.LayerNorm):
+            mod.reset_parameters()
+    for name, p in model.named_parameters():
+        leaf = name.split(".")[-1]
+        if leaf == "gamma":
+            p.fill_(1.0)
+        elif leaf in ("pos_embed", "scale_token"):
+            nn.init.trunc_normal_(p, std=0.02)
+        elif leaf == "cls_token":
+            nn.init.normal_(p, std=1e-6)
+        elif leaf == "mask_token":
+            p.zero_()
+    return model
