@@ -2,7 +2,8 @@
 
 PyTorch is used for device memory and streams only: every function here hands raw device pointers and
 the current CUDA stream to `libmapanything_b200.so`.  `LAUNCHES` counts kernel launches issued through
-this module (bench.py reports it as `gpu_launches`).
+this module (bench.py reports it as `gpu_launches`); when `PROFILE` is a list, every launch is bracketed by
+CUDA events on the launching stream and appended as (family, algorithmic_flops, start_event, end_event).
 """
 from __future__ import annotations
 
@@ -15,6 +16,32 @@ from . import _lib
 from ._lib import MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU, MA_BF16, MA_F32, GemmEpilogue, check  # noqa: F401
 
 LAUNCHES = 0
+PROFILE = None
+
+
+class launch:
+    """Context manager around one kernel launch: counts it and (optionally) times it with CUDA events."""
+
+    __slots__ = ("name", "flops", "n", "s")
+
+    def __init__(self, name: str, flops: float = 0.0, n: int = 1):
+        self.name, self.flops, self.n, self.s = name, flops, n, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global LAUNCHES
+        if et is None:
+            LAUNCHES += self.n
+            if PROFILE is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                PROFILE.append((self.name, self.flops, self.s, e))
+        return False
 
 
 def _count(n: int = 1) -> None:
@@ -43,6 +70,12 @@ def _f32c(t: Optional[torch.Tensor], n: int, name: str) -> Optional[torch.Tensor
         return None
     if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != n or not t.is_cuda:
         raise ValueError(f"{name} must be a contiguous CUDA float32 tensor with {n} elements")
+    return t
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name} must be a contiguous CUDA {dtype} tensor")
     return t
 
 
@@ -95,11 +128,11 @@ def gemm(
     ep.row_offset_out = row_offset_out
     ep.flags = (1 if act_after_residual else 0) | (2 if relu_out_before_residual else 0)
     lib = _lib.load()
-    check(
-        lib.ma_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), block_n, _stream()),
-        "ma_gemm_bf16",
-    )
-    _count()
+    with launch("gemm", 2.0 * M * N * K):
+        check(
+            lib.ma_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), block_n, _stream()),
+            "ma_gemm_bf16",
+        )
     return out
 
 
@@ -133,24 +166,18 @@ def attention(
     lib = _lib.load()
     # Column offsets are folded into the base pointers; the tensor map width is the row stride, which
     # always covers [col0, col0 + heads*64) of the parent matrix when the view is a column slice of it.
-    check(
-        lib.ma_attention_fwd(
-            q.data_ptr(), q.stride(0), q.shape[0], 0,
-            k.data_ptr(), k.stride(0), k.shape[0], 0,
-            v.data_ptr(), v.stride(0), 0,
-            out.data_ptr(), out.stride(0), 0,
-            num_seqs, num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, float(scale), _stream(),
-        ),
-        "ma_attention_fwd",
-    )
-    _count()
+    with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64):
+        check(
+            lib.ma_attention_fwd(
+                q.data_ptr(), q.stride(0), q.shape[0], 0,
+                k.data_ptr(), k.stride(0), k.shape[0], 0,
+                v.data_ptr(), v.stride(0), 0,
+                out.data_ptr(), out.stride(0), 0,
+                num_seqs, num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, float(scale), _stream(),
+            ),
+            "ma_attention_fwd",
+        )
     return out
-
-
-def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
-    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
-        raise ValueError(f"{name} must be a contiguous CUDA {dtype} tensor")
-    return t
 
 
 def patchify(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
@@ -159,8 +186,8 @@ def patchify(img: torch.Tensor, out: torch.Tensor, patch: int) -> torch.Tensor:
     _req(out, torch.bfloat16, "out")
     n, c, H, W = img.shape
     assert c == 3 and out.shape[0] == n * (H // patch) * (W // patch)
-    check(_lib.load().ma_patchify(img.data_ptr(), out.data_ptr(), n, H, W, patch, out.shape[1], _stream()), "ma_patchify")
-    _count()
+    with launch("patchify"):
+        check(_lib.load().ma_patchify(img.data_ptr(), out.data_ptr(), n, H, W, patch, out.shape[1], _stream()), "ma_patchify")
     return out
 
 
@@ -179,34 +206,35 @@ def layernorm(
     out_row_offset: int = 0,
 ) -> torch.Tensor:
     """LayerNorm over the last dim of 2-D row-major x -> out, with optional row remapping (ma_layernorm)."""
-    C = x.shape[-1]
+    C_ = x.shape[-1]
     if rows is None:
         rows = x.shape[0]
-    if x.stride(-1) != 1 or out.stride(-1) != 1 or out.shape[-1] != C:
+    if x.stride(-1) != 1 or out.stride(-1) != 1 or out.shape[-1] != C_:
         raise ValueError("layernorm: rows must be contiguous and widths must match")
-    _f32c(gamma, C, "gamma")
-    _f32c(beta, C, "beta")
-    check(
-        _lib.load().ma_layernorm(
-            x.data_ptr(), _dt(x), x.stride(-2), out.data_ptr(), _dt(out), out.stride(-2), gamma.data_ptr(), beta.data_ptr(),
-            rows, C, float(eps), rows_per_group, in_group_stride, in_row_offset, out_group_stride, out_row_offset, _stream(),
-        ),
-        "ma_layernorm",
-    )
-    _count()
+    _f32c(gamma, C_, "gamma")
+    _f32c(beta, C_, "beta")
+    with launch("layernorm"):
+        check(
+            _lib.load().ma_layernorm(
+                x.data_ptr(), _dt(x), x.stride(-2), out.data_ptr(), _dt(out), out.stride(-2), gamma.data_ptr(),
+                beta.data_ptr(), rows, C_, float(eps), rows_per_group, in_group_stride, in_row_offset, out_group_stride,
+                out_row_offset, _stream(),
+            ),
+            "ma_layernorm",
+        )
     return out
 
 
 def set_rows(dst: torch.Tensor, a: torch.Tensor, b: Optional[torch.Tensor], *, groups: int, group_stride: int,
              row_offset: int) -> torch.Tensor:
-    C = dst.shape[-1]
+    C_ = dst.shape[-1]
     if dst.dtype != torch.float32 or dst.stride(-1) != 1:
         raise ValueError("set_rows: dst must be fp32 with contiguous rows")
-    _f32c(a, C, "a")
-    _f32c(b, C, "b")
-    check(_lib.load().ma_set_rows(dst.data_ptr(), dst.stride(-2), groups, group_stride, row_offset, a.data_ptr(), _ptr(b), C,
-                                  _stream()), "ma_set_rows")
-    _count()
+    _f32c(a, C_, "a")
+    _f32c(b, C_, "b")
+    with launch("set_rows"):
+        check(_lib.load().ma_set_rows(dst.data_ptr(), dst.stride(-2), groups, group_stride, row_offset, a.data_ptr(), _ptr(b),
+                                      C_, _stream()), "ma_set_rows")
     return dst
 
 
@@ -214,20 +242,20 @@ def im2col3x3(x: torch.Tensor, out: torch.Tensor, stride: int = 1) -> torch.Tens
     """NHWC bf16 (n,H,W,C) -> out [n*Ho*Wo, 9*C] (ma_im2col3x3)."""
     _req(x, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
-    n, H, W, C = x.shape
+    n, H, W, C_ = x.shape
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
-    assert out.numel() == n * Ho * Wo * 9 * C, "im2col3x3: bad output size"
-    check(_lib.load().ma_im2col3x3(x.data_ptr(), out.data_ptr(), n, H, W, C, stride, _stream()), "ma_im2col3x3")
-    _count()
+    assert out.numel() == n * Ho * Wo * 9 * C_, "im2col3x3: bad output size"
+    with launch("im2col"):
+        check(_lib.load().ma_im2col3x3(x.data_ptr(), out.data_ptr(), n, H, W, C_, stride, _stream()), "ma_im2col3x3")
     return out
 
 
-def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C: int, s: int) -> torch.Tensor:
+def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C_: int, s: int) -> torch.Tensor:
     _req(x, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
-    assert x.numel() == n * h * w * s * s * C == out.numel()
-    check(_lib.load().ma_pixel_shuffle(x.data_ptr(), out.data_ptr(), n, h, w, C, s, _stream()), "ma_pixel_shuffle")
-    _count()
+    assert x.numel() == n * h * w * s * s * C_ == out.numel()
+    with launch("pixel_shuffle"):
+        check(_lib.load().ma_pixel_shuffle(x.data_ptr(), out.data_ptr(), n, h, w, C_, s, _stream()), "ma_pixel_shuffle")
     return out
 
 
@@ -235,12 +263,12 @@ def bilinear_ac(x: torch.Tensor, out: torch.Tensor, virtual_hw=None) -> torch.Te
     """NHWC bf16 bilinear resize with align_corners=True; out (n,Ho,Wo,C); virtual_hw = uncropped output size."""
     _req(x, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
-    n, Hin, Win, C = x.shape
+    n, Hin, Win, C_ = x.shape
     _, Ho, Wo, _ = out.shape
     Hv, Wv = virtual_hw if virtual_hw is not None else (Ho, Wo)
-    check(_lib.load().ma_bilinear_align_corners(x.data_ptr(), out.data_ptr(), n, Hin, Win, C, Hv, Wv, Ho, Wo, _stream()),
-          "ma_bilinear_align_corners")
-    _count()
+    with launch("bilinear"):
+        check(_lib.load().ma_bilinear_align_corners(x.data_ptr(), out.data_ptr(), n, Hin, Win, C_, Hv, Wv, Ho, Wo, _stream()),
+              "ma_bilinear_align_corners")
     return out
 
 
@@ -248,9 +276,9 @@ def token_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     """bf16 (n,T,C) -> (n,C)."""
     _req(x, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
-    n, T, C = x.shape
-    check(_lib.load().ma_token_mean(x.data_ptr(), out.data_ptr(), n, T, C, _stream()), "ma_token_mean")
-    _count()
+    n, T, C_ = x.shape
+    with launch("token_mean"):
+        check(_lib.load().ma_token_mean(x.data_ptr(), out.data_ptr(), n, T, C_, _stream()), "ma_token_mean")
     return out
 
 
@@ -270,14 +298,14 @@ def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Ten
         "cam_trans": torch.empty(n, 3, **f32), "cam_quats": torch.empty(n, 4, **f32),
         "metric_scaling_factor": torch.empty(1, 1, **f32),
     }
-    check(
-        _lib.load().ma_decode_dense(
-            raw.data_ptr(), raw.stride(0), pose_raw.data_ptr(), scale_raw.data_ptr(), n, H * W, o["pts3d"].data_ptr(),
-            o["pts3d_cam"].data_ptr(), o["ray_directions"].data_ptr(), o["depth_along_ray"].data_ptr(), o["conf"].data_ptr(),
-            o["non_ambiguous_mask_logits"].data_ptr(), o["non_ambiguous_mask"].data_ptr(), o["cam_trans"].data_ptr(),
-            o["cam_quats"].data_ptr(), o["metric_scaling_factor"].data_ptr(), _stream(),
-        ),
-        "ma_decode_dense",
-    )
-    _count()
+    with launch("decode"):
+        check(
+            _lib.load().ma_decode_dense(
+                raw.data_ptr(), raw.stride(0), pose_raw.data_ptr(), scale_raw.data_ptr(), n, H * W, o["pts3d"].data_ptr(),
+                o["pts3d_cam"].data_ptr(), o["ray_directions"].data_ptr(), o["depth_along_ray"].data_ptr(),
+                o["conf"].data_ptr(), o["non_ambiguous_mask_logits"].data_ptr(), o["non_ambiguous_mask"].data_ptr(),
+                o["cam_trans"].data_ptr(), o["cam_quats"].data_ptr(), o["metric_scaling_factor"].data_ptr(), _stream(),
+            ),
+            "ma_decode_dense",
+        )
     return o
