@@ -218,6 +218,14 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    if args.profile_mode:  # short, un-reported run for ncu: one warm-up step, one step, nothing else
+        fwd_step()
+        torch.cuda.synchronize()
+        fwd_step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "views": V, "launches_per_step": ops.LAUNCHES // 2}))
+        return
     for _ in range(max(args.warmup, 3)):
         fwd_step()
     with ClockSampler(local_rank) as clocks:
@@ -308,6 +316,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
