@@ -136,6 +136,14 @@ int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win
 /* AdaptiveAvgPool2d(1) over tokens: bf16 [n][T][C] -> bf16 [n][C] (pose head). */
 int ma_token_mean(const void* in, void* out, int n, int T, int C, void* stream);
 
+/* fp32 [rows][C] -> bf16 [rows][3C] = [hi | lo | hi] (hi = bf16(x), lo = bf16(x - hi)).  With weights packed
+ * [w_hi | w_hi | w_lo] one ma_gemm_bf16 over K' = 3K evaluates the product to ~2^-16 relative accuracy: used for
+ * the pose / scale heads, which the reference runs with autocast disabled (model.py:1599). */
+int ma_split_bf16x3(const float* in, int64_t ld_in, void* out, int rows, int C, void* stream);
+
+/* fp32 variant of ma_token_mean. */
+int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* stream);
+
 /* Fused dense adaptor + pose/scale adaptors + factored-geometry decode + output packaging (reference
  * model.py:1683-1741, :1874-1907; geometry.py:855-907): raw [n*HW][ld_raw] fp32 = (ray xyz, depth logit,
  * confidence logit, mask logit); pose_raw [n][7] = (t, q xyzw); scale_raw [1] (log metric scale).

@@ -306,6 +306,54 @@ __global__ void decode_dense_kernel(const DecodeParams p) {
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// split_bf16x3: fp32 [rows][C] -> bf16 [rows][3C] = [hi | lo | hi] per group of C channels, hi = bf16(x),
+// lo = bf16(x - hi).  Against weights packed as [w_hi | w_hi | w_lo] one bf16 tensor-core GEMM over K' = 3K computes
+// a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation: ~2^-16 relative error per product instead of 2^-8.
+// Used where the reference runs fp32 (autocast disabled, model.py:1599) and the output feeds a normalisation
+// (pose quaternion, metric scale).
+// ----------------------------------------------------------------------------------------------
+__global__ void split_bf16x3_kernel(const float* __restrict__ in, int64_t ld_in, __nv_bfloat16* __restrict__ out, int rows,
+                                    int C) {
+  const int c4 = C >> 2;
+  const int64_t total = (int64_t)rows * c4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / c4;
+    const int c = static_cast<int>(idx - r * c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    float hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __bfloat162float(__float2bfloat16(x[i]));
+      lo[i] = x[i] - hi[i];
+    }
+    const uint2 h = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
+    const uint2 l = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
+    __nv_bfloat16* o = out + r * (3 * (int64_t)C) + c;
+    *reinterpret_cast<uint2*>(o) = h;
+    *reinterpret_cast<uint2*>(o + C) = l;
+    *reinterpret_cast<uint2*>(o + 2 * C) = h;
+  }
+}
+
+// fp32 token mean: [n][T][C] -> [n][C]
+__global__ void token_mean_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C) {
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int rl = threadIdx.x >> 6;
+  const float* base = in + (size_t)blockIdx.y * T * C;
+  float s = 0.f;
+  if (c < C)
+    for (int t = rl; t < T; t += 4) s += base[(size_t)t * C + c];
+  red[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    const float tot = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    out[(size_t)blockIdx.y * C + c] = tot / T;
+  }
+}
+
 static inline int grid_for(int64_t total, int block, int max_blocks) {
   int64_t g = (total + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -389,6 +437,23 @@ extern "C" int ma_token_mean(const void* in, void* out, int n, int T, int C, voi
   dim3 grid((C + 63) / 64, n);
   token_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(in),
                                                                          static_cast<__nv_bfloat16*>(out), T, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_split_bf16x3(const float* in, int64_t ld_in, void* out, int rows, int C, void* stream) {
+  MA_REQUIRE(in && out && rows > 0 && C > 0 && C % 4 == 0 && ld_in % 4 == 0, "ma_split_bf16x3: bad arguments (C=%d)", C);
+  const int64_t total = (int64_t)rows * (C / 4);
+  split_bf16x3_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, static_cast<__nv_bfloat16*>(out), rows, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && T > 0 && C > 0, "ma_token_mean_f32: bad arguments");
+  dim3 grid((C + 63) / 64, n);
+  token_mean_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, T, C);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

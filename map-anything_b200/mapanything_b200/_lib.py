@@ -60,7 +60,9 @@ SIGNATURES = {
     "ma_bilinear_align_corners": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ma_token_mean": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_decode_dense": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "ma_denorm_image": (_i, [_p, _p, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p]),
+    "ma_split_bf16x3": (_i, [_p, _i64, _p, _i, _i, _p]),
+    "ma_token_mean_f32": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_denorm_image":(_i, [_p, _p, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p]),
     "ma_intrinsics_from_rays": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_pose_matrices": (_i, [_p, _p, _p, _i, _p]),
     "ma_edge_mask": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),

@@ -41,6 +41,23 @@ class Lin:
         self.n, self.k = self.w.shape
 
 
+class Lin3:
+    """y = x W^T + b evaluated to ~fp32 accuracy on the bf16 tensor cores (see ma_split_bf16x3): the weight is packed as
+    [w_hi | w_hi | w_lo] per `group` input channels, matching activations split as [a_hi | a_lo | a_hi].
+    group = K for a Linear / 1x1 conv; group = Cin for the (tap-major) im2col layout of a 3x3 conv."""
+
+    def __init__(self, w2d: torch.Tensor, b: Optional[torch.Tensor], group: Optional[int] = None):
+        w2d = w2d.detach().float().reshape(w2d.shape[0], -1)
+        n, k = w2d.shape
+        group = group or k
+        w = w2d.view(n, k // group, group)
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.float()).to(torch.bfloat16)
+        self.w = torch.cat([hi, hi, lo], dim=2).reshape(n, 3 * k).contiguous()
+        self.b = _f32(b) if b is not None else None
+        self.n, self.k = n, 3 * k
+
+
 def _conv3x3(conv: nn.Conv2d) -> Lin:
     return Lin(conv.weight.detach().permute(0, 2, 3, 1), conv.bias)  # [Cout][ky][kx][Cin]
 
@@ -134,10 +151,17 @@ class Engine:
         for rb in ph.res_conv:
             if not isinstance(rb.head_skip, nn.Identity):
                 raise ValueError("pose head with a projecting skip is not part of the released config")
-            self.pose_blocks.append((_conv1x1(rb.res_conv1), _conv3x3(rb.res_conv2), _conv1x1(rb.res_conv3)))
-        self.pose_mlp = [Lin(ph.more_mlps[0].weight, ph.more_mlps[0].bias), Lin(ph.more_mlps[2].weight, ph.more_mlps[2].bias)]
-        self.pose_out = Lin(torch.cat([ph.fc_t.weight, ph.fc_rot.weight], 0), torch.cat([ph.fc_t.bias, ph.fc_rot.bias], 0))
-        self.scale_mlp = [Lin(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
+            # pose + scale heads run in split-bf16 (~fp32) precision: their outputs are normalised / exponentiated and
+            # the reference computes them with autocast disabled (model.py:1599)
+            cin = rb.res_conv2.weight.shape[1]
+            self.pose_blocks.append((
+                Lin3(rb.res_conv1.weight, rb.res_conv1.bias),
+                Lin3(rb.res_conv2.weight.detach().permute(0, 2, 3, 1), rb.res_conv2.bias, group=cin),
+                Lin3(rb.res_conv3.weight, rb.res_conv3.bias),
+            ))
+        self.pose_mlp = [Lin3(ph.more_mlps[0].weight, ph.more_mlps[0].bias), Lin3(ph.more_mlps[2].weight, ph.more_mlps[2].bias)]
+        self.pose_out = Lin3(torch.cat([ph.fc_t.weight, ph.fc_rot.weight], 0), torch.cat([ph.fc_t.bias, ph.fc_rot.bias], 0))
+        self.scale_mlp = [Lin3(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
         self.dpt_chunk = 4  # views per DPT pass (bounds the im2col scratch: ~0.62 GB per view at 518 px)
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -252,9 +276,11 @@ class Engine:
                 else:
                     raise NotImplementedError("norm_intermediate=False is not part of the released config")
                 taps.append(tap)
-        final = self._empty(T, D)
-        ops.layernorm(y, final, self.is_nw, self.is_nb)
-        return taps, final[:V * N], final[V * N:]
+        final = self._empty(V * N, D)
+        ops.layernorm(y, final, self.is_nw, self.is_nb, rows=V * N)      # bf16: DPT tap 3
+        final32 = self._empty(T, D, dtype=torch.float32)
+        ops.layernorm(y, final32, self.is_nw, self.is_nb)                 # fp32: pose head input + scale-token feature
+        return taps, final, final32
 
     # ------------------------------------------------------------------------------------------ stage 3
     def _rcu(self, x_relu, x_skip, r, c1: str, c2: str, *, want_relu: bool):
@@ -291,8 +317,37 @@ class Engine:
         ops.bilinear_ac(o, up, virtual_hw=up_virtual)
         return up
 
-    def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int):
-        """taps4: 4 x bf16 [V*N][C_i] -> raw dense fp32 [V*H*W][8] (6 used), pose_raw fp32 [V][7]."""
+    def pose_head(self, x32: torch.Tensor, n: int, hp: int, wp: int, out: torch.Tensor):
+        """Pose head in split-bf16 precision. x32 fp32 [n*N][D] (final info-sharing features) -> out fp32 [n][7] = (t | q)."""
+        N = hp * wp
+        D = x32.shape[1]
+        for c1, c2, c3 in self.pose_blocks:
+            u = self._empty(n * N, c1.n, dtype=torch.float32)
+            ops.gemm(ops.split3(x32), c1.w, u, bias=c1.b, act=MA_ACT_RELU)
+            us = ops.split3(u).view(n, hp, wp, 3 * c1.n)
+            col = self._empty(n * N, 27 * c1.n)
+            ops.im2col3x3(us, col, 1)
+            u2 = self._empty(n * N, c2.n, dtype=torch.float32)
+            ops.gemm(col, c2.w, u2, bias=c2.b, act=MA_ACT_RELU)
+            xn = self._empty(n * N, c3.n, dtype=torch.float32)
+            ops.gemm(ops.split3(u2), c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU, act_after_residual=True)
+            x32 = xn
+        pooled = self._empty(n, D, dtype=torch.float32)
+        ops.token_mean_f32(x32.view(n, N, D), pooled)
+        g = pooled
+        for lin in self.pose_mlp:
+            gn = self._empty(n, lin.n, dtype=torch.float32)
+            ops.gemm(ops.split3(g), lin.w, gn, bias=lin.b, act=MA_ACT_RELU)
+            g = gn
+        ops.gemm(ops.split3(g), self.pose_out.w, out, bias=self.pose_out.b)
+        return out
+
+    def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int,
+                     final32: Optional[torch.Tensor] = None):
+        """taps4: 4 x bf16 [V*N][C_i] (+ final32 fp32 [V*N][D] for the pose head; defaults to taps4[3] upcast)
+        -> raw dense fp32 [V*H*W][8] (6 used), pose_raw fp32 [V][7]."""
+        if final32 is None:
+            final32 = taps4[3].float()
         N = hp * wp
         raw = self._empty(V * H * W, 8, dtype=torch.float32)
         pose_raw = self._empty(V, 7, dtype=torch.float32)
@@ -323,25 +378,17 @@ class Engine:
             ops.bilinear_ac(g1, g1u)
             g2 = self._conv3(g1u, self.reg2, act=MA_ACT_RELU)
             ops.gemm(g2.reshape(n * H * W, -1), self.reg3.w, raw[s * H * W:(s + n) * H * W, :self.reg3.n], bias=self.reg3.b)
-            # pose head on the final info-sharing features
-            x = t[3]
-            for c1, c2, c3 in self.pose_blocks:
-                u = self._lin(x, c1, act=MA_ACT_RELU).view(n, hp, wp, -1)
-                u = self._conv3(u, c2, act=MA_ACT_RELU).reshape(n * N, -1)
-                xn = self._empty(n * N, c3.n)
-                ops.gemm(u, c3.w, xn, bias=c3.b, residual=x, act=MA_ACT_RELU, act_after_residual=True)
-                x = xn
-            pooled = self._empty(n, x.shape[1])
-            ops.token_mean(x.view(n, N, -1), pooled)
-            g = self._lin(self._lin(pooled, self.pose_mlp[0], act=MA_ACT_RELU), self.pose_mlp[1], act=MA_ACT_RELU)
-            ops.gemm(g, self.pose_out.w, pose_raw[s:s + n], bias=self.pose_out.b)
+            # pose head on the final info-sharing features (split-bf16 precision)
+            self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n])
         return raw, pose_raw
 
-    def scale_head(self, tok_feat: torch.Tensor) -> torch.Tensor:
-        """scale-token feature bf16 [1][D] -> log metric scale fp32 [1]."""
-        x = tok_feat
+    def scale_head(self, tok_feat32: torch.Tensor) -> torch.Tensor:
+        """scale-token feature fp32 [1][D] -> log metric scale fp32 [1] (split-bf16 precision)."""
+        x = tok_feat32
         for lin in self.scale_mlp[:-1]:
-            x = self._lin(x, lin, act=MA_ACT_RELU)
+            xn = self._empty(x.shape[0], lin.n, dtype=torch.float32)
+            ops.gemm(ops.split3(x), lin.w, xn, bias=lin.b, act=MA_ACT_RELU)
+            x = xn
         out = self._empty(1, self.scale_mlp[-1].n, dtype=torch.float32)
-        ops.gemm(x, self.scale_mlp[-1].w, out, bias=self.scale_mlp[-1].b)
+        ops.gemm(ops.split3(x), self.scale_mlp[-1].w, out, bias=self.scale_mlp[-1].b)
         return out.reshape(-1)[:1].contiguous()

@@ -246,9 +246,10 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                 imgs = torch.cat([v["img"][b:b + 1] for v in views], dim=0).to(self.device, torch.float32)
                 feat = eng.encode(imgs)                       # fp32 [V*N][C]   DINOv2 x_norm_patchtokens
                 fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
-                taps, final, tok = eng.info_sharing(fused, num_views, N)
-                raw, pose_raw = eng.dpt_and_pose([fused, taps[0], taps[1], final], num_views, hp, wp, height, width)
-                scale_raw = eng.scale_head(tok)
+                taps, final, final32 = eng.info_sharing(fused, num_views, N)
+                raw, pose_raw = eng.dpt_and_pose([fused, taps[0], taps[1], final], num_views, hp, wp, height, width,
+                                                 final32=final32[:num_views * N])
+                scale_raw = eng.scale_head(final32[num_views * N:])
                 per_scene.append(ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width))
         res = []
         for i in range(num_views):

@@ -282,6 +282,29 @@ def token_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows][C] (any row stride) -> bf16 [rows][3C] = [hi | lo | hi] (ma_split_bf16x3)."""
+    if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise ValueError("split3: x must be 2-D fp32 with contiguous rows")
+    rows, C_ = x.shape
+    if out is None:
+        out = torch.empty(rows, 3 * C_, device=x.device, dtype=torch.bfloat16)
+    _req(out, torch.bfloat16, "out")
+    with launch("split3"):
+        check(_lib.load().ma_split_bf16x3(x.data_ptr(), x.stride(0), out.data_ptr(), rows, C_, _stream()), "ma_split_bf16x3")
+    return out
+
+
+def token_mean_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """fp32 (n,T,C) -> (n,C)."""
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    n, T, C_ = x.shape
+    with launch("token_mean"):
+        check(_lib.load().ma_token_mean_f32(x.data_ptr(), out.data_ptr(), n, T, C_, _stream()), "ma_token_mean_f32")
+    return out
+
+
 def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Tensor, n: int, H: int, W: int):
     """Fused adaptor + decode (ma_decode_dense). raw fp32 [n*H*W, ld>=6]; returns the dict of forward() tensors."""
     if raw.dtype != torch.float32 or raw.stride(-1) != 1:
