@@ -6,7 +6,11 @@
 
 One "step" = one forward pass over one synthetic V-view 518x518 image-only scene (random-init ViT-L + 24-layer
 alternating attention + DPT + pose/scale heads), inputs resident in HBM -> per-view output dicts resident in HBM.
-N = 1 runs BASELINE config[1] (8 views, bf16, 1xB200).  Rank 0 prints ONE JSON line.
+N = 1 runs BASELINE config[1] (8 views, bf16, 1xB200).  N > 1 (one process per GPU under torchrun): ONE scene of 8*N
+views sharded by view (8 views per GPU); the 12 global-attention blocks all-gather K/V over NCCL, overlapped with the
+attention over the local keys.  Per-GPU view count is fixed ("weak"), but the algorithmic work per view
+grows with the scene (global attention is quadratic): config.tflop_per_view and roofline.step_frac carry the
+FLOP-normalised picture.  `--multi replicas` runs N independent 8-view scenes instead.  Rank 0 prints ONE JSON line.
 
   value     views/sec of `model.forward` (device-resident inputs), CUDA events, max over ranks
   e2e       views/sec of `model.infer` from pinned HOST images (H2D inside the timed region, GPU post-processing,
@@ -149,18 +153,23 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": vps, "unit": "views/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm + 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.views, args.gpus), "views": args.views, "image": IMG, "l2": "inputs >> L2"},
+        "config": {"workload": workload_name(args.views, args.gpus, args.multi), "views": args.views * args.gpus,
+                   "views_per_gpu": args.views, "image": IMG, "l2": "inputs >> L2"},
         "cpu_baseline": {"value": vps, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(v: int, gpus: int) -> str:
+def workload_name(v: int, gpus: int, multi: str = "shard") -> str:
     if gpus == 1:
         return f"MapAnything image-only, {v} views 518x518 bf16 on 1xB200 (BASELINE config[1])" if v == 8 else \
             f"MapAnything image-only, {v} views 518x518 bf16 on 1xB200"
-    return f"MapAnything image-only, {v} views 518x518 bf16 per GPU, {gpus} independent scenes on {gpus}xB200"
+    if multi == "replicas":
+        return f"MapAnything image-only, {v} views 518x518 bf16 per GPU, {gpus} independent scenes on {gpus}xB200"
+    return (f"MapAnything image-only, ONE scene of {v * gpus} views 518x518 bf16 sharded by view over {gpus}xB200 "
+            f"({v} views per GPU; global attention = local queries x all-gathered K/V over NCCL); algorithmic work per view "
+            f"grows with the scene: {gflop_per_view(v * gpus) / 1e3:.2f} TFLOP/view vs {gflop_per_view(v) / 1e3:.2f} at {v} views")
 
 
 def run_ours(args):
@@ -181,10 +190,14 @@ def run_ours(args):
     _lib.load()  # fail loudly if the CUDA library is missing
     torch.manual_seed(0)
     model = MapAnything(**mapanything_config()).to(dev).eval()  # random-init weights of the architecture
-    V = args.views
+    V = args.views  # views per GPU
+    shard = world > 1 and args.multi == "shard"
+    v_scene = V * world if shard else V  # views of the scene each forward pass works on
     host_imgs = make_host_views(V, 1234 + rank)
     dev_views = [{"img": im.to(dev), "data_norm_type": ["dinov2"]} for im in host_imgs]
     model.engine()
+    if shard:
+        model.enable_view_sharding(views_per_rank=[V] * world)
 
     def barrier():
         if world > 1:
@@ -247,26 +260,31 @@ def run_ours(args):
     e2e_vps = world * V / (e2e_ms_step * 1e-3)
 
     peak_tf, peak_hbm, peak_src = measured_peaks()
+    if os.environ.get("MA_BENCH_DUMP") and rank == 0:  # per-launch list (family, algorithmic flops, ms) for offline analysis
+        Path(os.environ["MA_BENCH_DUMP"]).write_text(json.dumps([[n, f, s.elapsed_time(e), t] for n, f, s, e, t in prof]))
     fam = {}
-    for name, flops, s, e in prof:
+    for name, flops, s, e, _tag in prof:
         d = fam.setdefault(name, [0.0, 0.0, 0])
         d[0] += flops
         d[1] += s.elapsed_time(e)
         d[2] += 1
-    gemm = fam.get("gemm", [0.0, 1e-9, 0])
+    gemm = [a + b for a, b in zip(fam.get("gemm", [0.0, 1e-9, 0]), fam.get("conv3x3", [0.0, 0.0, 0]))]  # one kernel
     achieved = gemm[0] / (gemm[1] * 1e-3) / 1e12
-    step_tf = V * gflop_per_view(V) * 1e9 / (ms_step * 1e-3) / 1e12
+    step_tf = V * gflop_per_view(v_scene) * 1e9 / (ms_step * 1e-3) / 1e12  # per GPU
 
+    outs = e2e_step()  # every rank: the sharded step is collective
+    d2h = sum(o.numel() * o.element_size() for o in outs) * world
+    h2d = sum(im.numel() * 4 for im in host_imgs) * world
     if rank == 0:
         cpu = cpu_baseline(V)
-        h2d = sum(im.numel() * 4 for im in host_imgs)
-        outs = e2e_step()
-        d2h = sum(o.numel() * o.element_size() for o in outs)
         line = {
             "metric": METRIC, "value": vps, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(V, world), "views": V, "image": IMG, "weights": "random-init",
+            "config": {"workload": workload_name(V, world, args.multi), "views": V * world, "views_per_gpu": V,
+                       "scene_views": v_scene, "tflop_per_view": gflop_per_view(v_scene) / 1e3, "image": IMG,
+                       "weights": "random-init", "parallelism": "single" if world == 1 else
+                       (f"view-shard x{world} + K/V all-gather" if shard else f"replicas x{world}"),
                        "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
@@ -314,8 +332,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--views", type=int, default=8, help="views per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--multi", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: one scene of views*N views sharded by view (default) or N independent scenes")
     ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")
     args = ap.parse_args()
     if args.impl == "reference":

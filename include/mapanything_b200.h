@@ -81,9 +81,20 @@ typedef struct ma_gemm_epilogue {
  * relu(x1) and the fused skip x0 + x1 come out of one launch). */
 #define MA_GEMM_RELU_OUT_BEFORE_RESIDUAL 2
 
-/* block_n: 0 = choose automatically, else one of 64 / 128 / 256. */
+/* block_n: 0 = choose automatically (wave count x measured per-tile cost); 64 / 128 / 256 = one CTA per 128 x block_n
+ * tile; 2128 / 2256 = a CTA pair (tcgen05 cta_group::2, cluster of 2) per 256 x 128 / 256 x 256 tile.  Setting the
+ * environment variable MA_GEMM_2CTA=0 removes the pair kernels from the automatic choice. */
 int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                  const ma_gemm_epilogue* epi, int block_n, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution over NHWC bf16 (n,H,W,C) as an IMPLICIT GEMM on the same kernel: the A operand of
+ * each (pixel tile, tap) is one 4-D TMA box of the input shifted by the tap, the zero padding is TMA out-of-bounds fill;
+ * no im2col matrix exists.  w: [Cout][9*C] bf16, k = (ky*3+kx)*C + c (row stride ldw).  Output rows are pixel indices
+ * (i*H + y)*W + x; the epilogue is the one of ma_gemm_bf16 (row remapping unsupported).  Replaces the cuDNN 3x3 convs of
+ * the DPT feature head / regressor / pose head (reference model.py:1302-1338, :1449-1457) and of
+ * the dense geometric-input encoders (model.py:753-1010; App. A.2). */
+int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const void* w, int64_t ldw, int Cout,
+                    const ma_gemm_epilogue* epi, int block_n, void* stream);
 
 /* ---- Attention forward (head_dim 64, non-causal) ---------------------------------------------
  * Replaces the attention of the DINOv2 blocks (reference dinov2/layers/attention.py:53-90,
@@ -99,6 +110,32 @@ int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, con
                      int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
                      int o_col0, int num_seqs, int num_heads, int q_len, int kv_len, int64_t q_seq_stride,
                      int64_t kv_seq_stride, float softmax_scale, void* stream);
+
+/* Extended form for the view-sharded global attention (the reference runs it as one SDPA call over all
+ * views, uniception info-sharing invoked at model.py:1532-1542):
+ *  - the keys/values of a sequence may be n_segments row ranges [seg_row0[i], seg_row0[i] + seg_len[i]) (relative to the
+ *    sequence's first kv row, sum of seg_len == kv_len): one range per source rank of the all-gathered K/V buffer;
+ *  - MA_ATTN_STATE_OUT: instead of `out`, write the online-softmax state after the last key: state_o = normalised
+ *    output (fp32 [q_rows][ld_state_o], head h at column 64 h) and state_m [q_rows][num_heads] = running maximum
+ *    (raw score units) + log2(running sum) / (softmax_scale * log2 e);
+ *  - MA_ATTN_STATE_IN: resume from such a state (local keys first, remote keys when the all-gather has landed).
+ * ext == NULL is ma_attention_fwd. */
+#define MA_ATTN_MAX_SEGMENTS 16
+#define MA_ATTN_STATE_IN 1
+#define MA_ATTN_STATE_OUT 2
+typedef struct ma_attn_ext {
+  int32_t n_segments; /* 0 = single range [0, kv_len) */
+  int32_t flags;      /* MA_ATTN_STATE_* */
+  int32_t seg_row0[MA_ATTN_MAX_SEGMENTS];
+  int32_t seg_len[MA_ATTN_MAX_SEGMENTS];
+  float* state_o;
+  int64_t ld_state_o;
+  float* state_m;
+} ma_attn_ext;
+int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
+                        int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
+                        int o_col0, int num_seqs, int num_heads, int q_len, int kv_len, int64_t q_seq_stride,
+                        int64_t kv_seq_stride, float softmax_scale, const ma_attn_ext* ext, void* stream);
 
 /* ---- HBM-bound stage kernels ------------------------------------------------------------------ */
 
@@ -152,6 +189,42 @@ int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* st
 int ma_decode_dense(const float* raw, int ld_raw, const float* pose_raw, const float* scale_raw, int n, int HW,
                     float* pts3d, float* pts3d_cam, float* rays, float* depth, float* conf, float* logits, uint8_t* mask,
                     float* cam_trans, float* cam_quats, float* scale_out, void* stream);
+
+/* ---- infer() input preprocessing (reference mapanything/utils/inference.py:202-291) ------------ */
+
+/* get_rays_in_camera_frame(normalize_to_unit_sphere=True) (geometry.py:186-241): K [B][3][3] -> unit rays (B,H,W,3). */
+int ma_rays_from_intrinsics(const float* K, float* rays, int B, int H, int W, void* stream);
+/* rays / (|rays| + 1e-8) (inference.py:238-241). */
+int ma_normalize_rays(const float* in, float* out, int64_t pixels, void* stream);
+/* depth_along_ray = |depth_z * ray / ray_z| (inference.py:243-251). */
+int ma_depth_z_to_along_ray(const float* depth_z, const float* rays, float* out, int64_t pixels, void* stream);
+/* (B,4,4) cam2world matrices -> quats (B,4; xyzw, w >= 0; geometry.py:655-742) and translations (B,3). */
+int ma_pose_to_quat_trans(const float* poses, float* quats, float* trans, int B, void* stream);
+
+/* ---- geometric-input fusion (reference model.py:647-1261) -------------------------- */
+
+/* nn.PixelUnshuffle(patch) of an NHWC fp32 map (n,H,W,cin) (ray directions model.py:803-811 / depth :946-971) written as
+ * the split-bf16 activation [hi | lo | hi] of an NHWC token map (n,H/p,W/p,3*cpad), channel k = c*p*p + dy*p + dx zero
+ * padded to cpad (multiple of 8).  mode 1 (depth): v /= factor[i]; v = v/max(|v|,1e-8) * log1p(|v|) (geometry.py:1666-1679). */
+int ma_unshuffle_split(const float* in, void* out, int n, int H, int W, int cin, int patch, int cpad, int mode,
+                       const float* factor, void* stream);
+
+/* normalize_depth_using_non_zero_pixels (geometry.py:1523-1555): factor[i] = mean of the positive depths of view i
+ * (clipped at 1e-8); log_factor8[i] = (log(factor + 1e-8), 0 x 7): the K-padded input of the depth-scale encoder. */
+int ma_depth_factor(const float* depth, int n, int64_t per_view, float* factor, float* log_factor8, void* stream);
+
+/* Camera-pose inputs: poses relative to view 0 (model.py:647-751, geometry.py:814-852), identity for views without a
+ * pose (has_pose[v] == 0), translations normalised by the mean non-zero norm across views (geometry.py:1558-1595).
+ * quats [V][4] xyzw, trans [V][3]; outputs K-padded to 8 columns: quats8, trans8, log_scale8 (log(factor + 1e-8)). */
+int ma_pose_inputs(const float* quats, const float* trans, const uint8_t* has_pose, int V, float* quats8, float* trans8,
+                   float* log_scale8, void* stream);
+
+/* In-place fusion adds on the fp32 encoder features feat [V*N][C] (model.py:820-825, :1003-1008, :1124-1129):
+ * feat[v*N+t] += dense_a[a_slot[v]*N+t] + dense_b[b_slot[v]*N+t] + sum_j gw[j*V+v] * g_j[v]; slot -1 / NULL = absent;
+ * g3 (depth-scale features) has one row per b_slot and is read at g3[b_slot[v]]. */
+int ma_fuse_add(float* feat, int V, int N, int C, const float* dense_a, const int* a_slot, const float* dense_b,
+                const int* b_slot, const float* g0, const float* g1, const float* g2, const float* g3, const float* gw,
+                void* stream);
 
 /* ---- infer() post-processing (reference mapanything/utils/inference.py:294-480, host numpy there) ---- */
 

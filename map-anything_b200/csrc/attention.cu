@@ -31,10 +31,34 @@ constexpr int ATT_TMEM_COLS = 256;            // S: [0,128)  PV0: [128,192)  PV1
 struct AttnParams {
   __nv_bfloat16* out;
   int64_t ldo;
-  int q_len, kv_len;
+  int q_len;
   int64_t q_seq_stride, kv_seq_stride;  // rows between consecutive sequences
   int q_col0, k_col0, v_col0, o_col0;   // column of head 0 in the respective matrices
   float scale_log2;                     // softmax scale * log2(e)
+  // The keys of a sequence are the concatenation of n_segs row ranges [seg_row0[s], seg_row0[s] + seg_len[s]) (relative
+  // to the sequence's first kv row): one range for ordinary attention, one per source rank for the view-sharded
+  // global attention whose K/V were all-gathered into per-rank slots of a padded buffer.
+  int n_segs, n_kv_tiles;
+  int seg_row0[MA_ATTN_MAX_SEGMENTS];
+  int seg_len[MA_ATTN_MAX_SEGMENTS];
+  // Online-softmax state carried between launches (fp32): o = normalised output so far, m = reference maximum in raw
+  // score units with the running sum folded in (m' = m + log2(l) / scale_log2), i.e. the state (o, m', l = 1).
+  float* state_o;
+  int64_t ld_state_o;
+  float* state_m;  // [q_rows][num_heads]
+  int num_heads;
+  int flags;  // MA_ATTN_STATE_IN / MA_ATTN_STATE_OUT
+};
+
+// Cursor over the kv tiles of all segments, in segment order.
+struct KvCursor {
+  int seg = 0, jj = 0;
+  __device__ __forceinline__ int row0(const AttnParams& p) const { return p.seg_row0[seg] + jj * ATT_BN; }
+  __device__ __forceinline__ int valid(const AttnParams& p) const { return p.seg_len[seg] - jj * ATT_BN; }
+  __device__ __forceinline__ void next(const AttnParams& p) {
+    if ((jj + 1) * ATT_BN < p.seg_len[seg]) ++jj;
+    else { ++seg; jj = 0; }
+  }
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -64,7 +88,7 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
   const int q0 = blockIdx.x * ATT_BM;
   const int head = blockIdx.y;
   const int seq = blockIdx.z;
-  const int n_kv_tiles = (p.kv_len + ATT_BN - 1) / ATT_BN;
+  const int n_kv_tiles = p.n_kv_tiles;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("[ma] attention: dynamic smem base not 1024-byte aligned\n");
@@ -111,15 +135,17 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
       const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
       mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
       tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
-      for (int j = 0; j < n_kv_tiles; ++j) {
+      KvCursor cur;
+      for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
         const int st = j % ATT_STAGES;
         const uint32_t ph = (j / ATT_STAGES) & 1;
+        const int row = kv_row0 + cur.row0(p);
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, kv_row0 + j * ATT_BN);
+        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, row);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
-        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, kv_row0 + j * ATT_BN);
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, row);
       }
     }
   } else if (warp == 1) {
@@ -179,6 +205,18 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
     float m_run = -INFINITY;  // running max of raw scores
     float l_run = 0.f;
     float alpha_prev = 1.f;
+    const int q_idx = q0 + row;
+    const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
+    if ((p.flags & MA_ATTN_STATE_IN) && q_idx < p.q_len) {
+      const float4* so = reinterpret_cast<const float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D);
+#pragma unroll
+      for (int i = 0; i < ATT_D / 4; ++i) {
+        const float4 t = so[i];
+        o_acc[4 * i] = t.x; o_acc[4 * i + 1] = t.y; o_acc[4 * i + 2] = t.z; o_acc[4 * i + 3] = t.w;
+      }
+      m_run = p.state_m[q_grow * p.num_heads + head];
+      l_run = 1.f;
+    }
     const uint32_t sw = static_cast<uint32_t>(row & 7);
     uint8_t* p_row = sP + row * 128;
 
@@ -199,8 +237,9 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
       if (lane == 0) mbar_arrive(&pv_empty[buf]);
     };
 
-    for (int j = 0; j < n_kv_tiles; ++j) {
-      const int kv_valid = p.kv_len - j * ATT_BN;  // >= 1; < 128 only on the last tile
+    KvCursor cur;
+    for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
+      const int kv_valid = cur.valid(p);  // >= 1; < 128 only on the last tile of a segment
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       // pass 1: row max
@@ -263,10 +302,16 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
     }
     fold_pv(n_kv_tiles - 1, alpha_prev);
 
-    const int q_idx = q0 + row;
-    if (q_idx < p.q_len) {
+    if (q_idx < p.q_len && (p.flags & MA_ATTN_STATE_OUT)) {
       const float inv_l = 1.0f / l_run;
-      __nv_bfloat16* optr = p.out + (static_cast<int64_t>(seq) * p.q_seq_stride + q_idx) * p.ldo + p.o_col0 + head * ATT_D;
+      float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D);
+#pragma unroll
+      for (int i = 0; i < ATT_D / 4; ++i)
+        so[i] = make_float4(o_acc[4 * i] * inv_l, o_acc[4 * i + 1] * inv_l, o_acc[4 * i + 2] * inv_l, o_acc[4 * i + 3] * inv_l);
+      p.state_m[q_grow * p.num_heads + head] = m_run + __log2f(l_run) / p.scale_log2;
+    } else if (q_idx < p.q_len) {
+      const float inv_l = 1.0f / l_run;
+      __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D;
 #pragma unroll
       for (int q = 0; q < ATT_D / 8; ++q) {
         uint4 pk = make_uint4(pack_bf16x2(o_acc[8 * q + 0] * inv_l, o_acc[8 * q + 1] * inv_l),
@@ -292,14 +337,56 @@ extern "C" int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int 
                                 int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
                                 int64_t ldo, int o_col0, int num_seqs, int num_heads, int q_len, int kv_len,
                                 int64_t q_seq_stride, int64_t kv_seq_stride, float softmax_scale, void* stream) {
+  return ma_attention_fwd_ex(q, ldq, q_rows, q_col0, k, ldk, kv_rows, k_col0, v, ldv, v_col0, out, ldo, o_col0, num_seqs,
+                             num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, softmax_scale, nullptr, stream);
+}
+
+extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
+                                   int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out,
+                                   int64_t ldo, int o_col0, int num_seqs, int num_heads, int q_len, int kv_len,
+                                   int64_t q_seq_stride, int64_t kv_seq_stride, float softmax_scale,
+                                   const ma_attn_ext* ext, void* stream) {
   using namespace ma;
-  MA_REQUIRE(q && k && v && out, "ma_attention_fwd: null pointer");
+  MA_REQUIRE(q && k && v, "ma_attention_fwd: null pointer");
+  const int flags = ext ? ext->flags : 0;
+  MA_REQUIRE(out || (flags & MA_ATTN_STATE_OUT), "ma_attention_fwd: null output");
   MA_REQUIRE(num_seqs > 0 && num_heads > 0 && q_len > 0 && kv_len > 0, "ma_attention_fwd: bad sizes");
+  AttnParams p;
+  p.n_segs = 1;
+  p.seg_row0[0] = 0;
+  p.seg_len[0] = kv_len;
+  if (ext && ext->n_segments > 0) {
+    MA_REQUIRE(ext->n_segments <= MA_ATTN_MAX_SEGMENTS, "ma_attention_fwd: more than %d kv segments", MA_ATTN_MAX_SEGMENTS);
+    int64_t total = 0;
+    for (int s = 0; s < ext->n_segments; ++s) {
+      MA_REQUIRE(ext->seg_len[s] > 0 && ext->seg_row0[s] >= 0, "ma_attention_fwd: kv segment %d is empty / negative", s);
+      p.seg_row0[s] = ext->seg_row0[s];
+      p.seg_len[s] = ext->seg_len[s];
+      total += ext->seg_len[s];
+    }
+    MA_REQUIRE(total == kv_len, "ma_attention_fwd: kv segments sum to %lld, kv_len is %d", (long long)total, kv_len);
+    p.n_segs = ext->n_segments;
+  }
+  p.n_kv_tiles = 0;
+  int kv_extent = 0;
+  for (int s = 0; s < p.n_segs; ++s) {
+    p.n_kv_tiles += (p.seg_len[s] + ATT_BN - 1) / ATT_BN;
+    kv_extent = p.seg_row0[s] + p.seg_len[s] > kv_extent ? p.seg_row0[s] + p.seg_len[s] : kv_extent;
+  }
+  p.state_o = nullptr; p.state_m = nullptr; p.ld_state_o = 0;
+  if (flags & (MA_ATTN_STATE_IN | MA_ATTN_STATE_OUT)) {
+    MA_REQUIRE(ext->state_o && ext->state_m && ext->ld_state_o % 4 == 0 && ext->ld_state_o >= (int64_t)num_heads * ATT_D &&
+                   (reinterpret_cast<uintptr_t>(ext->state_o) & 15) == 0,
+               "ma_attention_fwd: softmax state buffers missing / misaligned");
+    p.state_o = ext->state_o; p.state_m = ext->state_m; p.ld_state_o = ext->ld_state_o;
+  }
+  p.num_heads = num_heads;
+  p.flags = flags;
   MA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
                  v_col0 % 8 == 0 && o_col0 % 8 == 0,
              "ma_attention_fwd: strides / column offsets must be multiples of 8 elements");
   MA_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "ma_attention_fwd: out not 16-byte aligned");
-  MA_REQUIRE((int64_t)(num_seqs - 1) * q_seq_stride + q_len <= q_rows && (int64_t)(num_seqs - 1) * kv_seq_stride + kv_len <= kv_rows,
+  MA_REQUIRE((int64_t)(num_seqs - 1) * q_seq_stride + q_len <= q_rows && (int64_t)(num_seqs - 1) * kv_seq_stride + kv_extent <= kv_rows,
              "ma_attention_fwd: sequences exceed the q / kv row counts");
   MA_REQUIRE(q_col0 + num_heads * ATT_D <= ldq && k_col0 + num_heads * ATT_D <= ldk && v_col0 + num_heads * ATT_D <= ldv &&
                  o_col0 + num_heads * ATT_D <= ldo,
@@ -331,11 +418,9 @@ extern "C" int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int 
                                        ATT_SMEM_BYTES));
     configured = true;
   }
-  AttnParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.q_len = q_len;
-  p.kv_len = kv_len;
   p.q_seq_stride = q_seq_stride;
   p.kv_seq_stride = kv_seq_stride;
   p.q_col0 = q_col0;

@@ -9,13 +9,12 @@
 // MMA main loop of tile i+1.  Tiles are scheduled statically, M fastest, so CTAs running at the same
 // time share the same weight tile in L2.  Ragged M / N / K edges are handled by TMA out-of-bounds
 // zero fill on the load side and predicated stores on the store side.
-#include "host_common.h"
-#include "ptx.cuh"
+#include <stdlib.h>
+
+#include "gemm_common.cuh"
 
 namespace ma {
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
 
@@ -30,148 +29,10 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BN;                                   // 128 / 256 / 512: powers of two
 };
 
-// 32 consecutive output columns of one row: fused epilogue + store.
-__device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep, const uint32_t (&acc)[32], int m,
-                                                     int col0, int N) {
-  int out_row = m;
-  if (ep.rows_per_group_in > 0) {
-    int g = m / ep.rows_per_group_in;
-    out_row = g * ep.rows_per_group_out + ep.row_offset_out + (m - g * ep.rows_per_group_in);
-  }
-  const int res_row = ep.residual_row_mod > 0 ? (m % ep.residual_row_mod) : out_row;
-  const int nvalid = min(32, N - col0);
-
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-
-  if (nvalid == 32) {
-    if (ep.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-      }
-    }
-    const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
-    const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
-    if (!act_late) {
-      if (ep.act == MA_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      } else if (ep.act == MA_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-      }
-    }
-    if (ep.out_relu && relu_early) {
-      uint4* o4 =
-          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
-    }
-    if (ep.colscale) {
-      const float4* s4 = reinterpret_cast<const float4*>(ep.colscale + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 s = __ldg(s4 + j);
-        v[4 * j + 0] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
-      }
-    }
-    if (ep.residual) {
-      if (ep.residual_dtype == MA_F32) {
-        const float4* r4 =
-            reinterpret_cast<const float4*>(static_cast<const float*>(ep.residual) + (size_t)res_row * ep.ldr + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 r = r4[j];
-          v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-        }
-      } else {
-        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ep.residual) +
-                                                         (size_t)res_row * ep.ldr + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 r = r4[j];
-          v[8 * j + 0] += bf16_lo(r.x); v[8 * j + 1] += bf16_hi(r.x);
-          v[8 * j + 2] += bf16_lo(r.y); v[8 * j + 3] += bf16_hi(r.y);
-          v[8 * j + 4] += bf16_lo(r.z); v[8 * j + 5] += bf16_hi(r.z);
-          v[8 * j + 6] += bf16_lo(r.w); v[8 * j + 7] += bf16_hi(r.w);
-        }
-      }
-    }
-    if (act_late) {
-      if (ep.act == MA_ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-      } else if (ep.act == MA_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-      }
-    }
-    if (ep.out_dtype == MA_F32) {
-      float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (size_t)out_row * ep.ldo + col0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-      uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + (size_t)out_row * ep.ldo + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-    }
-    if (ep.out_relu && !relu_early) {
-      uint4* o4 =
-          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
-                           pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
-    }
-  } else {
-    // ragged N edge: scalar path (fully unrolled + predicated so v[] stays in registers)
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (j >= nvalid) continue;
-      const int n = col0 + j;
-      float x = v[j];
-      const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
-      const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
-      if (ep.bias) x += __ldg(ep.bias + n);
-      if (!act_late) {
-        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
-        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
-      }
-      if (ep.out_relu && relu_early)
-        static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
-      if (ep.colscale) x *= __ldg(ep.colscale + n);
-      if (ep.residual) {
-        if (ep.residual_dtype == MA_F32) x += static_cast<const float*>(ep.residual)[(size_t)res_row * ep.ldr + n];
-        else x += __bfloat162float(static_cast<const __nv_bfloat16*>(ep.residual)[(size_t)res_row * ep.ldr + n]);
-      }
-      if (act_late) {
-        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
-        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
-      }
-      if (ep.out_dtype == MA_F32) static_cast<float*>(ep.out)[(size_t)out_row * ep.ldo + n] = x;
-      else static_cast<__nv_bfloat16*>(ep.out)[(size_t)out_row * ep.ldo + n] = __float2bfloat16(x);
-      if (ep.out_relu && !relu_early)
-        static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
-    }
-  }
-}
-
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                         const ma_gemm_epilogue ep, const int M, const int N, const int K) {
+                         const ma_gemm_epilogue ep, const int M, const int N, const int K, const ConvGeom cg) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -211,24 +72,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_per_img = cg.tiles_x * cg.tiles_y;
+  const int tiles_m = cg.mode ? (M / (cg.H * cg.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;
   const int tiles_n = (N + BN - 1) / BN;
   const int total_tiles = tiles_m * tiles_n;
-  const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  const int kblocks = cg.mode ? 9 * cg.cblocks : (K + GEMM_BK - 1) / GEMM_BK;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m0 = (t % tiles_m) * GEMM_BM;
+        const int tm = t % tiles_m;
         const int n0 = (t / tiles_m) * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_w, &bar_full[stage], kb * GEMM_BK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (cg.mode) {
+          const int img = tm / tiles_per_img;
+          const int r = tm - img * tiles_per_img;
+          const int y0 = (r / cg.tiles_x) * cg.bh, x0 = (r % cg.tiles_x) * cg.bw;
+          const uint32_t bytes = static_cast<uint32_t>(cg.bw * cg.bh * 128) + Cfg::B_BYTES;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            for (int cb = 0; cb < cg.cblocks; ++cb) {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&bar_full[stage], bytes);
+              tma_load_4d(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], cb * GEMM_BK, x0 + dx, y0 + dy, img);
+              tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_w, &bar_full[stage], tap * cg.C + cb * GEMM_BK, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          const int m0 = tm * GEMM_BM;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], kb * GEMM_BK, m0);
+            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_w, &bar_full[stage], kb * GEMM_BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -268,11 +148,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int m0 = (t % tiles_m) * GEMM_BM;
+      const int tm = t % tiles_m;
       const int n0 = (t / tiles_m) * BN;
+      // output row of this thread's accumulator lane: tile row r = quarter*32 + lane
+      int m;
+      bool row_ok;
+      if (cg.mode) {
+        const int img = tm / tiles_per_img;
+        const int rr = tm - img * tiles_per_img;
+        const int r = quarter * 32 + lane;
+        const int y = (rr / cg.tiles_x) * cg.bh + r / cg.bw, x = (rr % cg.tiles_x) * cg.bw + r % cg.bw;
+        row_ok = r < cg.bw * cg.bh && y < cg.H && x < cg.W;
+        m = (img * cg.H + y) * cg.W + x;
+      } else {
+        m = tm * GEMM_BM + quarter * 32 + lane;
+        row_ok = m < M;
+      }
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col0 = n0 + half * (BN / 2) + c;
@@ -280,7 +173,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (m < M && col0 < N) epilogue_store_chunk(ep, v, m, col0, N);
+        if (row_ok && col0 < N) epilogue_store_chunk(ep, v, m, col0, N);
       }
       tc_fence_before();
       __syncwarp();
@@ -298,7 +191,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const ConvGeom& cg = ConvGeom{}) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -306,16 +199,26 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const ma_ge
                                        Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int tiles_m = cg.mode ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles = tiles_m * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, ep, M, N, K);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, ep, M, N, K, cg);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
 
-static int pick_block_n(int M, int N) {
+int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
+                     cudaStream_t stream, const ConvGeom& cg);  // gemm2.cu
+
+// Tile configuration codes accepted as `block_n`: 64 / 128 / 256 = one CTA per 128 x block_n tile (gemm.cu);
+// MA_GEMM_2CTA + 128 / 256 = CTA pair per 256 x bn tile (gemm2.cu).
+constexpr int MA_GEMM_2CTA = 2000;
+
+constexpr double G2_COST_256 = 0.82, G2_COST_128 = 0.56;
+
+static int pick_block_n(int M, int N, int tiles_m_override = 0) {
   const int sms = device_sm_count();
-  const int tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles_m = tiles_m_override ? tiles_m_override : (M + GEMM_BM - 1) / GEMM_BM;
   int best = 128;
   double best_cost = 1e30;
   const int cands[3] = {256, 128, 64};
@@ -328,10 +231,109 @@ static int pick_block_n(int M, int N) {
     const double cost = waves * (bn == 256 ? 1.0 : (bn == 128 ? 0.66 : 0.58));
     if (cost < best_cost) { best_cost = cost; best = bn; }
   }
+  // CTA pairs: 256 x bn tiles over sms/2 clusters.  Per-tile cost relative to a 1-CTA 128x256 tile (measured on B200,
+  // tools/bench_kernels.py): the pair tile does twice the work at the full tensor rate (operand traffic per SM is 2/3).
+  static const bool use_pairs = [] {
+    const char* e = getenv("MA_GEMM_2CTA");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int pcands[2] = {256, 128};
+  for (int i = 0; use_pairs && i < 2; ++i) {
+    const int bn = pcands[i];
+    const int tiles = ((tiles_m + 1) / 2) * ((N + bn - 1) / bn);
+    const int clusters = sms / 2;
+    const int waves = (tiles + clusters - 1) / clusters;
+    const double cost = waves * (bn == 256 ? G2_COST_256 : G2_COST_128);
+    if (cost < best_cost) { best_cost = cost; best = MA_GEMM_2CTA + bn; }
+  }
   return best;
 }
 
+static bool valid_block_code(int bn) {
+  return bn == 64 || bn == 128 || bn == 256 || bn == MA_GEMM_2CTA + 128 || bn == MA_GEMM_2CTA + 256;
+}
+
 }  // namespace ma
+
+static int check_epilogue(const ma_gemm_epilogue* epi, int N, const char* who) {
+  if (N % 32 == 0) {
+    const int64_t oalign = epi->out_dtype == MA_F32 ? 4 : 8;
+    MA_REQUIRE(epi->ldo % oalign == 0 && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0,
+               "%s: output not 16-byte aligned (ldo=%lld)", who, (long long)epi->ldo);
+    if (epi->residual) {
+      const int64_t ralign = epi->residual_dtype == MA_F32 ? 4 : 8;
+      MA_REQUIRE(epi->ldr % ralign == 0 && (reinterpret_cast<uintptr_t>(epi->residual) & 15) == 0,
+                 "%s: residual not 16-byte aligned", who);
+    }
+    if (epi->out_relu)
+      MA_REQUIRE(epi->ldo_relu % 8 == 0 && (reinterpret_cast<uintptr_t>(epi->out_relu) & 15) == 0,
+                 "%s: out_relu not 16-byte aligned", who);
+    if (epi->bias) MA_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "%s: bias not 16-byte aligned", who);
+    if (epi->colscale)
+      MA_REQUIRE((reinterpret_cast<uintptr_t>(epi->colscale) & 15) == 0, "%s: colscale not 16-byte aligned", who);
+  } else {
+    // A ragged last N chunk takes the scalar store path, full chunks before it still use vector stores.
+    const int64_t oalign = epi->out_dtype == MA_F32 ? 4 : 8;
+    MA_REQUIRE(N <= 32 || (epi->ldo % oalign == 0 && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0),
+               "%s: output not 16-byte aligned (ldo=%lld)", who, (long long)epi->ldo);
+  }
+  return MA_OK;
+}
+
+extern "C" int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const void* w, int64_t ldw, int Cout,
+                               const ma_gemm_epilogue* epi, int block_n, void* stream) {
+  using namespace ma;
+  MA_REQUIRE(x && w && epi && epi->out, "ma_conv3x3_bf16: null pointer");
+  MA_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "ma_conv3x3_bf16: bad shape");
+  MA_REQUIRE(C % 8 == 0 && ldw % 8 == 0 && ldw >= 9 * (int64_t)C, "ma_conv3x3_bf16: C / ldw must be multiples of 8, ldw >= 9C");
+  MA_REQUIRE((int64_t)n * H * W < (1ll << 31), "ma_conv3x3_bf16: too many pixels");
+  MA_REQUIRE(epi->rows_per_group_in == 0, "ma_conv3x3_bf16: row remapping is not supported");
+  int rc = check_epilogue(epi, Cout, "ma_conv3x3_bf16");
+  if (rc != MA_OK) return rc;
+
+  // pixel box of one M tile: maximise useful rows / 128 over all bw x bh <= 128 boxes
+  ConvGeom cg;
+  cg.mode = 1; cg.H = H; cg.W = W; cg.C = C;
+  double best = -1.0;
+  for (int bw = 1; bw <= 128 && bw <= W; ++bw) {
+    int bh = 128 / bw;
+    if (bh > H) bh = H;
+    const int tx = (W + bw - 1) / bw, ty = (H + bh - 1) / bh;
+    const double eff = (double)W * H / ((double)tx * ty * 128.0);
+    if (eff > best + 1e-9) { best = eff; cg.bw = bw; cg.bh = bh; cg.tiles_x = tx; cg.tiles_y = ty; }
+  }
+  cg.cblocks = (C + GEMM_BK - 1) / GEMM_BK;
+  const int M = n * H * W;
+  const int tiles_m = n * cg.tiles_x * cg.tiles_y;
+  int bn = block_n ? block_n : pick_block_n(M, Cout, tiles_m);
+  MA_REQUIRE(valid_block_code(bn), "ma_conv3x3_bf16: bad block_n %d", block_n);
+  const bool pair = bn > MA_GEMM_2CTA;
+  if (pair) bn -= MA_GEMM_2CTA;
+
+  CUtensorMap tx, tw;
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)n};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {GEMM_BK, (uint32_t)cg.bw, (uint32_t)cg.bh, 1};
+    rc = make_tmap_bf16(&tx, x, 4, dims, strides, box);
+    if (rc != MA_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)Cout};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(pair ? bn / 2 : bn)};
+    rc = make_tmap_bf16(&tw, w, 2, dims, strides, box);
+    if (rc != MA_OK) return rc;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int K = 9 * C;
+  if (pair) return launch_gemm_2cta(bn, tx, tw, *epi, M, Cout, K, s, cg);
+  switch (bn) {
+    case 256: return launch_gemm<256>(tx, tw, *epi, M, Cout, K, s, cg);
+    case 128: return launch_gemm<128>(tx, tw, *epi, M, Cout, K, s, cg);
+    default: return launch_gemm<64>(tx, tw, *epi, M, Cout, K, s, cg);
+  }
+}
 
 extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                             const ma_gemm_epilogue* epi, int block_n, void* stream) {
@@ -341,30 +343,14 @@ extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t l
   MA_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "ma_gemm_bf16: K/ldx/ldw must be multiples of 8 (K=%d ldx=%lld ldw=%lld)",
              K, (long long)ldx, (long long)ldw);
   MA_REQUIRE(ldx >= K && ldw >= K, "ma_gemm_bf16: leading dimension smaller than K");
-  if (N % 32 == 0) {
-    const int64_t oalign = epi->out_dtype == MA_F32 ? 4 : 8;
-    MA_REQUIRE(epi->ldo % oalign == 0 && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0,
-               "ma_gemm_bf16: output not 16-byte aligned (ldo=%lld)", (long long)epi->ldo);
-    if (epi->residual) {
-      const int64_t ralign = epi->residual_dtype == MA_F32 ? 4 : 8;
-      MA_REQUIRE(epi->ldr % ralign == 0 && (reinterpret_cast<uintptr_t>(epi->residual) & 15) == 0,
-                 "ma_gemm_bf16: residual not 16-byte aligned");
-    }
-    if (epi->out_relu)
-      MA_REQUIRE(epi->ldo_relu % 8 == 0 && (reinterpret_cast<uintptr_t>(epi->out_relu) & 15) == 0,
-                 "ma_gemm_bf16: out_relu not 16-byte aligned");
-    if (epi->bias) MA_REQUIRE((reinterpret_cast<uintptr_t>(epi->bias) & 15) == 0, "ma_gemm_bf16: bias not 16-byte aligned");
-    if (epi->colscale)
-      MA_REQUIRE((reinterpret_cast<uintptr_t>(epi->colscale) & 15) == 0, "ma_gemm_bf16: colscale not 16-byte aligned");
-  }
-  // A ragged last N chunk takes the scalar store path, full chunks before it still use vector stores.
-  if (N % 32 != 0) {
-    const int64_t oalign = epi->out_dtype == MA_F32 ? 4 : 8;
-    MA_REQUIRE(N <= 32 || (epi->ldo % oalign == 0 && (reinterpret_cast<uintptr_t>(epi->out) & 15) == 0),
-               "ma_gemm_bf16: output not 16-byte aligned (ldo=%lld)", (long long)epi->ldo);
+  {
+    int rc = check_epilogue(epi, N, "ma_gemm_bf16");
+    if (rc != MA_OK) return rc;
   }
   int bn = block_n ? block_n : pick_block_n(M, N);
-  MA_REQUIRE(bn == 64 || bn == 128 || bn == 256, "ma_gemm_bf16: block_n must be 0/64/128/256, got %d", block_n);
+  MA_REQUIRE(valid_block_code(bn), "ma_gemm_bf16: bad block_n %d", block_n);
+  const bool pair = bn > MA_GEMM_2CTA;
+  if (pair) bn -= MA_GEMM_2CTA;
 
   CUtensorMap tx, tw;
   {
@@ -377,11 +363,12 @@ extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t l
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {GEMM_BK, (uint32_t)bn};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(pair ? bn / 2 : bn)};
     int rc = make_tmap_bf16(&tw, w, 2, dims, strides, box);
     if (rc != MA_OK) return rc;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (pair) return launch_gemm_2cta(bn, tx, tw, *epi, M, N, K, s, ConvGeom{});
   switch (bn) {
     case 256: return launch_gemm<256>(tx, tw, *epi, M, N, K, s);
     case 128: return launch_gemm<128>(tx, tw, *epi, M, N, K, s);

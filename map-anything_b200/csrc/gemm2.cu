@@ -1,0 +1,222 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the persistent bf16 GEMM / implicit 3x3 conv:  Y = epilogue(X . W^T)
+//
+// A cluster of two CTAs (the two SMs of a TPC) owns one 256 x BN output tile.  CTA r loads A rows [m0 + 128 r, +128) and
+// B rows [n0 + BN/2 * r, + BN/2) of every K block; ONE thread of the leader CTA issues tcgen05.mma.cta_group::2 with
+// M = 256, N = BN: each SM's tensor core multiplies its own 128 A rows with all BN columns, reading the other half of
+// B from the peer SM's shared memory.  Per MMA an SM therefore reads 128x16 A + BN/2 x16 B instead of 128x16 + BNx16:
+// at BN = 256 that is 8 KB instead of 12 KB per 128 tensor-core cycles, which is what keeps the 1-CTA kernel (gemm.cu)
+// below the tensor pipe's rate (shared-memory operand bandwidth, B300_MICROARCH "tcgen05 floor").
+//
+//   warp 0 (both CTAs) : TMA producer; transaction bytes of both CTAs are credited to the LEADER's full barrier
+//   warp 1 (leader)    : MMA issuer; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
+//   warp 2 (both)      : TMEM allocator (cta_group::2)
+//   warps 4..11 (both) : epilogue for the CTA's own 128 rows; "accumulator drained" arrives on the leader's barrier
+#include "gemm_common.cuh"
+
+namespace ma {
+
+constexpr int G2_THREADS = 384;
+constexpr int G2_EPI_WARPS = 8;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int STAGES = BN == 256 ? 6 : 8;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the N rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                      const ma_gemm_epilogue ep, const int M, const int N, const int K, const ConvGeom cg) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bar_empty = bar_full + STAGES;
+  uint64_t* bar_tfull = bar_empty + STAGES;
+  uint64_t* bar_tempty = bar_tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  const uint32_t cta = cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bar_full[s], 1);   // leader's arrive.expect_tx; bytes from both CTAs
+      mbar_init(&bar_empty[s], 1);  // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bar_tfull[a], 1);                   // multicast tcgen05.commit
+      mbar_init(&bar_tempty[a], 2 * G2_EPI_WARPS);   // epilogue warps of BOTH CTAs (used on the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote signal; TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = cg.tiles_x * cg.tiles_y;
+  const int rows_tiles = cg.mode ? (M / (cg.H * cg.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;  // 128-row tiles
+  const int tiles_m = (rows_tiles + 1) / 2;                                                             // 256-row tiles
+  const int tiles_n = (N + BN - 1) / BN;
+  const int total_tiles = tiles_m * tiles_n;
+  const int kblocks = cg.mode ? 9 * cg.cblocks : (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        const int tm = (t % tiles_m) * 2 + static_cast<int>(cta);  // this CTA's 128-row tile
+        const int n0 = (t / tiles_m) * BN + static_cast<int>(cta) * (BN / 2);
+        if (cg.mode) {
+          // a row tile past the end (odd tile count) reads image index n: fully out of bounds -> zero fill
+          const int img = tm / tiles_per_img;
+          const int r = tm - img * tiles_per_img;
+          const int y0 = (r / cg.tiles_x) * cg.bh, x0 = (r % cg.tiles_x) * cg.bw;
+          const uint32_t bytes = 2u * (static_cast<uint32_t>(cg.bw * cg.bh * 128) + Cfg::B_BYTES);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            for (int cb = 0; cb < cg.cblocks; ++cb) {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              if (cta == 0) mbar_arrive_expect_tx(&bar_full[stage], bytes);
+              tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], cb * GEMM_BK, x0 + dx, y0 + dy, img);
+              tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmap_w, &bar_full[stage], tap * cg.C + cb * GEMM_BK, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          const int m0 = tm * GEMM_BM;
+          for (int kb = 0; kb < kblocks; ++kb) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            if (cta == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * Cfg::STAGE_BYTES);
+            tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], kb * GEMM_BK, m0);
+            tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmap_w, &bar_full[stage], kb * GEMM_BK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (cta == 0 && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait_cluster(&bar_tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&bar_full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&bar_empty[stage], 0x3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&bar_tfull[acc], 0x3);
+      }
+    }
+  } else if (warp >= 4) {
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t leader_tempty0 = mapa_shared(smem_u32(&bar_tempty[0]), 0);
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int tm = (t % tiles_m) * 2 + static_cast<int>(cta);
+      const int n0 = (t / tiles_m) * BN;
+      int m;
+      bool row_ok;
+      if (cg.mode) {
+        const int img = tm / tiles_per_img;
+        const int rr = tm - img * tiles_per_img;
+        const int r = quarter * 32 + lane;
+        const int y = (rr / cg.tiles_x) * cg.bh + r / cg.bw, x = (rr % cg.tiles_x) * cg.bw + r % cg.bw;
+        row_ok = tm < rows_tiles && r < cg.bw * cg.bh && y < cg.H && x < cg.W;
+        m = (img * cg.H + y) * cg.W + x;
+      } else {
+        m = tm * GEMM_BM + quarter * 32 + lane;
+        row_ok = m < M;
+      }
+      mbar_wait(&bar_tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 2; c += 32) {
+        const int col0 = n0 + half * (BN / 2) + c;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2) + c;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (row_ok && col0 < N) epilogue_store_chunk(ep, v, m, col0, N);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(leader_tempty0 + acc * 8);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / TMEM stay alive until the leader's last MMA and all remote arrives are done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
+                        cudaStream_t stream, const ConvGeom& cg) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    MA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int rows_tiles = cg.mode ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + GEMM_BM - 1) / GEMM_BM;
+  const int tiles = ((rows_tiles + 1) / 2) * ((N + BN - 1) / BN);
+  const int max_clusters = device_sm_count() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  gemm_bf16_2cta_kernel<BN><<<2 * clusters, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, ep, M, N, K, cg);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+// Entry used by gemm.cu's dispatchers. bn2 in {128, 256}.
+int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
+                     cudaStream_t stream, const ConvGeom& cg) {
+  if (bn2 == 256) return launch_gemm2<256>(tx, tw, ep, M, N, K, stream, cg);
+  return launch_gemm2<128>(tx, tw, ep, M, N, K, stream, cg);
+}
+
+}  // namespace ma

@@ -1,0 +1,162 @@
+// Shared by the 1-CTA (gemm.cu) and 2-CTA (gemm2.cu) tcgen05 GEMM kernels: implicit-conv geometry and the fused epilogue.
+#pragma once
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace ma {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+
+// Implicit-GEMM geometry of a 3x3 / stride 1 / pad 1 convolution over an NHWC tensor (mode 1).  The A operand of the
+// tile (bh x bw output pixels of one image) and of tap (ky,kx) is the input window shifted by (ky-1, kx-1): ONE 4-D TMA
+// box {64 channels, bw, bh, 1} whose out-of-bounds pixels (the zero padding) and channels are zero-filled by the TMA
+// unit -- no im2col matrix is ever written.  K runs over 9 taps x ceil(C/64) channel blocks.
+struct ConvGeom {
+  int mode;  // 0 = plain GEMM
+  int H, W, C;
+  int bw, bh;            // pixel box of one M tile (bw * bh <= 128)
+  int tiles_x, tiles_y;  // per image
+  int cblocks;           // ceil(C / 64)
+};
+
+// 32 consecutive output columns of one row: fused epilogue + store.
+__device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep, const uint32_t (&acc)[32], int m,
+                                                     int col0, int N) {
+  int out_row = m;
+  if (ep.rows_per_group_in > 0) {
+    int g = m / ep.rows_per_group_in;
+    out_row = g * ep.rows_per_group_out + ep.row_offset_out + (m - g * ep.rows_per_group_in);
+  }
+  const int res_row = ep.residual_row_mod > 0 ? (m % ep.residual_row_mod) : out_row;
+  const int nvalid = min(32, N - col0);
+
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+
+  if (nvalid == 32) {
+    if (ep.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    }
+    const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
+    const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
+    if (!act_late) {
+      if (ep.act == MA_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (ep.act == MA_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+    }
+    if (ep.out_relu && relu_early) {
+      uint4* o4 =
+          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
+    }
+    if (ep.colscale) {
+      const float4* s4 = reinterpret_cast<const float4*>(ep.colscale + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 s = __ldg(s4 + j);
+        v[4 * j + 0] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
+      }
+    }
+    if (ep.residual) {
+      if (ep.residual_dtype == MA_F32) {
+        const float4* r4 =
+            reinterpret_cast<const float4*>(static_cast<const float*>(ep.residual) + (size_t)res_row * ep.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r = r4[j];
+          v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+        }
+      } else {
+        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(ep.residual) +
+                                                         (size_t)res_row * ep.ldr + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 r = r4[j];
+          v[8 * j + 0] += bf16_lo(r.x); v[8 * j + 1] += bf16_hi(r.x);
+          v[8 * j + 2] += bf16_lo(r.y); v[8 * j + 3] += bf16_hi(r.y);
+          v[8 * j + 4] += bf16_lo(r.z); v[8 * j + 5] += bf16_hi(r.z);
+          v[8 * j + 6] += bf16_lo(r.w); v[8 * j + 7] += bf16_hi(r.w);
+        }
+      }
+    }
+    if (act_late) {
+      if (ep.act == MA_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (ep.act == MA_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      }
+    }
+    if (ep.out_dtype == MA_F32) {
+      float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + (size_t)out_row * ep.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out) + (size_t)out_row * ep.ldo + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+    }
+    if (ep.out_relu && !relu_early) {
+      uint4* o4 =
+          reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(ep.out_relu) + (size_t)out_row * ep.ldo_relu + col0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(fmaxf(v[8 * j], 0.f), fmaxf(v[8 * j + 1], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 2], 0.f), fmaxf(v[8 * j + 3], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 4], 0.f), fmaxf(v[8 * j + 5], 0.f)),
+                           pack_bf16x2(fmaxf(v[8 * j + 6], 0.f), fmaxf(v[8 * j + 7], 0.f)));
+    }
+  } else {
+    // ragged N edge: scalar path (fully unrolled + predicated so v[] stays in registers)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j >= nvalid) continue;
+      const int n = col0 + j;
+      float x = v[j];
+      const bool act_late = (ep.flags & MA_GEMM_ACT_AFTER_RESIDUAL) != 0;
+      const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
+      if (ep.bias) x += __ldg(ep.bias + n);
+      if (!act_late) {
+        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
+        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
+      }
+      if (ep.out_relu && relu_early)
+        static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
+      if (ep.colscale) x *= __ldg(ep.colscale + n);
+      if (ep.residual) {
+        if (ep.residual_dtype == MA_F32) x += static_cast<const float*>(ep.residual)[(size_t)res_row * ep.ldr + n];
+        else x += __bfloat162float(static_cast<const __nv_bfloat16*>(ep.residual)[(size_t)res_row * ep.ldr + n]);
+      }
+      if (act_late) {
+        if (ep.act == MA_ACT_GELU) x = gelu_erf(x);
+        else if (ep.act == MA_ACT_RELU) x = fmaxf(x, 0.0f);
+      }
+      if (ep.out_dtype == MA_F32) static_cast<float*>(ep.out)[(size_t)out_row * ep.ldo + n] = x;
+      else static_cast<__nv_bfloat16*>(ep.out)[(size_t)out_row * ep.ldo + n] = __float2bfloat16(x);
+      if (ep.out_relu && !relu_early)
+        static_cast<__nv_bfloat16*>(ep.out_relu)[(size_t)out_row * ep.ldo_relu + n] = __float2bfloat16(fmaxf(x, 0.f));
+    }
+  }
+}
+
+
+}  // namespace ma

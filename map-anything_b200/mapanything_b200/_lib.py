@@ -43,6 +43,21 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+MA_ATTN_MAX_SEGMENTS, MA_ATTN_STATE_IN, MA_ATTN_STATE_OUT = 16, 1, 2
+
+
+class AttnExt(C.Structure):
+    _fields_ = [
+        ("n_segments", C.c_int32),
+        ("flags", C.c_int32),
+        ("seg_row0", C.c_int32 * MA_ATTN_MAX_SEGMENTS),
+        ("seg_len", C.c_int32 * MA_ATTN_MAX_SEGMENTS),
+        ("state_o", C.c_void_p),
+        ("ld_state_o", C.c_int64),
+        ("state_m", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); must list every symbol include/mapanything_b200.h declares.
 _i, _i64, _p, _f = C.c_int, C.c_int64, C.c_void_p, C.c_float
 SIGNATURES = {
@@ -50,8 +65,11 @@ SIGNATURES = {
     "ma_abi_version": (_i, []),
     "ma_device_info": (_i, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "ma_gemm_bf16": (_i, [_p, _i64, _p, _i64, _i, _i, _i, C.POINTER(GemmEpilogue), _i, _p]),
+    "ma_conv3x3_bf16": (_i, [_p, _i, _i, _i, _i, _p, _i64, _i, C.POINTER(GemmEpilogue), _i, _p]),
     "ma_attention_fwd": (_i, [_p, _i64, _i64, _i, _p, _i64, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i64,
                               _i64, _f, _p]),
+    "ma_attention_fwd_ex": (_i, [_p, _i64, _i64, _i, _p, _i64, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i64,
+                                 _i64, _f, C.POINTER(AttnExt), _p]),
     "ma_patchify": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ma_layernorm": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i, _i, _f, _i, _i64, _i64, _i64, _i64, _p]),
     "ma_set_rows": (_i, [_p, _i64, _i, _i64, _i64, _p, _p, _i, _p]),
@@ -62,6 +80,14 @@ SIGNATURES = {
     "ma_decode_dense": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ma_split_bf16x3": (_i, [_p, _i64, _p, _i, _i, _p]),
     "ma_token_mean_f32": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_rays_from_intrinsics": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_normalize_rays": (_i, [_p, _p, _i64, _p]),
+    "ma_depth_z_to_along_ray": (_i, [_p, _p, _p, _i64, _p]),
+    "ma_pose_to_quat_trans": (_i, [_p, _p, _p, _i, _p]),
+    "ma_unshuffle_split": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "ma_depth_factor": (_i, [_p, _i, _i64, _p, _p, _p]),
+    "ma_pose_inputs": (_i, [_p, _p, _p, _i, _p, _p, _p, _p]),
+    "ma_fuse_add": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ma_denorm_image":(_i, [_p, _p, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p]),
     "ma_intrinsics_from_rays": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_pose_matrices": (_i, [_p, _p, _p, _i, _p]),

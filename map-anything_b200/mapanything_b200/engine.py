@@ -73,6 +73,72 @@ def _convT(conv: nn.ConvTranspose2d) -> Lin:
     return Lin(w, b)
 
 
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _conv3x3_padded(conv: nn.Conv2d, cin_pad: int, cout_pad: int, split: bool = False):
+    """3x3 conv weight [Cout][Cin][3][3] -> tap-major [cout_pad][9*cin_pad] with zero padded channels (TMA needs
+    channel counts that are multiples of 8; e.g. 588 -> 592).  split=True packs it for split-bf16 activations."""
+    w = conv.weight.detach().float().permute(0, 2, 3, 1)  # [Cout][ky][kx][Cin]
+    cout, _, _, cin = w.shape
+    wp = w.new_zeros(cout_pad, 3, 3, cin_pad)
+    wp[:cout, :, :, :cin] = w
+    b = conv.bias.detach().float() if conv.bias is not None else w.new_zeros(cout)
+    bp = b.new_zeros(cout_pad)
+    bp[:cout] = b
+    if split:
+        return Lin3(wp.reshape(cout_pad, 9 * cin_pad), bp, group=cin_pad)
+    return Lin(wp.reshape(cout_pad, 9 * cin_pad), bp)
+
+
+def _linear_padded(w: torch.Tensor, b: Optional[torch.Tensor], kpad: int, npad: int) -> Lin:
+    w = w.detach().float().reshape(w.shape[0], -1)
+    wp = w.new_zeros(npad, kpad)
+    wp[:w.shape[0], :w.shape[1]] = w
+    bp = w.new_zeros(npad)
+    if b is not None:
+        bp[:w.shape[0]] = b.detach().float()
+    return Lin(wp, bp)
+
+
+class DenseEncW:
+    """Packed `dense_rep_encoder`: PixelUnshuffle -> conv3x3 -> 2 residual blocks -> conv1x1 -> LayerNorm."""
+
+    def __init__(self, enc):
+        self.patch, self.in_chans = enc.patch_size, enc.in_chans
+        self.cpad0 = _pad8(enc.in_chans * enc.patch_size ** 2)
+        d0 = enc.conv_in.out_channels
+        # first conv in split-bf16 precision: its input is raw geometry (unit rays / log depth), fp32 in the reference
+        self.conv_in = _conv3x3_padded(enc.conv_in, self.cpad0, _pad8(d0), split=True)
+        self.blocks = []
+        cin = d0
+        for rb in (enc.encoder[0], enc.encoder[1]):
+            cout = rb.conv1.out_channels
+            sc = None if isinstance(rb.shortcut, nn.Identity) else \
+                _linear_padded(rb.shortcut.weight, rb.shortcut.bias, _pad8(cin), _pad8(cout))
+            self.blocks.append((_conv3x3_padded(rb.conv1, _pad8(cin), _pad8(cout)),
+                                _conv3x3_padded(rb.conv2, _pad8(cout), _pad8(cout)), sc))
+            cin = cout
+        last = enc.encoder[2]
+        self.out = _linear_padded(last.weight, last.bias, _pad8(cin), last.out_channels)
+        self.nw, self.nb, self.eps = _f32(enc.norm_layer.weight), _f32(enc.norm_layer.bias), float(enc.norm_layer.eps)
+
+
+class GlobalEncW:
+    """Packed `global_rep_encoder` (App. A.2): MLP with GELU + LayerNorm, split-bf16 (~fp32) precision."""
+
+    def __init__(self, enc):
+        lins = [m for m in enc.encoder if isinstance(m, nn.Linear)]
+        self.lins = []
+        for i, m in enumerate(lins):
+            w = m.weight.detach().float()
+            if i == 0:  # K padded to 8 (inputs arrive as [V][8] rows)
+                w = torch.cat([w, w.new_zeros(w.shape[0], 8 - w.shape[1])], dim=1)
+            self.lins.append(Lin3(w, m.bias))
+        self.nw, self.nb, self.eps = _f32(enc.norm_layer.weight), _f32(enc.norm_layer.bias), float(enc.norm_layer.eps)
+
+
 class BlockW:
     def __init__(self, blk):
         self.n1w, self.n1b = _f32(blk.norm1.weight), _f32(blk.norm1.bias)
@@ -83,6 +149,12 @@ class BlockW:
         self.fc2 = Lin(blk.mlp.fc2.weight, blk.mlp.fc2.bias)
         self.ls1 = _f32(blk.ls1.gamma) if hasattr(blk.ls1, "gamma") else None
         self.ls2 = _f32(blk.ls2.gamma) if hasattr(blk.ls2, "gamma") else None
+        # row slices of the fused qkv weight (views, no copies): the view-sharded global blocks write Q and K|V to
+        # different buffers (K|V goes straight into this rank's slot of the all-gather buffer)
+        d = self.qkv.n // 3
+        self.q_w, self.kv_w = self.qkv.w[:d], self.qkv.w[d:]
+        self.q_b = self.qkv.b[:d] if self.qkv.b is not None else None
+        self.kv_b = self.qkv.b[d:] if self.qkv.b is not None else None
 
 
 class Engine:
@@ -106,6 +178,9 @@ class Engine:
         self.enc_nw, self.enc_nb = _f32(enc.norm.weight), _f32(enc.norm.bias)
         self.fus_w, self.fus_b = _f32(model.fusion_norm_layer.weight), _f32(model.fusion_norm_layer.bias)
         self.fus_eps = float(model.fusion_norm_layer.eps)
+
+        self._model_ref = model  # geometric-input encoders are packed on first use (image-only scenes never need them)
+        self._geo = None
 
         isx = model.info_sharing
         self.D, self.is_heads, self.indices = isx.dim, isx.num_heads, list(isx.indices)
@@ -174,8 +249,13 @@ class Engine:
         return ops.gemm(x, lin.w, out, bias=lin.b, act=act, **kw)
 
     def _conv3(self, x, lin: Lin, stride=1, *, act=MA_ACT_NONE, **kw):
-        """x NHWC bf16 (n,H,W,C) -> (n,Ho,Wo,N) via explicit im2col + tcgen05 GEMM."""
+        """x NHWC bf16 (n,H,W,C) -> (n,Ho,Wo,N): implicit GEMM (4-D TMA boxes, no im2col) for stride 1; the single
+        stride-2 conv of the path (act_postprocess[3], 37 -> 19) goes through the explicit im2col."""
         n, H, W, C = x.shape
+        if stride == 1:
+            out = self._empty(n * H * W, lin.n)
+            ops.conv3x3(x, lin.w, out, bias=lin.b, act=act, **kw)
+            return out.view(n, H, W, lin.n)
         Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         col = self._empty(n * Ho * Wo, 9 * C)
         ops.im2col3x3(x, col, stride)
@@ -224,6 +304,38 @@ class Engine:
         f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
         ops.gemm(f, bw.fc2.w, xr, bias=bw.fc2.b, colscale=bw.ls2, residual=xr)
 
+    def _block_global_sharded(self, x, bw: BlockW, plan, comm, bufs):
+        """Global-attention block of the view-sharded stream: local query rows, keys/values of every rank.
+        K|V of the local rows are written by the GEMM epilogue into this rank's slot of the gather buffer; the NCCL
+        all-gather of the slots runs while the attention over the local keys executes; a second launch resumes the
+        online softmax over the remote slots."""
+        dim, heads = x.shape[1], self.is_heads
+        rows, slot = plan.rows(), plan.slot_rows
+        kvbuf, state = bufs["kv"], bufs["state"]
+        h = self._empty(rows, dim)
+        ops.layernorm(x, h, bw.n1w, bw.n1b)
+        mine = kvbuf[plan.rank * slot:plan.rank * slot + rows]
+        ops.gemm(h, bw.kv_w, mine, bias=bw.kv_b)
+        work = comm.all_gather_slots(kvbuf, slot)           # async: NCCL stream waits for the GEMM above
+        q = self._empty(rows, dim)
+        ops.gemm(h, bw.q_w, q, bias=bw.q_b)
+        K, Vv = kvbuf[:, :dim], kvbuf[:, dim:]
+        a = self._empty(rows, dim)
+        remote = plan.remote_segments()
+        common = dict(num_heads=heads, num_seqs=1, q_len=rows, kv_seq_stride=kvbuf.shape[0])
+        if remote:
+            ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=state, state_out=True, **common)
+            work.wait()                                      # current stream waits for the gathered slots
+            ops.attention(q, K, Vv, a, kv_len=sum(l for _, l in remote), kv_segments=remote, state=state, state_in=True,
+                          **common)
+        else:
+            work.wait()
+            ops.attention(q, K, Vv, a, kv_len=rows, kv_segments=plan.local_segment(), **common)
+        ops.gemm(a, bw.proj.w, x, bias=bw.proj.b, colscale=bw.ls1, residual=x)
+        ops.layernorm(x, h, bw.n2w, bw.n2b)
+        f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
+        ops.gemm(f, bw.fc2.w, x, bias=bw.fc2.b, colscale=bw.ls2, residual=x)
+
     # ------------------------------------------------------------------------------------------ stage 1
     def encode(self, imgs: torch.Tensor) -> torch.Tensor:
         """(n,3,H,W) fp32 normalised images -> DINOv2 x_norm_patchtokens, fp32 [n*N][C] token-major."""
@@ -252,20 +364,129 @@ class Engine:
         ops.layernorm(feat, out, self.fus_w, self.fus_b, eps=self.fus_eps)
         return out
 
-    def info_sharing(self, fused: torch.Tensor, V: int, N: int):
-        """fused bf16 [V*N][C] -> taps (bf16 [V*N][D]) after blocks `indices`, final (bf16 [V*N][D]), scale-token feature."""
-        D, T = self.D, V * N + 1
+    # ------------------------------------------------------------------------------------------ geometric inputs
+    def _geo_weights(self):
+        if self._geo is None:
+            m = self._model_ref
+            self._geo = {
+                "ray": DenseEncW(m.ray_dirs_encoder), "depth": DenseEncW(m.depth_encoder),
+                "depth_scale": GlobalEncW(m.depth_scale_encoder), "rot": GlobalEncW(m.cam_rot_encoder),
+                "trans": GlobalEncW(m.cam_trans_encoder), "trans_scale": GlobalEncW(m.cam_trans_scale_encoder),
+            }
+        return self._geo
+
+    def _dense_rep(self, w: DenseEncW, data: torch.Tensor, factor: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """fp32 NHWC (k,H,W,cin) -> fp32 [k*N][C] dense geometric features (reference model.py:812-814, :972-975)."""
+        x = ops.unshuffle_split(data.contiguous(), w.patch, w.cpad0, factor)   # bf16 (k,hp,wp,3*cpad0)
+        k, hp, wp, _ = x.shape
+        M = k * hp * wp
+        a = self._empty(M, w.conv_in.n)
+        ops.conv3x3(x, w.conv_in.w, a, bias=w.conv_in.b)
+        for c1, c2, sc in w.blocks:
+            t = self._empty(M, c1.n)
+            ops.conv3x3(a.view(k, hp, wp, -1), c1.w, t, bias=c1.b, act=MA_ACT_GELU)
+            if sc is None:
+                res = a
+            else:
+                res = self._empty(M, sc.n, dtype=torch.float32)
+                ops.gemm(a, sc.w, res, bias=sc.b)
+            o = self._empty(M, c2.n)
+            ops.conv3x3(t.view(k, hp, wp, -1), c2.w, o, bias=c2.b, residual=res, act=MA_ACT_GELU, act_after_residual=True)
+            a = o
+        y = self._empty(M, w.out.n, dtype=torch.float32)
+        ops.gemm(a, w.out.w, y, bias=w.out.b)
+        f = self._empty(M, w.out.n, dtype=torch.float32)
+        ops.layernorm(y, f, w.nw, w.nb, eps=w.eps)
+        return f
+
+    def _global_rep(self, w: GlobalEncW, x8: torch.Tensor) -> torch.Tensor:
+        """fp32 [rows][8] (K-padded input) -> fp32 [rows][C] global geometric features (model.py:986-987, :1050-1110)."""
+        g = x8
+        for i, lin in enumerate(w.lins):
+            o = self._empty(g.shape[0], lin.n, dtype=torch.float32)
+            ops.gemm(ops.split3(g), lin.w, o, bias=lin.b, act=MA_ACT_GELU if i + 1 < len(w.lins) else MA_ACT_NONE)
+            g = o
+        f = self._empty(g.shape[0], g.shape[1], dtype=torch.float32)
+        ops.layernorm(g, f, w.nw, w.nb, eps=w.eps)
+        return f
+
+    def fuse_geometric(self, feat: torch.Tensor, V: int, N: int, ray=None, depth=None, pose=None):
+        """Adds the encoded geometric inputs to the fp32 encoder features feat [V*N][C], in place
+        (reference _encode_and_fuse_optional_geometric_inputs, model.py:1133-1244; the fusion LayerNorm follows).
+          ray   = (view ids, fp32 (k,H,W,3) unit ray directions)
+          depth = (view ids, fp32 (k,H,W,1) depth along ray, metric gates [k] of 0/1)
+          pose  = (quats8, trans8, log_scale8 fp32 [V,8] from ops.pose_inputs, cam gates [V], metric gates [V])"""
+        gw_ = self._geo_weights()
+        dev = self.device
+
+        def slots(ids):
+            t = [-1] * V
+            for j, i in enumerate(ids):
+                t[i] = j
+            return torch.tensor(t, dtype=torch.int32, device=dev)
+
+        dense_a = a_slot = dense_b = b_slot = None
+        g = [None, None, None, None]
+        gates = [[0.0] * V for _ in range(4)]
+        if ray is not None and len(ray[0]):
+            dense_a, a_slot = self._dense_rep(gw_["ray"], ray[1]), slots(ray[0])
+        if depth is not None and len(depth[0]):
+            ids, d, metric = depth
+            factor, logf8 = ops.depth_factor(d.contiguous())
+            dense_b, b_slot = self._dense_rep(gw_["depth"], d, factor), slots(ids)
+            g[3] = self._global_rep(gw_["depth_scale"], logf8)
+            for j, i in enumerate(ids):
+                gates[3][i] = float(metric[j])
+        if pose is not None and any(pose[3]):
+            q8, t8, s8, cam, metric = pose
+            g[0] = self._global_rep(gw_["rot"], q8)
+            g[1] = self._global_rep(gw_["trans"], t8)
+            g[2] = self._global_rep(gw_["trans_scale"], s8)
+            for i in range(V):
+                gates[0][i] = gates[1][i] = float(cam[i])
+                gates[2][i] = float(cam[i]) * float(metric[i])
+        if dense_a is None and dense_b is None and all(x is None for x in g):
+            return feat
+        gw = torch.tensor(gates, dtype=torch.float32, device=dev)
+        # the kernel walks g_0..g_3 positionally; absent ones are NULL
+        return ops.fuse_add(feat, V, N, dense_a, a_slot, dense_b, b_slot, g, gw)
+
+    def info_sharing(self, fused: torch.Tensor, V: int, N: int, plan=None, comm=None):
+        """fused bf16 [V*N][C] -> taps (bf16 [V*N][D]) after blocks `indices`, final (bf16 [V*N][D]), and the fp32 final
+        features [T][D] (row V*N = scale-token feature when this rank holds the scale token).
+
+        With a ViewShardPlan, V is the number of LOCAL views, rank 0 holds the reference view and the scale token, and the
+        global blocks attend over the keys of all ranks (_block_global_sharded)."""
+        sharded = plan is not None and plan.world > 1
+        has_tok = (not sharded) or plan.rank == 0
+        has_ref = has_tok
+        D, T = self.D, V * N + (1 if has_tok else 0)
         y = self._empty(T, D, dtype=torch.float32)
-        if self.use_ref_pe:
+        if self.use_ref_pe and has_ref:
             ops.gemm(fused[:N], self.proj_embed.w, y[:N], bias=self.proj_embed.b, residual=self.pe0, residual_row_mod=1)
             if V > 1:
                 ops.gemm(fused[N:], self.proj_embed.w, y[N:V * N], bias=self.proj_embed.b)
         else:
             ops.gemm(fused, self.proj_embed.w, y[:V * N], bias=self.proj_embed.b)
-        ops.set_rows(y, self.scale_tok_proj.reshape(-1), None, groups=1, group_stride=0, row_offset=V * N)
+        if has_tok:
+            ops.set_rows(y, self.scale_tok_proj.reshape(-1), None, groups=1, group_stride=0, row_offset=V * N)
+        bufs = None
+        if sharded:
+            assert plan.rows() == T and plan.tokens_per_view == N
+            key = (plan.world * plan.slot_rows, T)
+            if getattr(self, "_shard_bufs_key", None) != key:
+                # zero-initialised once: slot padding rows are never written, so masked keys stay finite
+                self._shard_bufs = {
+                    "kv": torch.zeros(plan.world * plan.slot_rows, 2 * D, device=self.device, dtype=torch.bfloat16),
+                    "state": (self._empty(T, D, dtype=torch.float32), self._empty(T, self.is_heads, dtype=torch.float32)),
+                }
+                self._shard_bufs_key = key
+            bufs = self._shard_bufs
         taps: List[torch.Tensor] = []
         for i, bw in enumerate(self.is_blocks):
-            if i % 2 == 0:
+            if i % 2 == 0 and sharded:
+                self._block_global_sharded(y, bw, plan, comm, bufs)
+            elif i % 2 == 0:
                 self._block(y, bw, T, self.is_heads, 1, T, T)  # global: every token of every view + scale token
             else:
                 self._block(y, bw, V * N, self.is_heads, V, N, N)  # frame: per view, scale token bypasses the block
@@ -287,27 +508,24 @@ class Engine:
         """ResidualConvUnit: conv2(relu(conv1(relu(x)))) + skip; returns (out, relu(out) or None)."""
         t = self._conv3(x_relu, r[c1], act=MA_ACT_RELU)
         n, H, W, _ = t.shape
-        col = self._empty(n * H * W, 9 * t.shape[3])
-        ops.im2col3x3(t, col, 1)
         out = self._empty(n * H * W, r[c2].n)
         out_relu = self._empty(n * H * W, r[c2].n) if want_relu else None
-        ops.gemm(col, r[c2].w, out, bias=r[c2].b, residual=x_skip.reshape(n * H * W, -1), out_relu=out_relu)
+        ops.conv3x3(t, r[c2].w, out, bias=r[c2].b, residual=x_skip.reshape(n * H * W, -1), out_relu=out_relu)
         return out.view(n, H, W, -1), (out_relu.view(n, H, W, -1) if want_relu else None)
 
     def _fusion(self, r, x0, lay_in, rn: Lin, up_virtual, up_out):
         """FeatureFusionBlock on NHWC bf16. x0: previous path (or None for refinenet4); lay_in: act_postprocess output."""
         n, H, W, _ = lay_in.shape
         M = n * H * W
-        col = self._empty(M, 9 * lay_in.shape[3])
-        ops.im2col3x3(lay_in, col, 1)
+        lay_in = lay_in.contiguous()
         lay = self._empty(M, rn.n)
         lay_relu = self._empty(M, rn.n)
         if x0 is None:
-            ops.gemm(col, rn.w, lay, out_relu=lay_relu)  # l4 and relu(l4)
+            ops.conv3x3(lay_in, rn.w, lay, out_relu=lay_relu)  # l4 and relu(l4)
             y, y_relu = lay.view(n, H, W, -1), lay_relu.view(n, H, W, -1)
         else:
             # one launch: lay = x0 + layer_rn(x)  (skip for RCU1's output),  lay_relu = relu(layer_rn(x))  (RCU1 input)
-            ops.gemm(col, rn.w, lay, residual=x0.reshape(M, -1), out_relu=lay_relu, relu_out_before_residual=True)
+            ops.conv3x3(lay_in, rn.w, lay, residual=x0.reshape(M, -1), out_relu=lay_relu, relu_out_before_residual=True)
             y, y_relu = self._rcu(lay_relu.view(n, H, W, -1), lay.view(n, H, W, -1), r, "r1c1", "r1c2", want_relu=True)
         z, _ = self._rcu(y_relu, y, r, "r2c1", "r2c2", want_relu=False)
         # out_conv (1x1) commutes with the bilinear upsample (both linear, interpolation weights sum to 1):
@@ -325,10 +543,8 @@ class Engine:
             u = self._empty(n * N, c1.n, dtype=torch.float32)
             ops.gemm(ops.split3(x32), c1.w, u, bias=c1.b, act=MA_ACT_RELU)
             us = ops.split3(u).view(n, hp, wp, 3 * c1.n)
-            col = self._empty(n * N, 27 * c1.n)
-            ops.im2col3x3(us, col, 1)
             u2 = self._empty(n * N, c2.n, dtype=torch.float32)
-            ops.gemm(col, c2.w, u2, bias=c2.b, act=MA_ACT_RELU)
+            ops.conv3x3(us, c2.w, u2, bias=c2.b, act=MA_ACT_RELU)
             xn = self._empty(n * N, c3.n, dtype=torch.float32)
             ops.gemm(ops.split3(u2), c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU, act_after_residual=True)
             x32 = xn

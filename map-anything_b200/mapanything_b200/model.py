@@ -103,6 +103,8 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         self._initialize_adaptors(pred_head_config)
         self._load_pretrained_weights()
         self._engine = None
+        self._shard_comm = None
+        self._shard_counts = None
 
     # ------------------------------------------------------------------------------------------ construction
     def _initialize_info_sharing(self, cfg):
@@ -194,6 +196,23 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             self._engine = Engine(self)
         return self._engine
 
+    # ------------------------------------------------------------------------------------------ multi-GPU
+    def enable_view_sharding(self, group=None, views_per_rank=None):
+        """Shard ONE scene by view over the ranks of `group` (default: the world group), one process per GPU
+        (SURVEY.md 8e).  Afterwards every rank calls forward()/infer() with ITS OWN contiguous range of the scene's
+        views, in rank order (rank 0 holds view 0, the reference view), and gets the predictions of those views back;
+        all ranks must call together.  `views_per_rank` (list of ints) skips the per-call exchange of view counts."""
+        from .sharding import ViewShardComm
+
+        self._shard_comm = ViewShardComm(group)
+        self._shard_counts = list(views_per_rank) if views_per_rank is not None else None
+        return self
+
+    def disable_view_sharding(self):
+        self._shard_comm = None
+        self._shard_counts = None
+        return self
+
     def _geometric_inputs_active(self, views) -> bool:
         """With p in {0,1} (always the case inside infer) the masks of model.py:1155-1201 are deterministic: a modality is
         fused iff overall_prob and (1 - dropout_prob) and its own prob are all 1 and a view provides it.  When nothing
@@ -217,6 +236,59 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             keys += ["camera_pose_quats"]
         return any(k in v for v in views for k in keys)
 
+    def _fuse_geometric_inputs(self, eng, feat, views, b, N, plan, comm):
+        """Rows a7-a11 of SURVEY 8a for batch item b: with probabilities in {0,1} the reference's random masks
+        (model.py:1155-1201) reduce to "the view provides the modality".  Encodes ray directions, depth (+ its metric scale)
+        and the camera poses relative to view 0 (+ their metric scale) and adds them to the encoder features in place."""
+        g = self.geometric_input_config
+        V = len(views)
+        dev = self.device
+
+        def metric_flag(view):
+            return bool(view["is_metric_scale"][b]) if "is_metric_scale" in view else False
+
+        ray = depth = pose = None
+        if g["ray_dirs_prob"] == 1:
+            ids = [i for i, v in enumerate(views) if "ray_directions_cam" in v]
+            if ids:
+                ray = (ids, torch.cat([views[i]["ray_directions_cam"][b:b + 1] for i in ids], 0).to(dev, torch.float32))
+        if g["depth_prob"] == 1:
+            ids = [i for i, v in enumerate(views) if "depth_along_ray" in v]
+            if ids:
+                d = torch.cat([views[i]["depth_along_ray"][b:b + 1] for i in ids], 0).to(dev, torch.float32)
+                norm_all = g["depth_scale_norm_all_prob"] == 1
+                depth = (ids, d, [0.0 if norm_all else float(metric_flag(views[i])) for i in ids])
+        if g["cam_prob"] == 1:
+            has = [("camera_pose_quats" in v and "camera_pose_trans" in v) for v in views]
+            sharded = plan is not None and plan.world > 1
+            if any(has) or sharded:
+                q = torch.zeros(V, 4, device=dev)
+                t = torch.zeros(V, 3, device=dev)
+                for i, v in enumerate(views):
+                    if has[i]:
+                        q[i] = v["camera_pose_quats"][b].to(dev, torch.float32)
+                        t[i] = v["camera_pose_trans"][b].to(dev, torch.float32)
+                hp_ = torch.tensor(has, dtype=torch.uint8, device=dev)
+                lo, n_loc = 0, V
+                if sharded:  # the pose of view 0 and the translation norms of all views are needed on every rank
+                    packed = torch.cat([q, t, hp_.float().unsqueeze(1)], dim=1)           # [V_local, 8]
+                    allp = comm.all_gather_rows(packed, plan.counts)                      # [V_total, 8]
+                    q, t, hp_ = allp[:, :4].contiguous(), allp[:, 4:7].contiguous(), allp[:, 7].to(torch.uint8).contiguous()
+                    lo = plan.view_offset
+                    has_any = bool(hp_.any())  # one host sync; only with pose inputs in sharded mode
+                else:
+                    has_any = True
+                if has_any:
+                    if not bool(hp_[0]):
+                        raise ValueError("camera pose inputs need the pose of view 0 (the reference view)")
+                    from . import ops as _ops
+
+                    q8, t8, s8 = _ops.pose_inputs(q, t, hp_)
+                    norm_all = g["pose_scale_norm_all_prob"] == 1
+                    pose = (q8[lo:lo + n_loc].contiguous(), t8[lo:lo + n_loc].contiguous(), s8[lo:lo + n_loc].contiguous(),
+                            [float(x) for x in has], [0.0 if norm_all else float(metric_flag(v)) for v in views])
+        eng.fuse_geometric(feat, V, N, ray=ray, depth=depth, pose=pose)
+
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False) -> List[Dict[str, torch.Tensor]]:
         """Same contract as the reference forward (model.py:1477-1909). Runs under no_grad: this is an inference engine."""
@@ -230,26 +302,36 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         p = self.encoder.patch_size
         if height % p or width % p:
             raise AssertionError(f"Input image size ({height}, {width}) must be a multiple of the patch size {p}")
-        if self._geometric_inputs_active(views):
-            raise NotImplementedError(
-                "geometric-input fusion (ray directions / depth / pose encoders, SURVEY 8a rows a8-a11) is scheduled after "
-                "the image-only path; call infer(..., ignore_calibration_inputs=True, ignore_depth_inputs=True, "
-                "ignore_pose_inputs=True) or pass image-only views"
-            )
+        geo_active = self._geometric_inputs_active(views)
         eng = self.engine()
         eng.dpt_chunk = 2 if memory_efficient_inference else 4
         hp, wp = height // p, width // p
         N = hp * wp
+        plan, comm = None, self._shard_comm
+        if comm is not None and comm.world > 1:
+            from .sharding import ViewShardPlan
+
+            counts = self._shard_counts or comm.exchange_counts(num_views, self.device)
+            if counts[comm.rank] != num_views:
+                raise ValueError(f"rank {comm.rank} was given {num_views} views, views_per_rank says {counts[comm.rank]}")
+            plan = ViewShardPlan(counts, comm.rank, N)
         per_scene = []
         with torch.no_grad():
             for b in range(batch_size_per_view):
                 imgs = torch.cat([v["img"][b:b + 1] for v in views], dim=0).to(self.device, torch.float32)
                 feat = eng.encode(imgs)                       # fp32 [V*N][C]   DINOv2 x_norm_patchtokens
+                if geo_active:
+                    self._fuse_geometric_inputs(eng, feat, views, b, N, plan, comm)
                 fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
-                taps, final, final32 = eng.info_sharing(fused, num_views, N)
+                taps, final, final32 = eng.info_sharing(fused, num_views, N, plan=plan, comm=comm)
                 raw, pose_raw = eng.dpt_and_pose([fused, taps[0], taps[1], final], num_views, hp, wp, height, width,
                                                  final32=final32[:num_views * N])
-                scale_raw = eng.scale_head(final32[num_views * N:])
+                if plan is None:
+                    scale_raw = eng.scale_head(final32[num_views * N:])
+                else:  # the scale token lives on rank 0: one float travels to the other ranks
+                    scale_raw = eng.scale_head(final32[num_views * N:]) if plan.rank == 0 else \
+                        torch.empty(1, device=self.device, dtype=torch.float32)
+                    comm.broadcast(scale_raw, src=0)
                 per_scene.append(ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width))
         res = []
         for i in range(num_views):

@@ -3,7 +3,7 @@
 PyTorch is used for device memory and streams only: every function here hands raw device pointers and
 the current CUDA stream to `libmapanything_b200.so`.  `LAUNCHES` counts kernel launches issued through
 this module (bench.py reports it as `gpu_launches`); when `PROFILE` is a list, every launch is bracketed by
-CUDA events on the launching stream and appended as (family, algorithmic_flops, start_event, end_event).
+CUDA events on the launching stream and appended as (family, algorithmic_flops, start_event, end_event, shape tag).
 """
 from __future__ import annotations
 
@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU, MA_BF16, MA_F32, GemmEpilogue, check  # noqa: F401
+from ._lib import (MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU, MA_ATTN_MAX_SEGMENTS, MA_ATTN_STATE_IN,  # noqa: F401
+                   MA_ATTN_STATE_OUT, MA_BF16, MA_F32, AttnExt, GemmEpilogue, check)
 
 LAUNCHES = 0
 PROFILE = None
@@ -22,10 +23,10 @@ PROFILE = None
 class launch:
     """Context manager around one kernel launch: counts it and (optionally) times it with CUDA events."""
 
-    __slots__ = ("name", "flops", "n", "s")
+    __slots__ = ("name", "flops", "n", "s", "tag")
 
-    def __init__(self, name: str, flops: float = 0.0, n: int = 1):
-        self.name, self.flops, self.n, self.s = name, flops, n, None
+    def __init__(self, name: str, flops: float = 0.0, n: int = 1, tag: str = ""):
+        self.name, self.flops, self.n, self.s, self.tag = name, flops, n, None, tag
 
     def __enter__(self):
         if PROFILE is not None:
@@ -40,7 +41,7 @@ class launch:
             if PROFILE is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
-                PROFILE.append((self.name, self.flops, self.s, e))
+                PROFILE.append((self.name, self.flops, self.s, e, self.tag))
         return False
 
 
@@ -79,6 +80,32 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
+def _epilogue(out, N, bias, act, colscale, residual, residual_row_mod, out_relu, rows_per_group_in, rows_per_group_out,
+              row_offset_out, act_after_residual, relu_out_before_residual) -> GemmEpilogue:
+    ep = GemmEpilogue()
+    ep.out = out.data_ptr()
+    ep.ldo = out.stride(-2)
+    ep.out_dtype = _dt(out)
+    ep.act = act
+    ep.bias = _ptr(_f32c(bias, N, "bias"))
+    ep.colscale = _ptr(_f32c(colscale, N, "colscale"))
+    if residual is not None:
+        ep.residual = residual.data_ptr()
+        ep.ldr = residual.stride(-2)
+        ep.residual_dtype = _dt(residual)
+    ep.residual_row_mod = residual_row_mod
+    if out_relu is not None:
+        if out_relu.dtype != torch.bfloat16:
+            raise TypeError("out_relu must be bfloat16")
+        ep.out_relu = out_relu.data_ptr()
+        ep.ldo_relu = out_relu.stride(-2)
+    ep.rows_per_group_in = rows_per_group_in
+    ep.rows_per_group_out = rows_per_group_out
+    ep.row_offset_out = row_offset_out
+    ep.flags = (1 if act_after_residual else 0) | (2 if relu_out_before_residual else 0)
+    return ep
+
+
 def gemm(
     x: torch.Tensor,
     w: torch.Tensor,
@@ -106,33 +133,43 @@ def gemm(
     N, Kw = w.shape
     if K != Kw:
         raise ValueError(f"K mismatch: x {tuple(x.shape)} vs w {tuple(w.shape)}")
-    ep = GemmEpilogue()
-    ep.out = out.data_ptr()
-    ep.ldo = out.stride(-2)
-    ep.out_dtype = _dt(out)
-    ep.act = act
-    ep.bias = _ptr(_f32c(bias, N, "bias"))
-    ep.colscale = _ptr(_f32c(colscale, N, "colscale"))
-    if residual is not None:
-        ep.residual = residual.data_ptr()
-        ep.ldr = residual.stride(-2)
-        ep.residual_dtype = _dt(residual)
-    ep.residual_row_mod = residual_row_mod
-    if out_relu is not None:
-        if out_relu.dtype != torch.bfloat16:
-            raise TypeError("out_relu must be bfloat16")
-        ep.out_relu = out_relu.data_ptr()
-        ep.ldo_relu = out_relu.stride(-2)
-    ep.rows_per_group_in = rows_per_group_in
-    ep.rows_per_group_out = rows_per_group_out
-    ep.row_offset_out = row_offset_out
-    ep.flags = (1 if act_after_residual else 0) | (2 if relu_out_before_residual else 0)
+    ep = _epilogue(out, N, bias, act, colscale, residual, residual_row_mod, out_relu, rows_per_group_in, rows_per_group_out,
+                   row_offset_out, act_after_residual, relu_out_before_residual)
     lib = _lib.load()
-    with launch("gemm", 2.0 * M * N * K):
+    with launch("gemm", 2.0 * M * N * K, tag=f"{M}x{N}x{K}"):
         check(
             lib.ma_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), block_n, _stream()),
             "ma_gemm_bf16",
         )
+    return out
+
+
+def conv3x3(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    bias: Optional[torch.Tensor] = None,
+    act: int = MA_ACT_NONE,
+    residual: Optional[torch.Tensor] = None,
+    out_relu: Optional[torch.Tensor] = None,
+    block_n: int = 0,
+    act_after_residual: bool = False,
+    relu_out_before_residual: bool = False,
+) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 conv as implicit GEMM: x NHWC bf16 (n,H,W,C) contiguous, w [Cout, 9*C] bf16 (tap-major),
+    out [n*H*W, Cout] (rows = pixels). See ma_conv3x3_bf16."""
+    _req(x, torch.bfloat16, "x")
+    if w.dtype != torch.bfloat16 or w.dim() != 2 or w.stride(1) != 1 or out.stride(-1) != 1:
+        raise ValueError("conv3x3: w must be 2-D bf16 with contiguous rows")
+    n, H, W, C_ = x.shape
+    Cout = w.shape[0]
+    if w.shape[1] != 9 * C_ or out.shape[-1] != Cout or out.numel() // Cout != n * H * W:
+        raise ValueError(f"conv3x3: shape mismatch x {tuple(x.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
+    ep = _epilogue(out, Cout, bias, act, None, residual, 0, out_relu, 0, 0, 0, act_after_residual, relu_out_before_residual)
+    with launch("conv3x3", 2.0 * n * H * W * Cout * 9 * C_, tag=f"{n}x{H}x{W}x{C_}->{Cout}"):
+        check(_lib.load().ma_conv3x3_bf16(x.data_ptr(), n, H, W, C_, w.data_ptr(), w.stride(0), Cout, C.byref(ep), block_n,
+                                          _stream()), "ma_conv3x3_bf16")
     return out
 
 
@@ -149,12 +186,22 @@ def attention(
     q_seq_stride: Optional[int] = None,
     kv_seq_stride: Optional[int] = None,
     scale: Optional[float] = None,
+    kv_segments=None,
+    state=None,
+    state_in: bool = False,
+    state_out: bool = False,
 ) -> torch.Tensor:
     """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
 
     q/k/v/out are 2-D token-major bf16 views whose rows may be strided column slices of a wider matrix
-    (e.g. qkv[:, :D], qkv[:, D:2D], qkv[:, 2D:]); no head permutation is materialised. See ma_attention_fwd."""
+    (e.g. qkv[:, :D], qkv[:, D:2D], qkv[:, 2D:]); no head permutation is materialised. See ma_attention_fwd.
+
+    kv_segments: optional list of (row0, length) key/value row ranges (sum of lengths == kv_len).
+    state = (state_o fp32 [q_rows, heads*64], state_m fp32 [q_rows, heads]): with state_out the launch writes the
+    online-softmax state instead of `out`; with state_in it resumes from it.  See ma_attention_fwd_ex."""
     for t in (q, k, v, out):
+        if t is None:
+            continue
         if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
             raise ValueError("attention operands must be 2-D bf16 with contiguous rows")
     if q_seq_stride is None:
@@ -166,16 +213,33 @@ def attention(
     lib = _lib.load()
     # Column offsets are folded into the base pointers; the tensor map width is the row stride, which
     # always covers [col0, col0 + heads*64) of the parent matrix when the view is a column slice of it.
-    with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64):
+    ext = None
+    if kv_segments is not None or state_in or state_out:
+        ext = AttnExt()
+        if kv_segments is not None:
+            if len(kv_segments) > MA_ATTN_MAX_SEGMENTS:
+                raise ValueError(f"at most {MA_ATTN_MAX_SEGMENTS} kv segments")
+            ext.n_segments = len(kv_segments)
+            for i, (r0, ln) in enumerate(kv_segments):
+                ext.seg_row0[i], ext.seg_len[i] = int(r0), int(ln)
+        if state_in or state_out:
+            so, sm = state
+            if (so.dtype != torch.float32 or sm.dtype != torch.float32 or so.stride(1) != 1 or not sm.is_contiguous()
+                    or so.shape[0] < q.shape[0] or sm.shape != (so.shape[0], num_heads)):
+                raise ValueError("attention state must be (fp32 [q_rows, >=heads*64], fp32 contiguous [q_rows, heads])")
+            ext.flags = (MA_ATTN_STATE_IN if state_in else 0) | (MA_ATTN_STATE_OUT if state_out else 0)
+            ext.state_o, ext.ld_state_o, ext.state_m = so.data_ptr(), so.stride(0), sm.data_ptr()
+    with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64, tag=f"{num_seqs}x{num_heads}x{q_len}x{kv_len}"):
         check(
-            lib.ma_attention_fwd(
+            lib.ma_attention_fwd_ex(
                 q.data_ptr(), q.stride(0), q.shape[0], 0,
                 k.data_ptr(), k.stride(0), k.shape[0], 0,
                 v.data_ptr(), v.stride(0), 0,
-                out.data_ptr(), out.stride(0), 0,
-                num_seqs, num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, float(scale), _stream(),
+                _ptr(out), out.stride(0) if out is not None else num_heads * 64, 0,
+                num_seqs, num_heads, q_len, kv_len, q_seq_stride, kv_seq_stride, float(scale),
+                C.byref(ext) if ext is not None else None, _stream(),
             ),
-            "ma_attention_fwd",
+            "ma_attention_fwd_ex",
         )
     return out
 
@@ -332,3 +396,53 @@ def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Ten
             "ma_decode_dense",
         )
     return o
+
+
+# ------------------------------------------------------------------------------------------ geometric inputs
+def unshuffle_split(x: torch.Tensor, patch: int, cpad: int, factor: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 NHWC (n,H,W,cin) -> bf16 (n,H/p,W/p,3*cpad) split layout (ma_unshuffle_split); factor -> depth mode."""
+    _req(x, torch.float32, "x")
+    n, H, W, cin = x.shape
+    out = torch.empty(n, H // patch, W // patch, 3 * cpad, device=x.device, dtype=torch.bfloat16)
+    with launch("unshuffle"):
+        check(_lib.load().ma_unshuffle_split(x.data_ptr(), out.data_ptr(), n, H, W, cin, patch, cpad, 0 if factor is None else 1,
+                                             _ptr(factor), _stream()), "ma_unshuffle_split")
+    return out
+
+
+def depth_factor(depth: torch.Tensor):
+    """fp32 (n,H,W,1) -> (factor fp32 [n], log_factor8 fp32 [n,8]) (ma_depth_factor)."""
+    _req(depth, torch.float32, "depth")
+    n = depth.shape[0]
+    f = torch.empty(n, device=depth.device, dtype=torch.float32)
+    lf = torch.empty(n, 8, device=depth.device, dtype=torch.float32)
+    with launch("depth_factor"):
+        check(_lib.load().ma_depth_factor(depth.data_ptr(), n, depth.numel() // n, f.data_ptr(), lf.data_ptr(), _stream()),
+              "ma_depth_factor")
+    return f, lf
+
+
+def pose_inputs(quats: torch.Tensor, trans: torch.Tensor, has_pose: torch.Tensor):
+    """quats fp32 [V,4], trans fp32 [V,3], has_pose uint8 [V] -> (quats8, trans8, log_scale8) fp32 [V,8] (ma_pose_inputs)."""
+    _req(quats, torch.float32, "quats")
+    _req(trans, torch.float32, "trans")
+    _req(has_pose, torch.uint8, "has_pose")
+    V = quats.shape[0]
+    q8, t8, s8 = (torch.empty(V, 8, device=quats.device, dtype=torch.float32) for _ in range(3))
+    with launch("pose_inputs"):
+        check(_lib.load().ma_pose_inputs(quats.data_ptr(), trans.data_ptr(), has_pose.data_ptr(), V, q8.data_ptr(),
+                                         t8.data_ptr(), s8.data_ptr(), _stream()), "ma_pose_inputs")
+    return q8, t8, s8
+
+
+def fuse_add(feat: torch.Tensor, V: int, N: int, dense_a=None, a_slot=None, dense_b=None, b_slot=None, globals_=(), gw=None):
+    """In place: feat fp32 [V*N,C] += dense / global geometric features (ma_fuse_add)."""
+    _req(feat, torch.float32, "feat")
+    g = [None] * 4
+    for i, t in enumerate(globals_):
+        g[i] = None if t is None else _req(t, torch.float32, "global feature")
+    with launch("fuse_add"):
+        check(_lib.load().ma_fuse_add(feat.data_ptr(), V, N, feat.shape[1], _ptr(dense_a), _ptr(a_slot), _ptr(dense_b),
+                                      _ptr(b_slot), _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(gw), _stream()),
+              "ma_fuse_add")
+    return feat

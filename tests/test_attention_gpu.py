@@ -72,3 +72,63 @@ def test_attention_cross_lengths():
     ref = (torch.softmax(qf @ kf.transpose(1, 2) / 8.0, -1) @ vf).transpose(0, 1).reshape(Lq, D)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2, err
+
+
+def _ref_cross(q, k, v, H):
+    Lq, Lk = q.shape[0], k.shape[0]
+    qf = q.float().view(Lq, H, 64).transpose(0, 1)
+    kf = k.float().view(Lk, H, 64).transpose(0, 1)
+    vf = v.float().view(Lk, H, 64).transpose(0, 1)
+    return (torch.softmax(qf @ kf.transpose(1, 2) / 8.0, -1) @ vf).transpose(0, 1).reshape(Lq, H * 64)
+
+
+def test_attention_kv_segments_padded_slots():
+    """Keys spread over per-rank slots of a padded all-gather buffer (ragged slot lengths; NaN-free zero padding between)."""
+    from mapanything_b200 import ops
+
+    H, Lq, slot = 12, 1000, 1500
+    lens = [1370, 1369, 77, 1500]
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(7)
+    q = torch.randn(Lq, D, device="cuda", generator=g).bfloat16()
+    kv = torch.zeros(len(lens) * slot, 2 * D, device="cuda", dtype=torch.bfloat16)
+    parts = []
+    for r, ln in enumerate(lens):
+        blk = torch.randn(ln, 2 * D, device="cuda", generator=g).bfloat16()
+        kv[r * slot:r * slot + ln] = blk
+        parts.append(blk)
+    dense = torch.cat(parts, 0)
+    out = torch.empty(Lq, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, kv[:, :D], kv[:, D:], out, num_heads=H, num_seqs=1, q_len=Lq, kv_len=sum(lens),
+                  kv_seq_stride=kv.shape[0], kv_segments=[(r * slot, ln) for r, ln in enumerate(lens)])
+    ref = _ref_cross(q, dense[:, :D], dense[:, D:], H)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("order", [(0, 1, 2), (2, 0, 1)])
+def test_attention_state_carry_equals_single_pass(order):
+    """Local keys first (state out), remote keys later (state in): same result as one pass over all keys, any order."""
+    from mapanything_b200 import ops
+
+    H, Lq, slot = 12, 1369 * 2 + 1, 2800
+    lens = [2739, 2738, 1369]
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(8)
+    q = (torch.randn(Lq, D, device="cuda", generator=g) * 1.5).bfloat16()
+    kv = torch.zeros(len(lens) * slot, 2 * D, device="cuda", dtype=torch.bfloat16)
+    for r, ln in enumerate(lens):
+        kv[r * slot:r * slot + ln] = (torch.randn(ln, 2 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    segs = [(r * slot, ln) for r, ln in enumerate(lens)]
+    dense = torch.cat([kv[r0:r0 + ln] for r0, ln in segs], 0)
+    ref = _ref_cross(q, dense[:, :D], dense[:, D:], H)
+    state = (torch.full((Lq, D), float("nan"), device="cuda"), torch.full((Lq, H), float("nan"), device="cuda"))
+    first, rest = [segs[order[0]]], [segs[i] for i in order[1:]]
+    ops.attention(q, kv[:, :D], kv[:, D:], None, num_heads=H, num_seqs=1, q_len=Lq, kv_len=first[0][1],
+                  kv_seq_stride=kv.shape[0], kv_segments=first, state=state, state_out=True)
+    out = torch.empty(Lq, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, kv[:, :D], kv[:, D:], out, num_heads=H, num_seqs=1, q_len=Lq, kv_len=sum(l for _, l in rest),
+                  kv_seq_stride=kv.shape[0], kv_segments=rest, state=state, state_in=True)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out.float()).all()
+    assert err < 2e-2, err

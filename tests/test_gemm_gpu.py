@@ -26,7 +26,7 @@ def _check(y, ref, tol=2e-2, what=""):
     assert err <= tol * scale, f"{what}: max abs err {err:.4g} vs scale {scale:.4g}"
 
 
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 2128, 2256])
 @pytest.mark.parametrize("shape", [(128, 256, 64), (300, 512, 192), (2740, 1024, 1024), (1369, 96, 1024), (1000, 3072, 640)])
 def test_gemm_plain(bn, shape):
     from mapanything_b200 import ops
@@ -102,3 +102,38 @@ def test_gemm_row_remap_and_strides():
     ops.gemm(x2, w2, out2[:, :N2], bias=b2)
     _check(out2[:, :N2], _ref(x2, w2, b2), 2e-3, "ragged N")
     assert out2[:, N2:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n,H,W,C,Cout", [(2, 37, 37, 256, 256), (1, 19, 19, 768, 256), (3, 74, 74, 192, 256), (1, 148, 148, 96, 256),
+                                          (2, 40, 56, 128, 128), (1, 5, 3, 64, 32), (1, 130, 70, 128, 6)])
+@pytest.mark.parametrize("bn", [0, 128, 2128, 2256])
+def test_conv3x3_implicit_gemm_matches_torch(n, H, W, C, Cout, bn):
+    """Implicit-GEMM 3x3 conv (4-D TMA boxes, zero padding by out-of-bounds fill) vs F.conv2d on the same bf16 operands,
+    incl. C not a multiple of 64, ragged pixel tiles, ragged Cout, bias + ReLU + residual + twin ReLU output."""
+    import torch.nn.functional as F
+
+    from mapanything_b200 import ops
+    from mapanything_b200.ops import MA_ACT_RELU
+
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + H + W + C)
+    x = torch.randn(n, H, W, C, device="cuda", generator=g).bfloat16()
+    w4 = (torch.randn(Cout, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    w = w4.permute(0, 2, 3, 1).reshape(Cout, 9 * C).contiguous()  # [Cout][(ky,kx),Cin]
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * H * W, Cout)
+
+    out = torch.full((n * H * W, Cout), float("nan"), device="cuda")
+    ops.conv3x3(x, w, out, bias=bias, block_n=bn)
+    _check(out, ref, 2e-3, "conv3x3 fp32 out")
+
+    if Cout % 32 == 0:
+        res = torch.randn(n * H * W, Cout, device="cuda", generator=g).bfloat16()
+        o1 = torch.empty(n * H * W, Cout, device="cuda", dtype=torch.bfloat16)
+        o2 = torch.empty(n * H * W, Cout, device="cuda", dtype=torch.bfloat16)
+        ops.conv3x3(x, w, o1, bias=bias, residual=res, out_relu=o2, relu_out_before_residual=True, block_n=bn)
+        _check(o1, ref + res.float(), 1e-2, "conv3x3 + residual")
+        _check(o2, torch.relu(ref), 1e-2, "conv3x3 relu twin (before residual)")
+        o3 = torch.empty(n * H * W, Cout, device="cuda", dtype=torch.bfloat16)
+        ops.conv3x3(x, w, o3, bias=bias, act=MA_ACT_RELU, block_n=bn)
+        _check(o3, torch.relu(ref), 1e-2, "conv3x3 + relu")

@@ -1,0 +1,40 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): one scene sharded by view with the K/V all-gather global
+attention must reproduce the single-GPU forward of the same scene (same weights, same kernels; only the summation
+order of the online softmax differs)."""
+import json
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(world, cfg, V, size):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), str(ROOT / "tests" / "_sharded_worker.py"), cfg, str(V), str(size)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env={**os.environ})
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("SHARDED_RESULT ")][-1]
+    return json.loads(line[len("SHARDED_RESULT "):])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("cfg,V,size", [("tiny_config", 5, 70), ("mapanything_config", 5, 518)])
+def test_view_sharded_scene_matches_single_gpu(cfg, V, size):
+    world = 2
+    r = _run(world, cfg, V, size)
+    print(r)
+    assert r["counts"] == [3, 2]
+    assert r["worst_rel"] < 1e-2, r
