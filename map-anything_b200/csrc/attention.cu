@@ -14,6 +14,8 @@
 // Sequences are contiguous row ranges of a token-major matrix ([tokens][heads*64] slices of the fused
 // qkv GEMM output, so no head permute/copy is ever materialised).  Keys past kv_len are masked to -inf
 // (TMA zero-fills rows beyond the tensor; rows that belong to the next sequence are masked the same way).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -331,6 +333,318 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
   }
 }
 
+
+// ================================================================================================================
+// v2: one CTA per SM works on TWO 128-row query tiles (A, B) that share every K/V tile, with
+//   * 16 softmax warps (8 per query tile): a row is split between two threads (kv columns 0..63 / 64..127), so S is
+//     read from TMEM ONCE into 64 registers per thread and released immediately (the tensor core starts Q.K^T of the
+//     next tile while the exponentials of this one are computed); the row maximum is combined through shared memory;
+//   * the output accumulator O kept in TMEM (PV accumulates in place) with LAZY rescaling: O and the running sum are
+//     rescaled only when the row maximum grew by more than 2^8; until then probabilities are computed against the stale
+//     maximum (they stay <= 256, exact in fp32 / bf16 range), so the common tile does no correction work at all;
+//   * P written by the softmax warps straight into TENSOR MEMORY (tcgen05.st, two bf16 per 32-bit column) and consumed
+//     by the P.V MMA as a TMEM A operand: shared memory carries only Q, K and V.  With P staged in shared memory the
+//     kernel was bound by shared-memory bandwidth (Q.K^T reads 8 KB and P.V 6 KB per MMA, plus 32 KB of P writes per
+//     tile -- about as many cycles as the exponentials themselves on a 128 B/clk port);
+//   * a 4-deep K and V ring shared by both query tiles (half the L2 -> smem traffic per query row).
+// Same interface / masking / segment / carried-state semantics as the v1 kernel above.
+// ================================================================================================================
+constexpr int A2_THREADS = 18 * 32;
+constexpr int A2_KV_STAGES = 4;
+constexpr int A2_XBUF_BYTES = 2 * 2 * 128 * 2 * 4;
+constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + A2_XBUF_BYTES + 512;
+constexpr int A2_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
+constexpr float A2_RESCALE_LOG2 = 8.0f;
+
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                     // [2] tiles
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                  // [stages]
+  uint8_t* sV = sK + A2_KV_STAGES * ATT_TILE_BYTES;       // [stages]
+  float* xbuf = reinterpret_cast<float*>(sV + A2_KV_STAGES * ATT_TILE_BYTES);  // [2 parity][2 tiles][128 rows][2 halves]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xbuf) + A2_XBUF_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + A2_KV_STAGES;
+  uint64_t* v_full = k_empty + A2_KV_STAGES;
+  uint64_t* v_empty = v_full + A2_KV_STAGES;
+  uint64_t* s_full = v_empty + A2_KV_STAGES;  // [2]
+  uint64_t* s_empty = s_full + 2;             // [2]
+  uint64_t* p_full = s_empty + 2;             // [2]
+  uint64_t* p_empty = p_full + 2;             // [2]  (= "PV of the tile has completed")
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  const int q0 = blockIdx.x * 2 * ATT_BM;
+  const int head = blockIdx.y;
+  const int seq = blockIdx.z;
+  const int n_kv_tiles = p.n_kv_tiles;
+  const int n_qt = (q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
+  const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[ma] attention v2: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < A2_KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_empty[t], 8);
+      mbar_init(&p_full[t], 8);
+      mbar_init(&p_empty[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, A2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int q_row = static_cast<int>(seq * p.q_seq_stride) + q0;
+      const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
+      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
+      tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row + ATT_BM);
+      KvCursor cur;
+      for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
+        const int st = j % A2_KV_STAGES;
+        const uint32_t ph = (j / A2_KV_STAGES) & 1;
+        const int row = kv_row0 + cur.row0(p);
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, row);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+      auto issue_qk = [&](int j) {
+        const int st = j % A2_KV_STAGES;
+        const uint32_t ph = (j / A2_KV_STAGES) & 1;
+        mbar_wait(&k_full[st], ph);
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+        for (int t = 0; t < n_qt; ++t) {
+          mbar_wait(&s_empty[t], (j & 1) ^ 1);  // the softmax warps hold S of tile j-1 in registers
+          tc_fence_after();
+          const uint32_t q_addr = smem_u32(sQ + t * ATT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k)
+            umma_bf16_ss(tmem_base + t * ATT_BN, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[t]);
+        }
+        umma_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        if (j + 1 < n_kv_tiles) issue_qk(j + 1);
+        const int st = j % A2_KV_STAGES;
+        const uint32_t ph = (j / A2_KV_STAGES) & 1;
+        mbar_wait(&v_full[st], ph);
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        for (int t = 0; t < n_qt; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          tc_fence_after();
+          const uint32_t p_tmem = tmem_base + 384 + t * 64;  // 128 kv x bf16 = 64 columns, 8 columns per K = 16 step
+          const uint32_t acc0 = (j > 0 || state_in) ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
+            umma_bf16_ts(tmem_base + 256 + t * ATT_D, p_tmem + k * 8, bdesc, idesc_pv, k != 0 ? 1u : acc0);
+          }
+          umma_commit(&p_empty[t]);
+        }
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ---- softmax warps: (query tile t, TMEM lane quarter, kv-column half) ------------------------------------
+    const int sw = warp - 2;
+    const int t = sw >> 3;
+    const int quarter = warp & 3;
+    const int half = (sw & 7) >> 2;
+    if (t < n_qt) {
+      const int row = quarter * 32 + lane;
+      const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t tmem_s = tmem_base + lane_base + t * ATT_BN + half * 64;
+      const uint32_t tmem_o = tmem_base + lane_base + 256 + t * ATT_D + half * 32;
+      const uint32_t bar_id = 1 + t * 4 + quarter;
+      const int q_idx = q0 + t * ATT_BM + row;
+      const bool q_ok = q_idx < p.q_len;
+      const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
+      const uint32_t tmem_p = tmem_base + lane_base + 384 + t * 64 + half * 32;
+      float* xb = xbuf + (t * 128 + row) * 2;  // + parity * 512
+      const float sl2 = p.scale_log2;
+
+      float m_run = -INFINITY, l_run = 0.f;
+      if (state_in) {
+        const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D + half * 32;
+#pragma unroll 1
+        for (int c = 0; c < 32; c += 8) {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0u;
+          if (q_ok) {
+            const float4 x = *reinterpret_cast<const float4*>(so + c), y = *reinterpret_cast<const float4*>(so + c + 4);
+            o[0] = __float_as_uint(x.x); o[1] = __float_as_uint(x.y); o[2] = __float_as_uint(x.z); o[3] = __float_as_uint(x.w);
+            o[4] = __float_as_uint(y.x); o[5] = __float_as_uint(y.y); o[6] = __float_as_uint(y.z); o[7] = __float_as_uint(y.w);
+          }
+          tmem_st_32x32b_x8(tmem_o + c, o);
+        }
+        if (q_ok) {
+          m_run = p.state_m[q_grow * p.num_heads + head];
+          l_run = half == 0 ? 1.f : 0.f;
+        } else {
+          m_run = 0.f;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+
+      KvCursor cur;
+      for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
+        const int kv_valid = cur.valid(p);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t va[32], vb[32];  // this thread's 64 kv columns of row `row`
+        tmem_ld_32x32b_x32(tmem_s, va);
+        tmem_ld_32x32b_x32(tmem_s + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[t]);  // S is in registers: the tensor core may overwrite it
+
+        const int c0 = half * 64;
+        if (kv_valid < c0 + 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c0 + i >= kv_valid) va[i] = __float_as_uint(-INFINITY);
+            if (c0 + 32 + i >= kv_valid) vb[i] = __float_as_uint(-INFINITY);
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        float* xj = xb + (j & 1) * 512;
+        xj[half] = mx;
+        named_bar_sync(bar_id, 64);
+        const float m_tile = fmaxf(mx, xj[half ^ 1]);
+
+        // lazy rescale: adopt the new maximum only when it grew by more than 2^8
+        float m_new = m_run;
+        bool need = false;
+        if (j == 0 && !state_in) m_new = m_tile;
+        else if ((m_tile - m_run) * sl2 > A2_RESCALE_LOG2) { need = true; m_new = m_tile; }
+        bool waited = false;
+        if (__any_sync(0xffffffffu, need)) {
+          if (j > 0) { mbar_wait(&p_empty[t], (j - 1) & 1); waited = true; }  // PV of tile j-1 has completed
+          tc_fence_after();
+          const float alpha = need ? fast_exp2((m_run - m_new) * sl2) : 1.f;
+#pragma unroll 1
+          for (int c = 0; c < 32; c += 8) {  // rare path: 8 columns at a time keeps S (64 registers) resident
+            uint32_t o[8];
+            tmem_ld_32x32b_x8(tmem_o + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x8(tmem_o + c, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          l_run *= alpha;
+        }
+        m_run = m_new;
+        const float msc = m_run * sl2;
+        if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
+        // exponentials -> bf16 pairs -> this thread's 32 columns of the P operand in tensor memory, 8 columns per store
+        float l_tile = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t s0 = q < 2 ? va[16 * q + 2 * i] : vb[16 * (q - 2) + 2 * i];
+            const uint32_t s1 = q < 2 ? va[16 * q + 2 * i + 1] : vb[16 * (q - 2) + 2 * i + 1];
+            const float e0 = fast_exp2(fmaf(__uint_as_float(s0), sl2, -msc));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(s1), sl2, -msc));
+            l_tile += e0 + e1;
+            pk[i] = pack_bf16x2(e0, e1);
+          }
+          tmem_st_32x32b_x8(tmem_p + q * 8, pk);
+        }
+        l_run += l_tile;
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      // ---- finish: total row sum, normalise, store ----
+      mbar_wait(&p_empty[t], (n_kv_tiles - 1) & 1);
+      tc_fence_after();
+      float* xl = xb + (n_kv_tiles & 1) * 512;
+      xl[half] = l_run;
+      named_bar_sync(bar_id, 64);
+      const float l_tot = l_run + xl[half ^ 1];
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_o, o);
+      tmem_ld_wait();
+      const float inv_l = 1.0f / l_tot;
+      if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) {
+        float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D + half * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          so[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
+                              __uint_as_float(o[4 * i + 2]) * inv_l, __uint_as_float(o[4 * i + 3]) * inv_l);
+        if (half == 0) p.state_m[q_grow * p.num_heads + head] = m_run + __log2f(l_tot) / sl2;
+      } else if (q_ok) {
+        __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D + half * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<uint4*>(optr)[q] =
+              make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A2_TMEM_COLS);
+  }
+}
+
 }  // namespace ma
 
 extern "C" int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
@@ -428,8 +742,22 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.v_col0 = v_col0;
   p.o_col0 = o_col0;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  dim3 grid((q_len + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
-  attention_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  static const bool use_v1 = [] {
+    const char* e = getenv("MA_ATTN_V1");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (use_v1) {
+    dim3 grid((q_len + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
+    attention_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  } else {
+    static bool configured2 = false;
+    if (!configured2) {
+      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
+      configured2 = true;
+    }
+    dim3 grid((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM), num_heads, num_seqs);
+    attention_fwd_v2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+  }
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

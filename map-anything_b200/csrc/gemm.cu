@@ -24,15 +24,17 @@ struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+  static constexpr int BAR_BYTES = 1024;  // barrier block, padded so that the epilogue stages stay 1024-byte aligned
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024: manual alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                                   // 128 / 256 / 512: powers of two
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                         const ma_gemm_epilogue ep, const int M, const int N, const int K, const ConvGeom cg) {
+                         const __grid_constant__ CUtensorMap tmap_out, const ma_gemm_epilogue ep, const int M, const int N, const int K,
+                      const ConvGeom cg, const int epi_mode) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -44,6 +46,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;  // 8 x 4 KB TMA-store stages (1024-byte aligned)
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = lane_id();
@@ -142,6 +145,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       }
     }
   } else if (warp >= 4) {
+    uint8_t* epi_stage = sEpi + (warp - 4) * EPI_STAGE_BYTES;
     const int quarter = warp & 3;       // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;   // which half of the BN columns this warp drains
     int it = 0;
@@ -173,12 +177,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (row_ok && col0 < N) epilogue_store_chunk(ep, v, m, col0, N);
+        if (epi_mode) {  // warp-uniform: asynchronous bulk tensor store / reduce-add of the 32 x 32 chunk
+          if (col0 < N) epilogue_tma_chunk(&tmap_out, epi_mode, ep, v, tm * GEMM_BM + quarter * 32, col0, epi_stage, lane);
+        } else if (row_ok && col0 < N) {
+          epilogue_store_chunk(ep, v, m, col0, N);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[acc]);
     }
+    if (epi_mode && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -190,8 +199,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
-                       cudaStream_t stream, const ConvGeom& cg = ConvGeom{}) {
+static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
+                       const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg = ConvGeom{}) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -202,13 +211,13 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const ma_ge
   const int tiles_m = cg.mode ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = tiles_m * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, ep, M, N, K, cg);
+  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, tout, ep, M, N, K, cg, epi_mode);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
 
-int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
-                     cudaStream_t stream, const ConvGeom& cg);  // gemm2.cu
+int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
+                     const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg);  // gemm2.cu
 
 // Tile configuration codes accepted as `block_n`: 64 / 128 / 256 = one CTA per 128 x block_n tile (gemm.cu);
 // MA_GEMM_2CTA + 128 / 256 = CTA pair per 256 x bn tile (gemm2.cu).
@@ -327,11 +336,11 @@ extern "C" int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const 
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int K = 9 * C;
-  if (pair) return launch_gemm_2cta(bn, tx, tw, *epi, M, Cout, K, s, cg);
+  if (pair) return launch_gemm_2cta(bn, tx, tw, tw, 0, *epi, M, Cout, K, s, cg);
   switch (bn) {
-    case 256: return launch_gemm<256>(tx, tw, *epi, M, Cout, K, s, cg);
-    case 128: return launch_gemm<128>(tx, tw, *epi, M, Cout, K, s, cg);
-    default: return launch_gemm<64>(tx, tw, *epi, M, Cout, K, s, cg);
+    case 256: return launch_gemm<256>(tx, tw, tw, 0, *epi, M, Cout, K, s, cg);
+    case 128: return launch_gemm<128>(tx, tw, tw, 0, *epi, M, Cout, K, s, cg);
+    default: return launch_gemm<64>(tx, tw, tw, 0, *epi, M, Cout, K, s, cg);
   }
 }
 
@@ -367,11 +376,26 @@ extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t l
     int rc = make_tmap_bf16(&tw, w, 2, dims, strides, box);
     if (rc != MA_OK) return rc;
   }
+  // TMA epilogue (bulk tensor store / reduce-add) whenever the output rows are the GEMM rows
+  static const bool tma_epi = [] {
+    const char* e = getenv("MA_GEMM_TMA_EPILOGUE");
+    return e == nullptr || e[0] != '0';
+  }();
+  const int epi_mode = tma_epi ? tma_epilogue_mode(*epi, N, false) : 0;
+  CUtensorMap tout = tw;
+  if (epi_mode) {
+    const bool f32 = epi->out_dtype == MA_F32;
+    uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)epi->ldo * (f32 ? 4 : 2)};
+    uint32_t box[2] = {32, 32};
+    int rc = make_tmap(&tout, epi->out, f32 ? MA_F32 : MA_BF16, 2, dims, strides, box, f32 ? 128 : 64);
+    if (rc != MA_OK) return rc;
+  }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (pair) return launch_gemm_2cta(bn, tx, tw, *epi, M, N, K, s, ConvGeom{});
+  if (pair) return launch_gemm_2cta(bn, tx, tw, tout, epi_mode, *epi, M, N, K, s, ConvGeom{});
   switch (bn) {
-    case 256: return launch_gemm<256>(tx, tw, *epi, M, N, K, s);
-    case 128: return launch_gemm<128>(tx, tw, *epi, M, N, K, s);
-    default: return launch_gemm<64>(tx, tw, *epi, M, N, K, s);
+    case 256: return launch_gemm<256>(tx, tw, tout, epi_mode, *epi, M, N, K, s);
+    case 128: return launch_gemm<128>(tx, tw, tout, epi_mode, *epi, M, N, K, s);
+    default: return launch_gemm<64>(tx, tw, tout, epi_mode, *epi, M, N, K, s);
   }
 }

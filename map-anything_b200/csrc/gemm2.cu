@@ -24,15 +24,17 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the N rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int BAR_BYTES = 1024;  // padded: the epilogue stages behind it stay 1024-byte aligned
+  static constexpr int EPI_BYTES = G2_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const ma_gemm_epilogue ep, const int M, const int N, const int K, const ConvGeom cg) {
+                      const __grid_constant__ CUtensorMap tmap_out, const ma_gemm_epilogue ep, const int M, const int N, const int K,
+                      const ConvGeom cg, const int epi_mode) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -44,6 +46,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   uint64_t* bar_tfull = bar_empty + STAGES;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;  // 8 x 4 KB TMA-store stages (1024-byte aligned)
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = lane_id();
@@ -147,6 +150,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
     }
   } else if (warp >= 4) {
+    uint8_t* epi_stage = sEpi + (warp - 4) * EPI_STAGE_BYTES;
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&bar_tempty[0]), 0);
@@ -178,12 +182,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (row_ok && col0 < N) epilogue_store_chunk(ep, v, m, col0, N);
+        if (epi_mode) {  // warp-uniform: asynchronous bulk tensor store / reduce-add of the 32 x 32 chunk
+          if (col0 < N) epilogue_tma_chunk(&tmap_out, epi_mode, ep, v, tm * GEMM_BM + quarter * 32, col0, epi_stage, lane);
+        } else if (row_ok && col0 < N) {
+          epilogue_store_chunk(ep, v, m, col0, N);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tempty0 + acc * 8);
     }
+    if (epi_mode && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -195,8 +204,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 }
 
 template <int BN>
-static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
-                        cudaStream_t stream, const ConvGeom& cg) {
+static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
+                        const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg) {
   using Cfg = Gemm2Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -207,16 +216,16 @@ static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const ma_g
   const int tiles = ((rows_tiles + 1) / 2) * ((N + BN - 1) / BN);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm_bf16_2cta_kernel<BN><<<2 * clusters, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, ep, M, N, K, cg);
+  gemm_bf16_2cta_kernel<BN><<<2 * clusters, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, tout, ep, M, N, K, cg, epi_mode);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
 
 // Entry used by gemm.cu's dispatchers. bn2 in {128, 256}.
-int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const ma_gemm_epilogue& ep, int M, int N, int K,
-                     cudaStream_t stream, const ConvGeom& cg) {
-  if (bn2 == 256) return launch_gemm2<256>(tx, tw, ep, M, N, K, stream, cg);
-  return launch_gemm2<128>(tx, tw, ep, M, N, K, stream, cg);
+int launch_gemm_2cta(int bn2, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
+                     const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg) {
+  if (bn2 == 256) return launch_gemm2<256>(tx, tw, tout, epi_mode, ep, M, N, K, stream, cg);
+  return launch_gemm2<128>(tx, tw, tout, epi_mode, ep, M, N, K, stream, cg);
 }
 
 }  // namespace ma

@@ -159,4 +159,80 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
 }
 
 
+// ----------------------------------------------------------------------------------------------------------------
+// TMA epilogue (plain GEMMs whose output rows are the GEMM rows): the warp's 32 x 32 accumulator chunk gets
+// bias / activation / column scale applied per thread (thread = row), is written to a warp-private, hardware-swizzled
+// shared-memory stage and leaves the SM as ONE asynchronous bulk tensor store -- or, for the in-place fp32 residual of a
+// transformer block (x += gamma * (acc + b)), as a bulk tensor REDUCE-ADD executed at the L2, so the residual stream is
+// never read by the SM.  No strided 16-byte stores, no exposed global-load latency in the epilogue warps, ragged
+// M handled by TMA clipping.  mode: 1 = store, 2 = reduce-add.  All 32 lanes call; lane 0 issues the TMA.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
+
+__device__ __forceinline__ void epilogue_tma_chunk(const CUtensorMap* tmap_out, int mode, const ma_gemm_epilogue& ep,
+                                                   const uint32_t (&acc)[32], int row0, int col0, uint8_t* stage, int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (ep.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (ep.act == MA_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (ep.act == MA_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (ep.colscale) {
+    const float4* s4 = reinterpret_cast<const float4*>(ep.colscale + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s = __ldg(s4 + j);
+      v[4 * j] *= s.x; v[4 * j + 1] *= s.y; v[4 * j + 2] *= s.z; v[4 * j + 3] *= s.w;
+    }
+  }
+  // the previous bulk store of this warp must have finished reading the stage
+  if (lane == 0) tma_store_wait_read<0>();
+  __syncwarp();
+  if (ep.out_dtype == MA_F32) {
+    // rows of 128 B, SWIZZLE_128B: 16-byte chunk q of row r lives at r*128 + ((q ^ (r & 7)) << 4)
+    uint4* row = reinterpret_cast<uint4*>(stage + lane * 128);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      row[q ^ (lane & 7)] = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                                       __float_as_uint(v[4 * q + 3]));
+  } else {
+    // rows of 64 B, SWIZZLE_64B: chunk q of row r lives at r*64 + ((q ^ ((r >> 1) & 3)) << 4)
+    uint4* row = reinterpret_cast<uint4*>(stage + lane * 64);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      row[q ^ ((lane >> 1) & 3)] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                              pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (mode == 2) tma_reduce_add_2d(tmap_out, stage, col0, row0);
+    else tma_store_2d(tmap_out, stage, col0, row0);
+    tma_store_commit();
+  }
+}
+
+// Host side: can this launch use the TMA epilogue, and in which mode (0 = no)?
+inline int tma_epilogue_mode(const ma_gemm_epilogue& ep, int N, bool conv) {
+  if (conv || ep.rows_per_group_in != 0 || ep.residual_row_mod != 0 || ep.out_relu != nullptr || N % 32 != 0) return 0;
+  if ((ep.flags & (MA_GEMM_ACT_AFTER_RESIDUAL | MA_GEMM_RELU_OUT_BEFORE_RESIDUAL)) != 0) return 0;
+  const int64_t esz = ep.out_dtype == MA_F32 ? 4 : 2;
+  if ((ep.ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(ep.out) & 15) != 0) return 0;
+  if (ep.residual == nullptr) return 1;
+  if (ep.residual == ep.out && ep.residual_dtype == MA_F32 && ep.out_dtype == MA_F32 && ep.ldr == ep.ldo) return 2;
+  return 0;
+}
+
 }  // namespace ma

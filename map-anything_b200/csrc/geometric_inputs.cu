@@ -101,9 +101,14 @@ __global__ void pose_inputs_kernel(const float* __restrict__ quats, const float*
   const float r00 = 1 - 2 * (y * y + z * z), r01 = 2 * (x * y - w * z), r02 = 2 * (x * z + w * y);
   const float r10 = 2 * (x * y + w * z), r11 = 1 - 2 * (x * x + z * z), r12 = 2 * (y * z - w * x);
   const float r20 = 2 * (x * z - w * y), r21 = 2 * (y * z + w * x), r22 = 1 - 2 * (x * x + y * y);
+  // R t evaluated with ONE fixed operation order, so that R t_v - R t_0 is exactly 0 for v = 0 (the reference computes
+  // einsum(R, t_v) + (-einsum(R, t_0)) with identical kernels; a zero translation must not count as "non-zero" below)
+  auto rot_row = [](float a, float b, float c, float x_, float y_, float z_) {
+    return __fmaf_rn(c, z_, __fmaf_rn(b, y_, __fmul_rn(a, x_)));
+  };
   const float t0x = trans[0], t0y = trans[1], t0z = trans[2];
-  const float tix = -(r00 * t0x + r01 * t0y + r02 * t0z), tiy = -(r10 * t0x + r11 * t0y + r12 * t0z),
-              tiz = -(r20 * t0x + r21 * t0y + r22 * t0z);
+  const float tix = -rot_row(r00, r01, r02, t0x, t0y, t0z), tiy = -rot_row(r10, r11, r12, t0x, t0y, t0z),
+              tiz = -rot_row(r20, r21, r22, t0x, t0y, t0z);
   float dsum = 0.f, dcnt = 0.f;
   for (int v = threadIdx.x; v < V; v += blockDim.x) {
     float qx = 0.f, qy = 0.f, qz = 0.f, qw = 1.f, tx = 0.f, ty = 0.f, tz = 0.f;
@@ -115,9 +120,9 @@ __global__ void pose_inputs_kernel(const float* __restrict__ quats, const float*
       qz = iw * az + ix * ay - iy * ax + iz * aw;
       qw = iw * aw - ix * ax - iy * ay - iz * az;
       const float bx = trans[3 * v], by = trans[3 * v + 1], bz = trans[3 * v + 2];
-      tx = r00 * bx + r01 * by + r02 * bz + tix;
-      ty = r10 * bx + r11 * by + r12 * bz + tiy;
-      tz = r20 * bx + r21 * by + r22 * bz + tiz;
+      tx = __fadd_rn(rot_row(r00, r01, r02, bx, by, bz), tix);
+      ty = __fadd_rn(rot_row(r10, r11, r12, bx, by, bz), tiy);
+      tz = __fadd_rn(rot_row(r20, r21, r22, bx, by, bz), tiz);
     }
     float* q8 = quats8 + 8 * v;
     q8[0] = qx; q8[1] = qy; q8[2] = qz; q8[3] = qw; q8[4] = q8[5] = q8[6] = q8[7] = 0.f;

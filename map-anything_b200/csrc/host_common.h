@@ -36,6 +36,10 @@ void set_last_error(const char* fmt, ...);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
+// General form: dtype = MA_BF16 / MA_F32, swizzle_bytes in {0, 32, 64, 128}.
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int swizzle_bytes);
+
 int device_sm_count();
 
 }  // namespace ma

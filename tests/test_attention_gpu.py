@@ -35,7 +35,8 @@ def test_attention_self(nseq, L, H):
         got = out[s * L : (s + 1) * L].float()
         assert torch.isfinite(got).all(), f"non-finite output in seq {s}"
         err = (got - refs[s]).abs().max().item()
-        assert err < 2e-2, f"seq {s}: max abs err {err}"
+        # |out| reaches ~6 here (values are randn * 1.5): one bf16 ulp of the output alone is 1.6e-2 .. 3.1e-2
+        assert err < 3e-2, f"seq {s}: max abs err {err}"
 
 
 def test_attention_frame_inside_global_buffer():

@@ -35,11 +35,21 @@ def main():
         x = torch.randn(m, k, device="cuda").bfloat16()
         w = torch.randn(n, k, device="cuda").bfloat16()
         o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-        for bn in (0, 64, 128, 256):
+        for bn in (0, 128, 256, 2128, 2256):
             t = timeit(lambda: ops.gemm(x, w, o, block_n=bn))
             res.append({"kernel": "gemm", "name": name, "bn": bn, "M": m, "N": n, "K": k, "ms": t, "tflops": 2 * m * n * k / t / 1e9})
         t = timeit(lambda: torch.matmul(x, w.t()))
         res.append({"kernel": "cublas", "name": name, "M": m, "N": n, "K": k, "ms": t, "tflops": 2 * m * n * k / t / 1e9})
+    for name, (n, H, W, Cc, Co) in {"rn1_148": (4, 148, 148, 96, 256), "rcu_148": (4, 148, 148, 256, 256), "rcu_74": (4, 74, 74, 256, 256),
+                                    "reg1_296": (4, 296, 296, 256, 128), "reg2_518": (2, 518, 518, 128, 128)}.items():
+        x = torch.randn(n, H, W, Cc, device="cuda").bfloat16()
+        w = torch.randn(Co, 9 * Cc, device="cuda").bfloat16()
+        o = torch.empty(n * H * W, Co, device="cuda", dtype=torch.bfloat16)
+        for bn in (0, 128, 256, 2128, 2256):
+            if bn % 1000 > Co and bn:
+                continue
+            t = timeit(lambda: ops.conv3x3(x, w, o, block_n=bn))
+            res.append({"kernel": "conv3x3", "name": name, "bn": bn, "ms": t, "tflops": 2 * n * H * W * Co * 9 * Cc / t / 1e9})
     for name, (nseq, L, H) in {"enc_attn": (V, 1370, 16), "frame_attn": (V, 1369, 12), "global_attn": (1, 1369 * V + 1, 12)}.items():
         D = H * 64
         qkv = torch.randn(nseq * L, 3 * D, device="cuda").bfloat16()
