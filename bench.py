@@ -114,6 +114,32 @@ def make_host_views(v: int, seed: int):
     return [((torch.rand(1, 3, IMG, IMG, generator=g) - mean) / std).pin_memory() for _ in range(v)]
 
 
+def make_host_geometry(v: int, seed: int, first_view_identity: bool = True):
+    """SURVEY 8d config C3 inputs per view: pinhole intrinsics (f ~ U[400,600], c = 259), depth_z ~ U[1,4] m,
+    cam2world pose (view 0 identity), metric scale.  Pinned host tensors."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(v):
+        f = float(torch.empty(1).uniform_(400, 600, generator=g))
+        k = torch.tensor([[[f, 0, 259.0], [0, f, 259.0], [0, 0, 1.0]]])
+        d = torch.empty(1, IMG, IMG, 1).uniform_(1.0, 4.0, generator=g)
+        q = torch.randn(4, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 0.0, 1.0])
+        t = torch.randn(3, generator=g)
+        if i == 0 and first_view_identity:
+            q, t = torch.tensor([0.0, 0.0, 0.0, 1.0]), torch.zeros(3)
+        x, y, z, w = (q / q.norm()).tolist()
+        pose = torch.eye(4)
+        pose[:3, :3] = torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        pose[:3, 3] = t
+        out.append({"intrinsics": k.pin_memory(), "depth_z": d.pin_memory(), "camera_poses": pose[None].pin_memory(),
+                    "is_metric_scale": torch.tensor([True]).pin_memory()})
+    return out
+
+
 def run_reference(args):
     """The reference arm: the fp32 CPU oracle of the path, all host threads, bounded sample of the workload."""
     import torch
@@ -161,7 +187,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(v: int, gpus: int, multi: str = "shard") -> str:
+def workload_name(v: int, gpus: int, multi: str = "shard", multimodal: bool = False) -> str:
+    if multimodal:
+        return (f"MapAnything multi-modal (images+intrinsics+poses+depth), {v * gpus} views 518x518 bf16 on {gpus}xB200"
+                + (" (BASELINE config[2])" if v * gpus == 24 else ""))
     if gpus == 1:
         return f"MapAnything image-only, {v} views 518x518 bf16 on 1xB200 (BASELINE config[1])" if v == 8 else \
             f"MapAnything image-only, {v} views 518x518 bf16 on 1xB200"
@@ -194,7 +223,16 @@ def run_ours(args):
     shard = world > 1 and args.multi == "shard"
     v_scene = V * world if shard else V  # views of the scene each forward pass works on
     host_imgs = make_host_views(V, 1234 + rank)
+    host_extra = make_host_geometry(V, 4321 + rank, first_view_identity=(rank == 0)) if args.multimodal else [{} for _ in range(V)]
     dev_views = [{"img": im.to(dev), "data_norm_type": ["dinov2"]} for im in host_imgs]
+    if args.multimodal:
+        # forward() takes the model's internal keys: preprocess once (device resident), enable the geometric inputs
+        from mapanything_b200.preprocess import preprocess_input_views_for_inference
+
+        dev_views = preprocess_input_views_for_inference(
+            [{**v, **{k: x.to(dev) for k, x in e.items()}} for v, e in zip(dev_views, host_extra)])
+        model.geometric_input_config.update({"overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0, "depth_prob": 1.0,
+                                             "cam_prob": 1.0})
     model.engine()
     if shard:
         model.enable_view_sharding(views_per_rank=[V] * world)
@@ -210,7 +248,7 @@ def run_ours(args):
     d2h_keys = ("pts3d", "conf", "mask", "camera_poses", "intrinsics", "metric_scaling_factor")
 
     def e2e_step():
-        views = [{"img": im, "data_norm_type": ["dinov2"]} for im in host_imgs]  # pinned HOST tensors
+        views = [{"img": im, "data_norm_type": ["dinov2"], **e} for im, e in zip(host_imgs, host_extra)]  # pinned HOST tensors
         preds = model.infer(views)
         outs = [p[k].to("cpu", non_blocking=True) for p in preds for k in d2h_keys]
         torch.cuda.current_stream().synchronize()
@@ -274,14 +312,15 @@ def run_ours(args):
 
     outs = e2e_step()  # every rank: the sharded step is collective
     d2h = sum(o.numel() * o.element_size() for o in outs) * world
-    h2d = sum(im.numel() * 4 for im in host_imgs) * world
+    h2d = (sum(im.numel() * 4 for im in host_imgs)
+           + sum(x.numel() * x.element_size() for e in host_extra for x in e.values())) * world
     if rank == 0:
         cpu = cpu_baseline(V)
         line = {
             "metric": METRIC, "value": vps, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(V, world, args.multi), "views": V * world, "views_per_gpu": V,
+            "config": {"workload": workload_name(V, world, args.multi, args.multimodal), "views": V * world, "views_per_gpu": V,
                        "scene_views": v_scene, "tflop_per_view": gflop_per_view(v_scene) / 1e3, "image": IMG,
                        "weights": "random-init", "parallelism": "single" if world == 1 else
                        (f"view-shard x{world} + K/V all-gather" if shard else f"replicas x{world}"),
@@ -334,6 +373,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--views", type=int, default=8, help="views per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--multimodal", action="store_true",
+                    help="BASELINE config[2]: every view also carries intrinsics, depth and a camera pose (use with --views 24)")
     ap.add_argument("--multi", default="shard", choices=["shard", "replicas"],
                     help="N > 1: one scene of views*N views sharded by view (default) or N independent scenes")
     ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")

@@ -178,6 +178,11 @@ int ma_token_mean(const void* in, void* out, int n, int T, int C, void* stream);
  * the pose / scale heads, which the reference runs with autocast disabled (model.py:1599). */
 int ma_split_bf16x3(const float* in, int64_t ld_in, void* out, int rows, int C, void* stream);
 
+/* Narrow linear head out[row][0:N] = W[N][K] . x[row] + b (N <= 8, K <= 256, bf16 in, fp32 out): the final 1x1 conv of
+ * the DPT regressor (128 -> 6 channels per pixel; reference model.py:1326-1332) as a streaming kernel. */
+int ma_head_linear_small(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, float* out, int64_t ldo,
+                         int64_t rows, int N, int K, void* stream);
+
 /* fp32 variant of ma_token_mean. */
 int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* stream);
 

@@ -355,6 +355,7 @@ constexpr int A2_XBUF_BYTES = 2 * 2 * 128 * 2 * 4;
 constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + A2_XBUF_BYTES + 512;
 constexpr int A2_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 constexpr float A2_RESCALE_LOG2 = 8.0f;
+constexpr long long A2_STREAM_OFFSET_CYCLES = 1200;
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -528,6 +529,13 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tc_fence_before();
       }
 
+      // The two query tiles are independent softmax streams that share the MUFU unit.  Started together they stay in
+      // lockstep (both read S / reduce / synchronise at the same time, then both queue for MUFU); delaying stream B by
+      // about half a tile period once makes one stream's exponentials fill the other's load / reduce / barrier phases.
+      if (t == 1 && n_kv_tiles > 2) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < A2_STREAM_OFFSET_CYCLES) {}
+      }
       KvCursor cur;
       for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
         const int kv_valid = cur.valid(p);
@@ -549,9 +557,13 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
             if (c0 + 32 + i >= kv_valid) vb[i] = __float_as_uint(-INFINITY);
           }
         }
-        float mx = -INFINITY;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains, not one of length 64
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], fmaxf(__uint_as_float(va[i + c]), __uint_as_float(vb[i + c])));
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         float* xj = xb + (j & 1) * 512;
         xj[half] = mx;
         named_bar_sync(bar_id, 64);
@@ -582,23 +594,24 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         m_run = m_new;
         const float msc = m_run * sl2;
-        if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
-        // exponentials -> bf16 pairs -> this thread's 32 columns of the P operand in tensor memory, 8 columns per store
+        // exponentials -> bf16 pairs (two per 32-bit P column), all in registers first: the wait for the previous tile's
+        // P.V (which still reads the single P buffer in tensor memory) is only needed before the store below, so the
+        // whole exponential phase overlaps that MMA
         float l_tile = 0.f;
+        uint32_t pk[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t s0 = q < 2 ? va[16 * q + 2 * i] : vb[16 * (q - 2) + 2 * i];
-            const uint32_t s1 = q < 2 ? va[16 * q + 2 * i + 1] : vb[16 * (q - 2) + 2 * i + 1];
-            const float e0 = fast_exp2(fmaf(__uint_as_float(s0), sl2, -msc));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(s1), sl2, -msc));
-            l_tile += e0 + e1;
-            pk[i] = pack_bf16x2(e0, e1);
-          }
-          tmem_st_32x32b_x8(tmem_p + q * 8, pk);
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = fast_exp2(fmaf(__uint_as_float(va[2 * i]), sl2, -msc));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(va[2 * i + 1]), sl2, -msc));
+          const float e2 = fast_exp2(fmaf(__uint_as_float(vb[2 * i]), sl2, -msc));
+          const float e3 = fast_exp2(fmaf(__uint_as_float(vb[2 * i + 1]), sl2, -msc));
+          l_tile += (e0 + e1) + (e2 + e3);
+          pk[i] = pack_bf16x2(e0, e1);
+          pk[16 + i] = pack_bf16x2(e2, e3);
         }
+        if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
+        tc_fence_after();
+        tmem_st_32x32b_x32(tmem_p, pk);
         l_run += l_tile;
         tmem_st_wait();
         tc_fence_before();

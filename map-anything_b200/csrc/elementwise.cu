@@ -111,6 +111,52 @@ __global__ void layernorm_kernel(const LnParams p) {
   }
 }
 
+// Register-resident variant for fp32 rows with C = 128 * NV4 (768 / 1024 on this path): the row is read from global
+// memory ONCE (NV4 float4 per lane, all loads in flight together), mean and variance are reduced from registers
+// (two-pass, like nn.LayerNorm), the bf16 / fp32 result is written once: 4C B in + 2C (or 4C) B out per row.
+template <int NV4, typename TOut>
+__global__ void layernorm_f32_reg_kernel(const LnParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  const int lane = threadIdx.x & 31;
+  int64_t rin = r, rout = r;
+  if (p.rpg > 0) {
+    const int g = r / p.rpg, o = r - g * p.rpg;
+    rin = (int64_t)g * p.in_group_stride + p.in_row_offset + o;
+    rout = (int64_t)g * p.out_group_stride + p.out_row_offset + o;
+  }
+  const float4* x = reinterpret_cast<const float4*>(static_cast<const float*>(p.in) + rin * p.ld_in) + lane;
+  float4 v[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) v[i] = x[i * 32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / p.C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss = fmaf(a, a, ss); ss = fmaf(b, b, ss); ss = fmaf(c, c, ss); ss = fmaf(d, d, ss);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / p.C + p.eps);
+  TOut* y = static_cast<TOut*>(p.out) + rout * p.ld_out;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+    const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+    const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+    if constexpr (sizeof(TOut) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + c) = make_float4(o0, o1, o2, o3);
+    } else {
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // set_rows: dst[g*group_stride + row_offset][:] = a[:] (+ b[:]), fp32.  (cls token + pos_embed[0]; scale token.)
 // ----------------------------------------------------------------------------------------------
@@ -225,6 +271,45 @@ __global__ void token_mean_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfl
   if (rl == 0 && c < C) {
     const float tot = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
     out[(size_t)blockIdx.y * C + c] = __float2bfloat16(tot / T);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Narrow linear head: out[row][0:N] = W[N][K] . x[row] + b, N <= 8, K <= 256 (the last 1x1 conv of the DPT regressor,
+// 128 -> 6 channels on every 518 x 518 pixel).  Pure streaming read of x (2K bytes per row); a tensor-core tile would
+// carry 6 useful columns of 64.  One thread per row, W broadcast from shared memory, fp32 accumulate.
+// ----------------------------------------------------------------------------------------------
+__global__ void head_linear_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                                         int64_t ldw, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
+                                         int64_t rows, int N, int K) {
+  __shared__ __align__(16) float sw[8][256];
+  for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+    const int n = i / K, k = i - n * K;
+    sw[n][k] = n < N ? __bfloat162float(w[(int64_t)n * ldw + k]) : 0.f;
+  }
+  __syncthreads();
+  for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+      const uint4 u = xr[k8];
+      const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[n][k8 * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[n][k8 * 8 + 4]);
+        acc[n] = fmaf(xv[0], w0.x, acc[n]); acc[n] = fmaf(xv[1], w0.y, acc[n]);
+        acc[n] = fmaf(xv[2], w0.z, acc[n]); acc[n] = fmaf(xv[3], w0.w, acc[n]);
+        acc[n] = fmaf(xv[4], w1.x, acc[n]); acc[n] = fmaf(xv[5], w1.y, acc[n]);
+        acc[n] = fmaf(xv[6], w1.z, acc[n]); acc[n] = fmaf(xv[7], w1.w, acc[n]);
+      }
+    }
+    float* o = out + row * ldo;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) o[n] = acc[n];
   }
 }
 
@@ -386,7 +471,12 @@ extern "C" int ma_layernorm(const void* in, int in_dtype, int64_t ld_in, void* o
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (in_dtype == MA_F32 && out_dtype == MA_BF16) layernorm_kernel<float, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
+  const bool vec_ok = in_dtype == MA_F32 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec_ok && C == 1024 && out_dtype == MA_BF16) layernorm_f32_reg_kernel<8, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
+  else if (vec_ok && C == 768 && out_dtype == MA_BF16) layernorm_f32_reg_kernel<6, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
+  else if (vec_ok && C == 1024 && out_dtype == MA_F32) layernorm_f32_reg_kernel<8, float><<<grid, wpb * 32, 0, s>>>(p);
+  else if (vec_ok && C == 768 && out_dtype == MA_F32) layernorm_f32_reg_kernel<6, float><<<grid, wpb * 32, 0, s>>>(p);
+  else if (in_dtype == MA_F32 && out_dtype == MA_BF16) layernorm_kernel<float, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
   else if (in_dtype == MA_F32 && out_dtype == MA_F32) layernorm_kernel<float, float><<<grid, wpb * 32, 0, s>>>(p);
   else if (in_dtype == MA_BF16 && out_dtype == MA_BF16) layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
   else if (in_dtype == MA_BF16 && out_dtype == MA_F32) layernorm_kernel<__nv_bfloat16, float><<<grid, wpb * 32, 0, s>>>(p);
@@ -437,6 +527,18 @@ extern "C" int ma_token_mean(const void* in, void* out, int n, int T, int C, voi
   dim3 grid((C + 63) / 64, n);
   token_mean_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(in),
                                                                          static_cast<__nv_bfloat16*>(out), T, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_head_linear_small(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, float* out,
+                                    int64_t ldo, int64_t rows, int N, int K, void* stream) {
+  MA_REQUIRE(x && w && out && rows > 0, "ma_head_linear_small: null pointer");
+  MA_REQUIRE(N >= 1 && N <= 8 && K >= 8 && K <= 256 && K % 8 == 0 && ldx % 8 == 0 && ldo >= N,
+             "ma_head_linear_small: needs N <= 8, K <= 256, K %% 8 == 0 (N=%d K=%d)", N, K);
+  MA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "ma_head_linear_small: x not 16-byte aligned");
+  head_linear_small_kernel<<<grid_for(rows, 256, device_sm_count() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w), ldw, bias, out, ldo, rows, N, K);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

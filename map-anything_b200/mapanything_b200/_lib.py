@@ -78,6 +78,7 @@ SIGNATURES = {
     "ma_bilinear_align_corners": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ma_token_mean": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_decode_dense": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ma_head_linear_small": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _p]),
     "ma_split_bf16x3": (_i, [_p, _i64, _p, _i, _i, _p]),
     "ma_token_mean_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_rays_from_intrinsics": (_i, [_p, _p, _i, _i, _i, _p]),

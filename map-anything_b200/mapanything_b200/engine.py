@@ -593,7 +593,11 @@ class Engine:
             g1u = self._empty(n, H, W, g1.shape[3])
             ops.bilinear_ac(g1, g1u)
             g2 = self._conv3(g1u, self.reg2, act=MA_ACT_RELU)
-            ops.gemm(g2.reshape(n * H * W, -1), self.reg3.w, raw[s * H * W:(s + n) * H * W, :self.reg3.n], bias=self.reg3.b)
+            g2f, rawv = g2.reshape(n * H * W, -1), raw[s * H * W:(s + n) * H * W]
+            if self.reg3.n <= 8 and self.reg3.k <= 256 and self.reg3.k % 8 == 0:
+                ops.head_linear_small(g2f, self.reg3.w, self.reg3.b, rawv)   # 128 -> 6 per pixel: streaming kernel
+            else:
+                ops.gemm(g2f, self.reg3.w, rawv[:, :self.reg3.n], bias=self.reg3.b)
             # pose head on the final info-sharing features (split-bf16 precision)
             self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n])
         return raw, pose_raw

@@ -346,6 +346,18 @@ def token_mean(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def head_linear_small(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """out[:, :N] = x @ w.T + bias for N <= 8, K <= 256: x bf16 [rows,K], w bf16 [N,K], out fp32 [rows, >=N] (ma_head_linear_small)."""
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or out.dtype != torch.float32 or x.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("head_linear_small: bf16 x / w with contiguous rows, fp32 out")
+    rows, K = x.shape
+    N = w.shape[0]
+    with launch("head_linear", 2.0 * rows * N * K):
+        check(_lib.load().ma_head_linear_small(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _ptr(_f32c(bias, N, "bias")),
+                                               out.data_ptr(), out.stride(0), rows, N, K, _stream()), "ma_head_linear_small")
+    return out
+
+
 def split3(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [rows][C] (any row stride) -> bf16 [rows][3C] = [hi | lo | hi] (ma_split_bf16x3)."""
     if x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
