@@ -44,6 +44,15 @@ METRIC = "views_per_sec_518px"
 F_ENC, F_IS_LIN, F_FRAME, F_GLOBAL_PER_VIEW, F_DPT, F_POSE = 1013.6, 467.3, 69.1, 69.1, 308.9, 35.5
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM (10960 x 4096 x 1024, bf16 out), from the
+# `ncu --set full` capture profiles/r1_gemm_2cta_tma_epilogue.ncu-rep (summary: ..._ncu.csv, rows 1-2): 31.8 MB read +
+# 45.2 MB written.  Algorithmic bytes of that launch: 22.4 MB (X) + 8.4 MB (W) + 89.8 MB (Y) = 120.6 MB; DRAM traffic is
+# BELOW it because part of Y is still resident in the 126 MB L2 when the kernel ends -- no re-reads.
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 77.0e6
+NCU_GEMM_TRAFFIC_NOTE = ("bytes per launch of gemm 10960x4096x1024 (ncu, profiles/r1_gemm_2cta_tma_epilogue_ncu.csv); "
+                         "algorithmic 120.6 MB; the kernel is tensor-bound")
+
+
 def gflop_per_view(v: int) -> float:
     return F_ENC + F_IS_LIN + F_FRAME + F_GLOBAL_PER_VIEW * v + F_DPT + F_POSE
 
@@ -327,7 +336,8 @@ def run_ours(args):
                        "l2": "per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {
                 "bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH,
+                "traffic_note": NCU_GEMM_TRAFFIC_NOTE, "peak_source": peak_src,
                 "launches": gemm[2], "kernel_ms_per_step": gemm[1],
                 "gemm_share_of_step": gemm[1] / ms_step,
                 "step_achieved_tflops": step_tf, "step_frac": step_tf / peak_tf,

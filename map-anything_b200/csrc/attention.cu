@@ -336,9 +336,11 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
 
 // ================================================================================================================
 // v2: one CTA per SM works on TWO 128-row query tiles (A, B) that share every K/V tile, with
-//   * 16 softmax warps (8 per query tile): a row is split between two threads (kv columns 0..63 / 64..127), so S is
-//     read from TMEM ONCE into 64 registers per thread and released immediately (the tensor core starts Q.K^T of the
-//     next tile while the exponentials of this one are computed); the row maximum is combined through shared memory;
+//   * 8 softmax warps (4 per query tile), one thread per query ROW: the 128 scores of the row are read from TMEM ONCE
+//     into registers and S is released immediately (the tensor core starts Q.K^T of the next tile while the
+//     exponentials of this one are computed); row maximum and row sum are thread-local, so the softmax warps never
+//     synchronise with each other -- the two query tiles are free-running streams whose TMEM-read and MUFU phases
+//     interleave on each SM sub-partition (TMEM reads, 64 B/clk/SM, cost as many cycles as the exponentials);
 //   * the output accumulator O kept in TMEM (PV accumulates in place) with LAZY rescaling: O and the running sum are
 //     rescaled only when the row maximum grew by more than 2^8; until then probabilities are computed against the stale
 //     maximum (they stay <= 256, exact in fp32 / bf16 range), so the common tile does no correction work at all;
@@ -349,13 +351,11 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
 //   * a 4-deep K and V ring shared by both query tiles (half the L2 -> smem traffic per query row).
 // Same interface / masking / segment / carried-state semantics as the v1 kernel above.
 // ================================================================================================================
-constexpr int A2_THREADS = 18 * 32;
+constexpr int A2_THREADS = 10 * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 constexpr int A2_KV_STAGES = 4;
-constexpr int A2_XBUF_BYTES = 2 * 2 * 128 * 2 * 4;
-constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + A2_XBUF_BYTES + 512;
+constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + 512;
 constexpr int A2_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
 constexpr float A2_RESCALE_LOG2 = 8.0f;
-constexpr long long A2_STREAM_OFFSET_CYCLES = 1200;
 
 __global__ void __launch_bounds__(A2_THREADS, 1)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -364,8 +364,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint8_t* sQ = smem;                                     // [2] tiles
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                  // [stages]
   uint8_t* sV = sK + A2_KV_STAGES * ATT_TILE_BYTES;       // [stages]
-  float* xbuf = reinterpret_cast<float*>(sV + A2_KV_STAGES * ATT_TILE_BYTES);  // [2 parity][2 tiles][128 rows][2 halves]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xbuf) + A2_XBUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A2_KV_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = k_full + A2_KV_STAGES;
@@ -400,8 +399,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
-      mbar_init(&s_empty[t], 8);
-      mbar_init(&p_full[t], 8);
+      mbar_init(&s_empty[t], 4);
+      mbar_init(&p_full[t], 4);
       mbar_init(&p_empty[t], 1);
     }
     fence_barrier_init();
@@ -486,29 +485,25 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else {
-    // ---- softmax warps: (query tile t, TMEM lane quarter, kv-column half) ------------------------------------
-    const int sw = warp - 2;
-    const int t = sw >> 3;
+    // ---- softmax warps: (query tile t, TMEM lane quarter); thread = query row -------------------------------
+    const int t = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    const int half = (sw & 7) >> 2;
     if (t < n_qt) {
       const int row = quarter * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-      const uint32_t tmem_s = tmem_base + lane_base + t * ATT_BN + half * 64;
-      const uint32_t tmem_o = tmem_base + lane_base + 256 + t * ATT_D + half * 32;
-      const uint32_t bar_id = 1 + t * 4 + quarter;
+      const uint32_t tmem_s = tmem_base + lane_base + t * ATT_BN;
+      const uint32_t tmem_o = tmem_base + lane_base + 256 + t * ATT_D;
+      const uint32_t tmem_p = tmem_base + lane_base + 384 + t * 64;
       const int q_idx = q0 + t * ATT_BM + row;
       const bool q_ok = q_idx < p.q_len;
       const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
-      const uint32_t tmem_p = tmem_base + lane_base + 384 + t * 64 + half * 32;
-      float* xb = xbuf + (t * 128 + row) * 2;  // + parity * 512
       const float sl2 = p.scale_log2;
 
       float m_run = -INFINITY, l_run = 0.f;
       if (state_in) {
-        const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D + half * 32;
+        const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D;
 #pragma unroll 1
-        for (int c = 0; c < 32; c += 8) {
+        for (int c = 0; c < ATT_D; c += 8) {
           uint32_t o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = 0u;
@@ -519,55 +514,45 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           }
           tmem_st_32x32b_x8(tmem_o + c, o);
         }
-        if (q_ok) {
-          m_run = p.state_m[q_grow * p.num_heads + head];
-          l_run = half == 0 ? 1.f : 0.f;
-        } else {
-          m_run = 0.f;
-        }
+        m_run = q_ok ? p.state_m[q_grow * p.num_heads + head] : 0.f;
+        l_run = q_ok ? 1.f : 0.f;
         tmem_st_wait();
         tc_fence_before();
       }
 
-      // The two query tiles are independent softmax streams that share the MUFU unit.  Started together they stay in
-      // lockstep (both read S / reduce / synchronise at the same time, then both queue for MUFU); delaying stream B by
-      // about half a tile period once makes one stream's exponentials fill the other's load / reduce / barrier phases.
-      if (t == 1 && n_kv_tiles > 2) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < A2_STREAM_OFFSET_CYCLES) {}
-      }
       KvCursor cur;
       for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
         const int kv_valid = cur.valid(p);
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        uint32_t va[32], vb[32];  // this thread's 64 kv columns of row `row`
-        tmem_ld_32x32b_x32(tmem_s, va);
-        tmem_ld_32x32b_x32(tmem_s + 32, vb);
+        uint32_t v0[32], v1[32], v2[32], v3[32];  // the 128 scores of this thread's row
+        tmem_ld_32x32b_x32(tmem_s, v0);
+        tmem_ld_32x32b_x32(tmem_s + 32, v1);
+        tmem_ld_32x32b_x32(tmem_s + 64, v2);
+        tmem_ld_32x32b_x32(tmem_s + 96, v3);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[t]);  // S is in registers: the tensor core may overwrite it
 
-        const int c0 = half * 64;
-        if (kv_valid < c0 + 64) {
+        if (kv_valid < ATT_BN) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            if (c0 + i >= kv_valid) va[i] = __float_as_uint(-INFINITY);
-            if (c0 + 32 + i >= kv_valid) vb[i] = __float_as_uint(-INFINITY);
+            if (i >= kv_valid) v0[i] = __float_as_uint(-INFINITY);
+            if (32 + i >= kv_valid) v1[i] = __float_as_uint(-INFINITY);
+            if (64 + i >= kv_valid) v2[i] = __float_as_uint(-INFINITY);
+            if (96 + i >= kv_valid) v3[i] = __float_as_uint(-INFINITY);
           }
         }
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains, not one of length 64
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) mx4[c] = fmaxf(mx4[c], fmaxf(__uint_as_float(va[i + c]), __uint_as_float(vb[i + c])));
+        for (int i = 0; i < 32; ++i) {
+          mx4[0] = fmaxf(mx4[0], __uint_as_float(v0[i]));
+          mx4[1] = fmaxf(mx4[1], __uint_as_float(v1[i]));
+          mx4[2] = fmaxf(mx4[2], __uint_as_float(v2[i]));
+          mx4[3] = fmaxf(mx4[3], __uint_as_float(v3[i]));
         }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        float* xj = xb + (j & 1) * 512;
-        xj[half] = mx;
-        named_bar_sync(bar_id, 64);
-        const float m_tile = fmaxf(mx, xj[half ^ 1]);
+        const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
         // lazy rescale: adopt the new maximum only when it grew by more than 2^8
         float m_new = m_run;
@@ -580,7 +565,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tc_fence_after();
           const float alpha = need ? fast_exp2((m_run - m_new) * sl2) : 1.f;
 #pragma unroll 1
-          for (int c = 0; c < 32; c += 8) {  // rare path: 8 columns at a time keeps S (64 registers) resident
+          for (int c = 0; c < ATT_D; c += 8) {  // rare path
             uint32_t o[8];
             tmem_ld_32x32b_x8(tmem_o + c, o);
             tmem_ld_wait();
@@ -594,59 +579,65 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         m_run = m_new;
         const float msc = m_run * sl2;
-        // exponentials -> bf16 pairs (two per 32-bit P column), all in registers first: the wait for the previous tile's
-        // P.V (which still reads the single P buffer in tensor memory) is only needed before the store below, so the
-        // whole exponential phase overlaps that MMA
-        float l_tile = 0.f;
-        uint32_t pk[32];
+
+        // exponentials -> bf16 pairs (two per 32-bit P column) in registers; the wait for the previous tile's P.V
+        // (which still reads the single P buffer in tensor memory) is only needed before the stores
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pa[32], pb[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(va[2 * i]), sl2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(va[2 * i + 1]), sl2, -msc));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(vb[2 * i]), sl2, -msc));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(vb[2 * i + 1]), sl2, -msc));
-          l_tile += (e0 + e1) + (e2 + e3);
-          pk[i] = pack_bf16x2(e0, e1);
-          pk[16 + i] = pack_bf16x2(e2, e3);
+          const float e0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, -msc));
+          const float e1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, -msc));
+          const float e2 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, -msc));
+          const float e3 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, -msc));
+          const float e4 = fast_exp2(fmaf(__uint_as_float(v2[2 * i]), sl2, -msc));
+          const float e5 = fast_exp2(fmaf(__uint_as_float(v2[2 * i + 1]), sl2, -msc));
+          const float e6 = fast_exp2(fmaf(__uint_as_float(v3[2 * i]), sl2, -msc));
+          const float e7 = fast_exp2(fmaf(__uint_as_float(v3[2 * i + 1]), sl2, -msc));
+          l4[0] += e0 + e1; l4[1] += e2 + e3; l4[2] += e4 + e5; l4[3] += e6 + e7;
+          pa[i] = pack_bf16x2(e0, e1);
+          pa[16 + i] = pack_bf16x2(e2, e3);
+          pb[i] = pack_bf16x2(e4, e5);
+          pb[16 + i] = pack_bf16x2(e6, e7);
         }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
         tc_fence_after();
-        tmem_st_32x32b_x32(tmem_p, pk);
-        l_run += l_tile;
+        tmem_st_32x32b_x32(tmem_p, pa);
+        tmem_st_32x32b_x32(tmem_p + 32, pb);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
       }
 
-      // ---- finish: total row sum, normalise, store ----
+      // ---- finish: normalise, store ----
       mbar_wait(&p_empty[t], (n_kv_tiles - 1) & 1);
       tc_fence_after();
-      float* xl = xb + (n_kv_tiles & 1) * 512;
-      xl[half] = l_run;
-      named_bar_sync(bar_id, 64);
-      const float l_tot = l_run + xl[half ^ 1];
+      const float inv_l = 1.0f / l_run;
       uint32_t o[32];
-      tmem_ld_32x32b_x32(tmem_o, o);
-      tmem_ld_wait();
-      const float inv_l = 1.0f / l_tot;
-      if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) {
-        float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D + half * 32);
+#pragma unroll 1
+      for (int c = 0; c < ATT_D; c += 32) {
+        tmem_ld_32x32b_x32(tmem_o + c, o);
+        tmem_ld_wait();
+        if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) {
+          float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D + c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          so[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
-                              __uint_as_float(o[4 * i + 2]) * inv_l, __uint_as_float(o[4 * i + 3]) * inv_l);
-        if (half == 0) p.state_m[q_grow * p.num_heads + head] = m_run + __log2f(l_tot) / sl2;
-      } else if (q_ok) {
-        __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D + half * 32;
+          for (int i = 0; i < 8; ++i)
+            so[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
+                                __uint_as_float(o[4 * i + 2]) * inv_l, __uint_as_float(o[4 * i + 3]) * inv_l);
+        } else if (q_ok) {
+          __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D + c;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          reinterpret_cast<uint4*>(optr)[q] =
-              make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l),
-                         pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l),
-                         pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l),
-                         pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<uint4*>(optr)[q] =
+                make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
+        }
       }
+      if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) p.state_m[q_grow * p.num_heads + head] = m_run + __log2f(l_run) / sl2;
     }
   }
 
