@@ -48,7 +48,7 @@ struct AttnParams {
   float* state_o;
   int64_t ld_state_o;
   float* state_m;  // [q_rows][num_heads]
-  int num_heads;
+  int num_heads, num_seqs;
   int flags;  // MA_ATTN_STATE_IN / MA_ATTN_STATE_OUT
 };
 
@@ -351,7 +351,7 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
 //   * a 4-deep K and V ring shared by both query tiles (half the L2 -> smem traffic per query row).
 // Same interface / masking / segment / carried-state semantics as the v1 kernel above.
 // ================================================================================================================
-constexpr int A2_THREADS = 10 * 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
+constexpr int A2_THREADS = 11 * 32;  // warp 0 TMA, warp 1 / warp 10 MMA issuers of query tile A / B, warps 2..9 softmax
 constexpr int A2_KV_STAGES = 4;
 constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + 512;
 constexpr int A2_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
@@ -378,9 +378,22 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
   const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
   const int lane = lane_id();
-  const int q0 = blockIdx.x * 2 * ATT_BM;
-  const int head = blockIdx.y;
-  const int seq = blockIdx.z;
+  // 1-D grid over (query block, head, sequence).  All FULL 256-row query blocks come first, the ragged last block of
+  // every (head, sequence) -- cheaper, often a single 128-row tile -- is scheduled at the end where it fills the tail
+  // wave instead of occupying an SM slot for a full block's duration in the middle (1370-token views: 5 full + 1 ragged).
+  const int n_full = p.q_len / (2 * ATT_BM);
+  const int hs_count = p.num_heads * p.num_seqs;
+  int qb, hs;
+  if (static_cast<int>(blockIdx.x) < n_full * hs_count) {
+    qb = blockIdx.x % n_full;
+    hs = blockIdx.x / n_full;
+  } else {
+    qb = n_full;
+    hs = blockIdx.x - n_full * hs_count;
+  }
+  const int q0 = qb * 2 * ATT_BM;
+  const int head = hs % p.num_heads;
+  const int seq = hs / p.num_heads;
   const int n_kv_tiles = p.n_kv_tiles;
   const int n_qt = (q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
   const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
@@ -393,9 +406,9 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     mbar_init(q_full, 1);
     for (int s = 0; s < A2_KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], n_qt);  // one tcgen05.commit per query-tile stream
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], n_qt);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
@@ -440,25 +453,29 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, row);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 10) {
+    // One MMA issuer per query tile: the two softmax streams only meet at the K / V ring (a stage is released when
+    // BOTH issuers have committed it), so a slow row block in one tile never delays the other tile's Q.K^T.
+    const int t = warp == 1 ? 0 : 1;
+    if (lane == 0 && t < n_qt) {
       constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ + t * ATT_TILE_BYTES);
+      const uint32_t tmem_s = tmem_base + t * ATT_BN;
+      const uint32_t tmem_o = tmem_base + 256 + t * ATT_D;
+      const uint32_t p_tmem = tmem_base + 384 + t * 64;  // 128 kv x bf16 = 64 columns, 8 columns per K = 16 step
       auto issue_qk = [&](int j) {
         const int st = j % A2_KV_STAGES;
         const uint32_t ph = (j / A2_KV_STAGES) & 1;
         mbar_wait(&k_full[st], ph);
+        mbar_wait(&s_empty[t], (j & 1) ^ 1);  // the softmax warps hold S of tile j-1 in registers
+        tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-        for (int t = 0; t < n_qt; ++t) {
-          mbar_wait(&s_empty[t], (j & 1) ^ 1);  // the softmax warps hold S of tile j-1 in registers
-          tc_fence_after();
-          const uint32_t q_addr = smem_u32(sQ + t * ATT_TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k)
-            umma_bf16_ss(tmem_base + t * ATT_BN, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                         make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[t]);
-        }
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                       idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
         umma_commit(&k_empty[st]);
       };
       mbar_wait(q_full, 0);
@@ -468,19 +485,14 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int st = j % A2_KV_STAGES;
         const uint32_t ph = (j / A2_KV_STAGES) & 1;
         mbar_wait(&v_full[st], ph);
+        mbar_wait(&p_full[t], j & 1);
+        tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-        for (int t = 0; t < n_qt; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          tc_fence_after();
-          const uint32_t p_tmem = tmem_base + 384 + t * 64;  // 128 kv x bf16 = 64 columns, 8 columns per K = 16 step
-          const uint32_t acc0 = (j > 0 || state_in) ? 1u : 0u;
+        const uint32_t acc0 = (j > 0 || state_in) ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
-            const uint64_t bdesc = make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024);
-            umma_bf16_ts(tmem_base + 256 + t * ATT_D, p_tmem + k * 8, bdesc, idesc_pv, k != 0 ? 1u : acc0);
-          }
-          umma_commit(&p_empty[t]);
-        }
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_bf16_ts(tmem_o, p_tmem + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, k != 0 ? 1u : acc0);
+        umma_commit(&p_empty[t]);
         umma_commit(&v_empty[st]);
       }
     }
@@ -699,6 +711,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     p.state_o = ext->state_o; p.state_m = ext->state_m; p.ld_state_o = ext->ld_state_o;
   }
   p.num_heads = num_heads;
+  p.num_seqs = num_seqs;
   p.flags = flags;
   MA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
                  v_col0 % 8 == 0 && o_col0 % 8 == 0,
@@ -759,7 +772,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
       configured2 = true;
     }
-    dim3 grid((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM), num_heads, num_seqs);
+    dim3 grid(((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads * num_seqs);
     attention_fwd_v2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   }
   MA_CHECK_CUDA(cudaGetLastError());
