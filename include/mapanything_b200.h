@@ -255,6 +255,10 @@ int ma_edge_mask(const float* pts3d, const float* depth_z, int depth_stride, con
 int ma_apply_mask(const float* in, int in_stride, int in_offset, const uint8_t* mask, float* out, int64_t pixels, int width,
                   void* stream);
 
+/* Confidence mask (inference.py:393-415): per image thr = torch.quantile(conf, q) (linear interpolation, float32
+ * arithmetic of torch) by exact radix selection, mask = conf > thr (1 byte bool).  thr_out [n] optional. */
+int ma_quantile_mask(const float* conf, uint8_t* mask, float* thr_out, int n, int64_t per_image, float q, void* stream);
+
 /* out = a & b over n bool bytes. */
 int ma_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t n, void* stream);
 

@@ -273,6 +273,84 @@ __global__ void mask_and_kernel(const uint8_t* __restrict__ a, const uint8_t* __
     out[i] = (a[i] != 0 && b[i] != 0) ? 1 : 0;
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Per-image confidence quantile mask (reference inference.py:393-415): thr = torch.quantile(conf, q) with linear
+// interpolation, mask = conf > thr.  One block per image: exact order statistics by a 4 x 8-bit radix select over the
+// order-preserving integer image of the floats (no sort), then torch's lerp in float32:
+//   rank = q * (n - 1) (float32), lo = floor(rank), w = rank - lo,
+//   thr = w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w)      with a, b = the lo-th / ceil(rank)-th smallest values.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void quantile_mask_kernel(const float* __restrict__ conf, uint8_t* __restrict__ mask, float* __restrict__ thr_out,
+                                     int64_t per_image, float q) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_k, s_next, s_cnt_le;
+  const float* x = conf + (int64_t)blockIdx.x * per_image;
+  const float rank = q * static_cast<float>(per_image - 1);  // float32 like torch (q and n - 1 as float32 tensors)
+  const float lo_f = floorf(rank);
+  const float w = rank - lo_f;
+  const uint32_t k_lo = static_cast<uint32_t>(lo_f);
+  const bool need_hi = ceilf(rank) != lo_f;
+
+  if (threadIdx.x == 0) { s_prefix = 0u; s_k = k_lo; }
+  __syncthreads();
+  uint32_t less_total = 0;  // (thread 0) number of elements strictly below the selected value so far
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    const uint32_t pmask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int64_t i = threadIdx.x; i < per_image; i += blockDim.x) {
+      const uint32_t u = float_to_ordered(x[i]);
+      if ((u & pmask) == prefix) atomicAdd(&hist[(u >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t k = s_k, acc = 0;
+      int b = 0;
+      for (; b < 256; ++b) {
+        if (acc + hist[b] > k) break;
+        acc += hist[b];
+      }
+      s_k = k - acc;
+      less_total += acc;
+      s_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+      if (pass == 3) s_cnt_le = less_total + hist[b];  // elements <= selected value
+    }
+    __syncthreads();
+  }
+  const uint32_t v_lo = s_prefix;
+  float a = ordered_to_float(v_lo), b = a;
+  if (need_hi) {
+    if (k_lo + 1 >= s_cnt_le) {  // the next order statistic is the smallest value above v_lo
+      if (threadIdx.x == 0) s_next = 0xffffffffu;
+      __syncthreads();
+      uint32_t mn = 0xffffffffu;
+      for (int64_t i = threadIdx.x; i < per_image; i += blockDim.x) {
+        const uint32_t u = float_to_ordered(x[i]);
+        if (u > v_lo && u < mn) mn = u;
+      }
+      atomicMin(&s_next, mn);
+      __syncthreads();
+      b = ordered_to_float(s_next);
+    }
+  }
+  const float diff = b - a;
+  const float thr = w < 0.5f ? __fadd_rn(a, __fmul_rn(w, diff)) : __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.0f, w)));
+  if (threadIdx.x == 0 && thr_out) thr_out[blockIdx.x] = thr;
+  uint8_t* m = mask + (int64_t)blockIdx.x * per_image;
+  for (int64_t i = threadIdx.x; i < per_image; i += blockDim.x) m[i] = x[i] > thr ? 1 : 0;
+}
+
 }  // namespace ma
 
 using namespace ma;
@@ -335,6 +413,15 @@ extern "C" int ma_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, int
   MA_REQUIRE(a && b && out && n > 0, "ma_mask_and: bad arguments");
   const int grid = static_cast<int>((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
   mask_and_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_quantile_mask(const float* conf, uint8_t* mask, float* thr_out, int n, int64_t per_image, float q, void* stream) {
+  using namespace ma;
+  MA_REQUIRE(conf && mask && n > 0 && per_image > 0 && per_image < (1ll << 31), "ma_quantile_mask: bad arguments");
+  MA_REQUIRE(q >= 0.f && q <= 1.f, "ma_quantile_mask: q must be in [0, 1], got %f", (double)q);
+  quantile_mask_kernel<<<n, 1024, 0, static_cast<cudaStream_t>(stream)>>>(conf, mask, thr_out, per_image, q);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

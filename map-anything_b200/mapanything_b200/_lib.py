@@ -94,6 +94,7 @@ SIGNATURES = {
     "ma_pose_matrices": (_i, [_p, _p, _p, _i, _p]),
     "ma_edge_mask": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _p]),
     "ma_apply_mask": (_i, [_p, _i, _i, _p, _p, _i64, _i, _p]),
+    "ma_quantile_mask": (_i, [_p, _p, _p, _i, _i64, _f, _p]),
     "ma_mask_and": (_i, [_p, _p, _p, _i64, _p]),
 }
 

@@ -147,6 +147,17 @@ def mask_and(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def quantile_mask(conf: torch.Tensor, q: float) -> torch.Tensor:
+    """conf (B,H,W) fp32 -> bool (B,H,W): conf > torch.quantile(conf per image, q), computed by ma_quantile_mask."""
+    conf = conf.contiguous()
+    b = conf.shape[0]
+    out = torch.empty(conf.shape, device=conf.device, dtype=torch.bool)
+    check(_lib.load().ma_quantile_mask(conf.data_ptr(), out.data_ptr(), None, b, conf.numel() // b, float(q), _stream()),
+          "ma_quantile_mask")
+    ops._count()
+    return out
+
+
 def postprocess_model_outputs_for_inference(
     raw_outputs: List[Dict[str, torch.Tensor]],
     input_views: List[Dict[str, Any]],
@@ -172,11 +183,7 @@ def postprocess_model_outputs_for_inference(
         if apply_mask:
             final = out.get("non_ambiguous_mask")
             if apply_confidence_mask and "conf" in out:
-                # Non-default option ("next"): per-image quantile via torch on the device.
-                conf = out["conf"]
-                b = conf.shape[0]
-                thr = torch.quantile(conf.reshape(b, -1), confidence_percentile / 100.0, dim=1).view(b, 1, 1)
-                cm = conf > thr
+                cm = quantile_mask(out["conf"], confidence_percentile / 100.0)
                 final = cm if final is None else mask_and(final, cm)
             if mask_edges and final is not None and "pts3d" in out:
                 final = edge_mask(out["pts3d"], out["pts3d_cam"], final, edge_normal_threshold, edge_depth_threshold)

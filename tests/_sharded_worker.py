@@ -14,6 +14,7 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     cfg_name, V, size = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    multimodal = len(sys.argv) > 4 and sys.argv[4] == "mm"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -27,6 +28,24 @@ def main():
     model = mb.MapAnything(**cfg).to(dev).eval()
     g = torch.Generator().manual_seed(99)
     views = [{"img": torch.randn(1, 3, size, size, generator=g).to(dev), "data_norm_type": ["dinov2"]} for _ in range(V)]
+    if multimodal:  # internal keys of forward(): unit rays, depth along ray, poses (view 0 = identity), metric scale
+        from mapanything_b200.preprocess import preprocess_input_views_for_inference
+
+        for i, v in enumerate(views):
+            f = 0.8 * size + 0.4 * size * float(torch.rand(1, generator=g))
+            v["intrinsics"] = torch.tensor([[[f, 0, size / 2], [0, f, size / 2], [0, 0, 1.0]]], device=dev)
+            if i != 2:
+                v["depth_z"] = (1.0 + 3.0 * torch.rand(1, size, size, 1, generator=g)).to(dev)
+            if i != 3:
+                q = torch.randn(4, generator=g) * 0.2 + torch.tensor([0.0, 0.0, 0.0, 1.0])
+                t = torch.randn(3, generator=g)
+                if i == 0:
+                    q, t = torch.tensor([0.0, 0.0, 0.0, 1.0]), torch.zeros(3)
+                v["camera_poses"] = ((q / q.norm())[None].to(dev), t[None].to(dev))
+            v["is_metric_scale"] = torch.tensor([True], device=dev)
+        views = preprocess_input_views_for_inference(views)
+        model.geometric_input_config.update({"overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0, "depth_prob": 1.0,
+                                             "cam_prob": 1.0})
     counts = partition_views(V, world)
     lo = sum(counts[:rank])
     mine = views[lo:lo + counts[rank]]
@@ -34,7 +53,7 @@ def main():
     full = model([dict(v) for v in views])  # the whole scene on this GPU alone
     model.enable_view_sharding()
     part = model([dict(v) for v in mine])
-    part2 = model.infer([dict(v) for v in mine])  # infer() over the shard, count exchange included
+    part2 = model.infer([dict(v) for v in mine]) if not multimodal else part  # infer() over the shard, count exchange included
     model.disable_view_sharding()
     torch.cuda.synchronize()
 
@@ -46,7 +65,7 @@ def main():
             rel = ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
             worst[k] = max(worst.get(k, 0.0), rel)
         assert torch.isfinite(p["pts3d"]).all()
-    assert len(part2) == len(mine) and "mask" in part2[0]
+    assert len(part2) == len(mine) and (multimodal or "mask" in part2[0])
     t = torch.tensor([max(worst.values())], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -52,3 +52,18 @@ def test_head_linear_small_matches_torch(N, K):
     ref = x.float() @ w.float().t() + b
     assert (out[:, :N] - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
     assert (out[:, N:] == 7.0).all()
+
+
+@pytest.mark.parametrize("pct", [10, 50, 0, 100, 33.3])
+def test_quantile_mask_matches_torch_quantile(pct):
+    """apply_confidence_mask (reference inference.py:393-415): exact radix select + torch's float32 lerp."""
+    from mapanything_b200.inference import quantile_mask
+
+    g = torch.Generator().manual_seed(int(pct * 10))
+    conf = 1.0 + torch.exp(torch.randn(3, 70, 70, generator=g) * 2)
+    conf[1, :10] = 1.0          # many ties at the minimum
+    conf[2] = conf[2].round()   # heavy ties everywhere
+    thr = torch.quantile(conf.reshape(3, -1), pct / 100.0, dim=1).view(3, 1, 1)
+    want = conf > thr
+    got = quantile_mask(conf.cuda(), pct / 100.0).cpu()
+    assert torch.equal(got, want), (got != want).sum().item()
