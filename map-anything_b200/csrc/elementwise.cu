@@ -293,8 +293,9 @@ __global__ void head_linear_small_kernel(const __nv_bfloat16* __restrict__ x, in
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[n] = (bias && n < N) ? __ldg(bias + n) : 0.f;
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * ldx);
+#pragma unroll 4
     for (int k8 = 0; k8 < K / 8; ++k8) {
-      const uint4 u = xr[k8];
+      const uint4 u = __ldcs(xr + k8);  // streamed once
       const float xv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -537,7 +538,7 @@ extern "C" int ma_head_linear_small(const void* x, int64_t ldx, const void* w, i
   MA_REQUIRE(N >= 1 && N <= 8 && K >= 8 && K <= 256 && K % 8 == 0 && ldx % 8 == 0 && ldo >= N,
              "ma_head_linear_small: needs N <= 8, K <= 256, K %% 8 == 0 (N=%d K=%d)", N, K);
   MA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "ma_head_linear_small: x not 16-byte aligned");
-  head_linear_small_kernel<<<grid_for(rows, 256, device_sm_count() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  head_linear_small_kernel<<<grid_for(rows, 128, device_sm_count() * 16), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w), ldw, bias, out, ldo, rows, N, K);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;

@@ -48,8 +48,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
     const bool relu_early = (ep.flags & MA_GEMM_RELU_OUT_BEFORE_RESIDUAL) != 0;
     if (!act_late) {
       if (ep.act == MA_ACT_GELU) {
+        if (ep.out_dtype == MA_F32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+        }
       } else if (ep.act == MA_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -97,8 +102,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
     }
     if (act_late) {
       if (ep.act == MA_ACT_GELU) {
+        if (ep.out_dtype == MA_F32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+        }
       } else if (ep.act == MA_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -183,8 +193,13 @@ __device__ __forceinline__ void epilogue_tma_chunk(const CUtensorMap* tmap_out, 
     }
   }
   if (ep.act == MA_ACT_GELU) {
+    if (ep.out_dtype == MA_F32) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_fast(v[j]);
+    }
   } else if (ep.act == MA_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
