@@ -390,6 +390,9 @@ def main():
     ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core (set before torch is imported)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+        os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
         run_reference(args)
     else:
         run_ours(args)
