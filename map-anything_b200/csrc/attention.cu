@@ -50,6 +50,11 @@ struct AttnParams {
   float* state_m;  // [q_rows][num_heads]
   int num_heads, num_seqs;
   int flags;  // MA_ATTN_STATE_IN / MA_ATTN_STATE_OUT
+  // kv_split > 1: the kv tile range is cut into kv_split equal parts, each handled by its own CTA, which writes its
+  // partial softmax state to state_o + part * split_stride_o / state_m + part * split_stride_m (ma_attention_merge joins
+  // them).  Doubles / triples the CTA count when (query blocks x heads) fills the last wave of SMs badly.
+  int kv_split;
+  int64_t split_stride_o, split_stride_m;
 };
 
 // Cursor over the kv tiles of all segments, in segment order.
@@ -60,6 +65,9 @@ struct KvCursor {
   __device__ __forceinline__ void next(const AttnParams& p) {
     if ((jj + 1) * ATT_BN < p.seg_len[seg]) ++jj;
     else { ++seg; jj = 0; }
+  }
+  __device__ __forceinline__ void skip(const AttnParams& p, int n) {
+    for (int i = 0; i < n; ++i) next(p);
   }
 };
 
@@ -383,18 +391,22 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   // wave instead of occupying an SM slot for a full block's duration in the middle (1370-token views: 5 full + 1 ragged).
   const int n_full = p.q_len / (2 * ATT_BM);
   const int hs_count = p.num_heads * p.num_seqs;
+  const int n_slots = ((p.q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * hs_count;
+  const int part = blockIdx.x / n_slots;       // kv partition of this CTA (0 when kv_split == 1)
+  const int bid = blockIdx.x - part * n_slots;
   int qb, hs;
-  if (static_cast<int>(blockIdx.x) < n_full * hs_count) {
-    qb = blockIdx.x % n_full;
-    hs = blockIdx.x / n_full;
+  if (bid < n_full * hs_count) {
+    qb = bid % n_full;
+    hs = bid / n_full;
   } else {
     qb = n_full;
-    hs = blockIdx.x - n_full * hs_count;
+    hs = bid - n_full * hs_count;
   }
   const int q0 = qb * 2 * ATT_BM;
   const int head = hs % p.num_heads;
   const int seq = hs / p.num_heads;
-  const int n_kv_tiles = p.n_kv_tiles;
+  const int kv_tile0 = static_cast<int>((static_cast<int64_t>(part) * p.n_kv_tiles) / p.kv_split);
+  const int n_kv_tiles = static_cast<int>((static_cast<int64_t>(part + 1) * p.n_kv_tiles) / p.kv_split) - kv_tile0;
   const int n_qt = (q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
   const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
 
@@ -441,6 +453,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
       tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row + ATT_BM);
       KvCursor cur;
+      cur.skip(p, kv_tile0);
       for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
         const int st = j % A2_KV_STAGES;
         const uint32_t ph = (j / A2_KV_STAGES) & 1;
@@ -533,6 +546,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
 
       KvCursor cur;
+      cur.skip(p, kv_tile0);
       for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
         const int kv_valid = cur.valid(p);
         mbar_wait(&s_full[t], j & 1);
@@ -633,7 +647,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         tmem_ld_32x32b_x32(tmem_o + c, o);
         tmem_ld_wait();
         if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) {
-          float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D + c);
+          float4* so = reinterpret_cast<float4*>(p.state_o + part * p.split_stride_o + q_grow * p.ld_state_o + head * ATT_D + c);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             so[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
@@ -649,7 +663,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                            pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
         }
       }
-      if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) p.state_m[q_grow * p.num_heads + head] = m_run + __log2f(l_run) / sl2;
+      if (q_ok && (p.flags & MA_ATTN_STATE_OUT))
+        p.state_m[part * p.split_stride_m + q_grow * p.num_heads + head] = m_run + __log2f(l_run) / sl2;
     }
   }
 
@@ -659,6 +674,34 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     tc_fence_after();
     tmem_dealloc(tmem_base, A2_TMEM_COLS);
   }
+}
+
+
+// ----------------------------------------------------------------------------------------------------------------
+// Join of partial softmax states (kv_split > 1, or local + remote key ranges of the view-sharded global attention):
+//   out[row, h, :] = sum_p w_p o_p / sum_p w_p,   w_p = 2^((m'_p - max_p m'_p) * scale * log2 e)
+// where o_p is the normalised partial output and m'_p its shifted maximum.  One warp per (row, head); 256 B per partial.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void attention_merge_kernel(const float* __restrict__ state_o, int64_t ld_o, int64_t stride_o,
+                                       const float* __restrict__ state_m, int64_t stride_m, int n_part, int64_t rows,
+                                       int num_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= rows * num_heads) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = wid / num_heads;
+  const int h = static_cast<int>(wid - row * num_heads);
+  float mx = -INFINITY;
+  for (int pidx = 0; pidx < n_part; ++pidx) mx = fmaxf(mx, state_m[pidx * stride_m + row * num_heads + h]);
+  float ax = 0.f, ay = 0.f, wsum = 0.f;
+  for (int pidx = 0; pidx < n_part; ++pidx) {
+    const float w = fast_exp2((state_m[pidx * stride_m + row * num_heads + h] - mx) * scale_log2);
+    const float2 o = *reinterpret_cast<const float2*>(state_o + pidx * stride_o + row * ld_o + h * ATT_D + 2 * lane);
+    ax = fmaf(w, o.x, ax);
+    ay = fmaf(w, o.y, ay);
+    wsum += w;
+  }
+  const float inv = 1.0f / wsum;
+  *reinterpret_cast<uint32_t*>(out + row * ldo + h * ATT_D + 2 * lane) = pack_bf16x2(ax * inv, ay * inv);
 }
 
 }  // namespace ma
@@ -713,6 +756,17 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.num_heads = num_heads;
   p.num_seqs = num_seqs;
   p.flags = flags;
+  p.kv_split = 1;
+  p.split_stride_o = 0;
+  p.split_stride_m = 0;
+  if (ext && ext->kv_split > 1) {
+    MA_REQUIRE((flags & MA_ATTN_STATE_OUT) && !(flags & MA_ATTN_STATE_IN), "ma_attention_fwd: kv_split needs STATE_OUT and no STATE_IN");
+    MA_REQUIRE(ext->kv_split <= p.n_kv_tiles, "ma_attention_fwd: kv_split %d exceeds the %d kv tiles", ext->kv_split, p.n_kv_tiles);
+    MA_REQUIRE(ext->split_stride_o % 4 == 0, "ma_attention_fwd: split_stride_o must be a multiple of 4 floats");
+    p.kv_split = ext->kv_split;
+    p.split_stride_o = ext->split_stride_o;
+    p.split_stride_m = ext->split_stride_m;
+  }
   MA_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 &&
                  v_col0 % 8 == 0 && o_col0 % 8 == 0,
              "ma_attention_fwd: strides / column offsets must be multiples of 8 elements");
@@ -764,6 +818,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     return e != nullptr && e[0] == '1';
   }();
   if (use_v1) {
+    MA_REQUIRE(p.kv_split == 1, "ma_attention_fwd: kv_split is not supported by the v1 kernel");
     dim3 grid((q_len + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
     attention_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   } else {
@@ -772,9 +827,24 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
       configured2 = true;
     }
-    dim3 grid(((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads * num_seqs);
+    dim3 grid(((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads * num_seqs * p.kv_split);
     attention_fwd_v2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   }
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_attention_merge(const float* state_o, int64_t ld_state_o, int64_t split_stride_o, const float* state_m,
+                                  int64_t split_stride_m, int n_partials, int64_t rows, int num_heads, float softmax_scale,
+                                  void* out, int64_t ldo, void* stream) {
+  using namespace ma;
+  MA_REQUIRE(state_o && state_m && out && n_partials >= 1 && rows > 0 && num_heads > 0, "ma_attention_merge: bad arguments");
+  MA_REQUIRE(ld_state_o % 2 == 0 && split_stride_o % 2 == 0 && ldo % 2 == 0, "ma_attention_merge: strides must be even");
+  const int64_t warps = rows * num_heads;
+  const int64_t blocks = (warps * 32 + 255) / 256;
+  attention_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      state_o, ld_state_o, split_stride_o, state_m, split_stride_m, n_partials, rows, num_heads,
+      softmax_scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

@@ -240,6 +240,10 @@ class Engine:
         import os
 
         self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "2")))
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # measured on B200 (8 views, A/B in one run): splitting fills the last wave but the step time does not move (the
+        # chip is power-capped while the attention kernel runs) and the merge pass costs 0.5 ms -> off by default
+        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "0") == "1"
         self.dpt_chunk = 4  # views per DPT pass (bounds the im2col scratch: ~0.62 GB per view at 518 px)
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -292,6 +296,40 @@ class Engine:
         self._pos_cache[key] = out
         return out
 
+    def _pick_kv_split(self, q_len: int, kv_len: int, heads: int) -> int:
+        """How many CTAs share one (query block, head) of a long single-sequence attention.  (query blocks x heads) CTAs of
+        equal cost fill the SMs in whole waves (8 views: 516 CTAs on 148 SMs = 3.49 -> 4 waves); cutting the key range in
+        S parts multiplies the CTA count (1032 -> 6.97 waves) at the price of S fp32 partial states + one merge pass."""
+        if not getattr(self, "kv_split_enabled", True):
+            return 1
+        sms = self.sm_count
+        slots = -(-q_len // 256) * heads
+        tiles = -(-kv_len // 128)
+        t_core = 4.0 * q_len * kv_len * heads * 64 / 650e12
+        best, best_cost = 1, None
+        for S in (1, 2, 3, 4):
+            if S > 1 and tiles // S < 8:
+                break
+            waves = -(-slots * S // sms)
+            eff = slots * S / (waves * sms)
+            cost = t_core / eff * (1.0 + 0.02 * (S - 1))
+            if S > 1:
+                cost += q_len * heads * 64 * (8.0 * S + 2.0) / 5e12 + 4e-6
+            if best_cost is None or cost < best_cost:
+                best, best_cost = S, cost
+        return best
+
+    def _attention_one_sequence(self, q, k, v, out, heads: int, q_len: int, kv_len: int):
+        """Global attention over one long sequence, with the key range split over several CTAs when that fills the SMs."""
+        S = self._pick_kv_split(q_len, kv_len, heads)
+        if S == 1:
+            return ops.attention(q, k, v, out, num_heads=heads, num_seqs=1, q_len=q_len, kv_len=kv_len,
+                                 q_seq_stride=q_len, kv_seq_stride=kv_len)
+        state = (self._empty(S, q_len, heads * 64, dtype=torch.float32), self._empty(S, q_len, heads, dtype=torch.float32))
+        ops.attention(q, k, v, None, num_heads=heads, num_seqs=1, q_len=q_len, kv_len=kv_len, q_seq_stride=q_len,
+                      kv_seq_stride=kv_len, state=state, state_out=True, kv_split=S)
+        return ops.attention_merge(state, out, num_heads=heads)
+
     def _block(self, x, bw: BlockW, rows: int, heads: int, num_seqs: int, seq_len: int, seq_stride: int):
         """One pre-LN transformer block, in place on the fp32 residual stream x[:rows]."""
         dim = x.shape[1]
@@ -300,8 +338,11 @@ class Engine:
         ops.layernorm(xr, h, bw.n1w, bw.n1b)
         qkv = self._lin(h, bw.qkv)
         a = self._empty(rows, dim)
-        ops.attention(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, num_heads=heads, num_seqs=num_seqs,
-                      q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride)
+        if num_seqs == 1 and seq_len >= 2048:
+            self._attention_one_sequence(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, heads, seq_len, seq_len)
+        else:
+            ops.attention(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, num_heads=heads, num_seqs=num_seqs,
+                          q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride)
         ops.gemm(a, bw.proj.w, xr, bias=bw.proj.b, colscale=bw.ls1, residual=xr)
         ops.layernorm(xr, h, bw.n2w, bw.n2b)
         f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
@@ -327,10 +368,21 @@ class Engine:
         remote = plan.remote_segments()
         common = dict(num_heads=heads, num_seqs=1, q_len=rows, kv_seq_stride=kvbuf.shape[0])
         if remote:
-            ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=state, state_out=True, **common)
+            # partial softmax states: the local key range (runs while the all-gather is in flight) and the remote ranges
+            # (after it landed), each cut into as many parts as fills the SMs; one merge pass joins them all
+            kv_r = sum(l for _, l in remote)
+            s_l, s_r = self._pick_kv_split(rows, rows, heads), self._pick_kv_split(rows, kv_r, heads)
+            so, sm = state
+            if so.shape[0] < s_l + s_r:
+                so = self._empty(s_l + s_r, rows, dim, dtype=torch.float32)
+                sm = self._empty(s_l + s_r, rows, heads, dtype=torch.float32)
+                bufs["state"] = (so, sm)
+            ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=(so[:s_l], sm[:s_l]),
+                          state_out=True, kv_split=s_l, **common)
             work.wait()                                      # current stream waits for the gathered slots
-            ops.attention(q, K, Vv, a, kv_len=sum(l for _, l in remote), kv_segments=remote, state=state, state_in=True,
-                          **common)
+            ops.attention(q, K, Vv, None, kv_len=kv_r, kv_segments=remote, state=(so[s_l:s_l + s_r], sm[s_l:s_l + s_r]),
+                          state_out=True, kv_split=s_r, **common)
+            ops.attention_merge((so[:s_l + s_r], sm[:s_l + s_r]), a, num_heads=heads)
         else:
             work.wait()
             ops.attention(q, K, Vv, a, kv_len=rows, kv_segments=plan.local_segment(), **common)
@@ -510,7 +562,7 @@ class Engine:
                 # zero-initialised once: slot padding rows are never written, so masked keys stay finite
                 self._shard_bufs = {
                     "kv": torch.zeros(plan.world * plan.slot_rows, 2 * D, device=self.device, dtype=torch.bfloat16),
-                    "state": (self._empty(T, D, dtype=torch.float32), self._empty(T, self.is_heads, dtype=torch.float32)),
+                    "state": (self._empty(2, T, D, dtype=torch.float32), self._empty(2, T, self.is_heads, dtype=torch.float32)),
                 }
                 self._shard_bufs_key = key
             bufs = self._shard_bufs

@@ -190,6 +190,7 @@ def attention(
     state=None,
     state_in: bool = False,
     state_out: bool = False,
+    kv_split: int = 1,
 ) -> torch.Tensor:
     """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
 
@@ -198,7 +199,9 @@ def attention(
 
     kv_segments: optional list of (row0, length) key/value row ranges (sum of lengths == kv_len).
     state = (state_o fp32 [q_rows, heads*64], state_m fp32 [q_rows, heads]): with state_out the launch writes the
-    online-softmax state instead of `out`; with state_in it resumes from it.  See ma_attention_fwd_ex."""
+    online-softmax state instead of `out`; with state_in it resumes from it.  kv_split > 1 (with state_out): the key range
+    is cut into kv_split parts, one CTA each, and `state` holds one partial per part: (fp32 [kv_split, q_rows, heads*64],
+    fp32 [kv_split, q_rows, heads]); join them with attention_merge.  See ma_attention_fwd_ex."""
     for t in (q, k, v, out):
         if t is None:
             continue
@@ -213,6 +216,8 @@ def attention(
     lib = _lib.load()
     # Column offsets are folded into the base pointers; the tensor map width is the row stride, which
     # always covers [col0, col0 + heads*64) of the parent matrix when the view is a column slice of it.
+    if kv_split > 1 and not state_out:
+        raise ValueError("kv_split > 1 writes partial states: pass state=... and state_out=True")
     ext = None
     if kv_segments is not None or state_in or state_out:
         ext = AttnExt()
@@ -224,11 +229,15 @@ def attention(
                 ext.seg_row0[i], ext.seg_len[i] = int(r0), int(ln)
         if state_in or state_out:
             so, sm = state
-            if (so.dtype != torch.float32 or sm.dtype != torch.float32 or so.stride(1) != 1 or not sm.is_contiguous()
-                    or so.shape[0] < q.shape[0] or sm.shape != (so.shape[0], num_heads)):
-                raise ValueError("attention state must be (fp32 [q_rows, >=heads*64], fp32 contiguous [q_rows, heads])")
+            if so.dim() == 2:
+                so, sm = so.unsqueeze(0), sm.unsqueeze(0)
+            if (so.dtype != torch.float32 or sm.dtype != torch.float32 or so.stride(2) != 1 or sm.stride(2) != 1
+                    or sm.stride(1) != num_heads or so.shape[1] < q.shape[0] or sm.shape[1:] != (so.shape[1], num_heads)
+                    or so.shape[0] < kv_split or sm.shape[0] < kv_split):
+                raise ValueError("attention state must be (fp32 [parts, q_rows, >=heads*64], fp32 [parts, q_rows, heads])")
             ext.flags = (MA_ATTN_STATE_IN if state_in else 0) | (MA_ATTN_STATE_OUT if state_out else 0)
-            ext.state_o, ext.ld_state_o, ext.state_m = so.data_ptr(), so.stride(0), sm.data_ptr()
+            ext.state_o, ext.ld_state_o, ext.state_m = so.data_ptr(), so.stride(1), sm.data_ptr()
+            ext.kv_split, ext.split_stride_o, ext.split_stride_m = kv_split, so.stride(0), sm.stride(0)
     with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64, tag=f"{num_seqs}x{num_heads}x{q_len}x{kv_len}"):
         check(
             lib.ma_attention_fwd_ex(
@@ -241,6 +250,24 @@ def attention(
             ),
             "ma_attention_fwd_ex",
         )
+    return out
+
+
+def attention_merge(state, out: torch.Tensor, *, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """Joins partial softmax states (fp32 [parts, rows, heads*64], fp32 [parts, rows, heads]) into bf16 out [rows, heads*64]
+    (ma_attention_merge)."""
+    so, sm = state
+    if so.dim() != 3 or sm.dim() != 3 or so.dtype != torch.float32 or sm.dtype != torch.float32 or so.stride(2) != 1:
+        raise ValueError("attention_merge: state must be (fp32 [parts, rows, D], fp32 [parts, rows, heads])")
+    if out.dtype != torch.bfloat16 or out.stride(1) != 1 or sm.stride(1) != num_heads or sm.stride(2) != 1:
+        raise ValueError("attention_merge: out must be bf16 with contiguous rows")
+    parts, rows = so.shape[0], out.shape[0]
+    if scale is None:
+        scale = 64 ** -0.5
+    with launch("attention_merge"):
+        check(_lib.load().ma_attention_merge(so.data_ptr(), so.stride(1), so.stride(0), sm.data_ptr(), sm.stride(0), parts, rows,
+                                             num_heads, float(scale), out.data_ptr(), out.stride(0), _stream()),
+              "ma_attention_merge")
     return out
 
 

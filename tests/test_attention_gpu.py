@@ -133,3 +133,24 @@ def test_attention_state_carry_equals_single_pass(order):
     err = (out.float() - ref).abs().max().item()
     assert torch.isfinite(out.float()).all()
     assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("split", [2, 3])
+def test_attention_kv_split_and_merge(split):
+    """kv range cut into parts (one CTA each, partial states) + ma_attention_merge == one pass."""
+    from mapanything_b200 import ops
+
+    H, Lq, Lk = 12, 1369 * 2 + 1, 1369 * 3 + 1
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(9 + split)
+    q = (torch.randn(Lq, D, device="cuda", generator=g) * 1.2).bfloat16()
+    kv = (torch.randn(Lk, 2 * D, device="cuda", generator=g) * 1.2).bfloat16()
+    ref = _ref_cross(q, kv[:, :D], kv[:, D:], H)
+    state = (torch.full((split, Lq, D), float("nan"), device="cuda"), torch.full((split, Lq, H), float("nan"), device="cuda"))
+    ops.attention(q, kv[:, :D], kv[:, D:], None, num_heads=H, num_seqs=1, q_len=Lq, kv_len=Lk, state=state, state_out=True,
+                  kv_split=split)
+    out = torch.empty(Lq, D, device="cuda", dtype=torch.bfloat16)
+    ops.attention_merge(state, out, num_heads=H)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2.5e-2, err
