@@ -99,10 +99,11 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        sm, pw, mx, reasons = [], [], 0.0, set()
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
+                pw.append(float(r[2]))
                 mx = max(mx, float(r[1]))
                 for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if val.lower().startswith("active"):
@@ -110,8 +111,8 @@ class ClockSampler:
             except Exception:
                 continue
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx or None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def make_host_views(v: int, seed: int):
@@ -293,11 +294,16 @@ def run_ours(args):
         ms_fwd = timed(fwd_step, args.steps)
         launches = ops.LAUNCHES - launches0
         # instrumented pass of the same step for the per-kernel roofline (events around every GEMM launch)
+        # (single stream for this pass: with the encoder's two view groups on two streams the kernels overlap and the
+        # per-launch event times would count the time spent waiting for SMs)
+        eng = model.engine()
+        n_streams, eng.encoder_streams = eng.encoder_streams, 1
         ops.PROFILE = []
         barrier()
         fwd_step()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        eng.encoder_streams = n_streams
         for _ in range(2):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
