@@ -131,19 +131,24 @@ typedef struct ma_attn_ext {
   float* state_o;
   int64_t ld_state_o;
   float* state_m;
-  /* kv_split > 1 (needs MA_ATTN_STATE_OUT): the kv tile range is cut into kv_split parts, one CTA each; part i writes its
-   * state at state_o + i * split_stride_o, state_m + i * split_stride_m.  Join with ma_attention_merge.  0 / 1 = off. */
+  /* kv_split > 1: (query block, head) slots with index >= kv_split_from (slot order: full 256-row blocks of all heads
+   * first, ragged last blocks after them) are cut into kv_split CTAs, each taking a share of the key range; part i
+   * writes its state at state_o + i * split_stride_o, state_m + i * split_stride_m (state buffers required; state_m
+   * pre-filled with -inf).  Slots below kv_split_from run as one CTA and write `out` (or part 0 with STATE_OUT).
+   * Join with ma_attention_merge.  kv_split 0 / 1 = off. */
   int32_t kv_split;
-  int32_t reserved_;
+  int32_t kv_split_from;
   int64_t split_stride_o;
   int64_t split_stride_m;
 } ma_attn_ext;
 
 /* Joins n_partials partial softmax states (kv_split parts and / or local + remote key ranges of the sharded global
- * attention) into the bf16 attention output: out = sum_p w_p o_p / sum_p w_p, w_p = exp((m'_p - max m') * softmax_scale). */
+ * attention) into the bf16 attention output: out = sum_p w_p o_p / sum_p w_p, w_p = exp((m'_p - max m') * softmax_scale).
+ * first_slot >= 0 (single sequence): only the rows of the (query block, head) slots >= first_slot are visited (tail-only
+ * splitting); -1 = every (row, head).  state_m must be pre-filled with -inf (unused partials are skipped). */
 int ma_attention_merge(const float* state_o, int64_t ld_state_o, int64_t split_stride_o, const float* state_m,
                        int64_t split_stride_m, int n_partials, int64_t rows, int num_heads, float softmax_scale, void* out,
-                       int64_t ldo, void* stream);
+                       int64_t ldo, int first_slot, void* stream);
 int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, int q_col0, const void* k, int64_t ldk,
                         int64_t kv_rows, int k_col0, const void* v, int64_t ldv, int v_col0, void* out, int64_t ldo,
                         int o_col0, int num_seqs, int num_heads, int q_len, int kv_len, int64_t q_seq_stride,

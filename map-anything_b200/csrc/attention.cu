@@ -53,7 +53,7 @@ struct AttnParams {
   // kv_split > 1: the kv tile range is cut into kv_split equal parts, each handled by its own CTA, which writes its
   // partial softmax state to state_o + part * split_stride_o / state_m + part * split_stride_m (ma_attention_merge joins
   // them).  Doubles / triples the CTA count when (query blocks x heads) fills the last wave of SMs badly.
-  int kv_split;
+  int kv_split, split_from;  // CTAs of slots >= split_from are split (tail-only splitting); 0 = every slot
   int64_t split_stride_o, split_stride_m;
 };
 
@@ -392,8 +392,16 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const int n_full = p.q_len / (2 * ATT_BM);
   const int hs_count = p.num_heads * p.num_seqs;
   const int n_slots = ((p.q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * hs_count;
-  const int part = blockIdx.x / n_slots;       // kv partition of this CTA (0 when kv_split == 1)
-  const int bid = blockIdx.x - part * n_slots;
+  // slots [0, split_from) run as one CTA each; every later slot -- the ones that would form the badly filled last wave
+  // of SMs -- is cut into kv_split CTAs that each take a share of the key range and leave a partial softmax state
+  int bid = blockIdx.x, part = 0, nparts = 1;
+  if (static_cast<int>(blockIdx.x) >= p.split_from && p.kv_split > 1) {
+    const int r = blockIdx.x - p.split_from;
+    bid = p.split_from + r / p.kv_split;
+    part = r % p.kv_split;
+    nparts = p.kv_split;
+  }
+  (void)n_slots;
   int qb, hs;
   if (bid < n_full * hs_count) {
     qb = bid % n_full;
@@ -405,8 +413,9 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const int q0 = qb * 2 * ATT_BM;
   const int head = hs % p.num_heads;
   const int seq = hs / p.num_heads;
-  const int kv_tile0 = static_cast<int>((static_cast<int64_t>(part) * p.n_kv_tiles) / p.kv_split);
-  const int n_kv_tiles = static_cast<int>((static_cast<int64_t>(part + 1) * p.n_kv_tiles) / p.kv_split) - kv_tile0;
+  const int kv_tile0 = static_cast<int>((static_cast<int64_t>(part) * p.n_kv_tiles) / nparts);
+  const int n_kv_tiles = static_cast<int>((static_cast<int64_t>(part + 1) * p.n_kv_tiles) / nparts) - kv_tile0;
+  const bool write_state = (p.flags & MA_ATTN_STATE_OUT) != 0 || nparts > 1;
   const int n_qt = (q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
   const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
 
@@ -646,7 +655,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       for (int c = 0; c < ATT_D; c += 32) {
         tmem_ld_32x32b_x32(tmem_o + c, o);
         tmem_ld_wait();
-        if (q_ok && (p.flags & MA_ATTN_STATE_OUT)) {
+        if (q_ok && write_state) {
           float4* so = reinterpret_cast<float4*>(p.state_o + part * p.split_stride_o + q_grow * p.ld_state_o + head * ATT_D + c);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -663,7 +672,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
                            pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
         }
       }
-      if (q_ok && (p.flags & MA_ATTN_STATE_OUT))
+      if (q_ok && write_state)
         p.state_m[part * p.split_stride_m + q_grow * p.num_heads + head] = m_run + __log2f(l_run) / sl2;
     }
   }
@@ -681,20 +690,39 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 // Join of partial softmax states (kv_split > 1, or local + remote key ranges of the view-sharded global attention):
 //   out[row, h, :] = sum_p w_p o_p / sum_p w_p,   w_p = 2^((m'_p - max_p m'_p) * scale * log2 e)
 // where o_p is the normalised partial output and m'_p its shifted maximum.  One warp per (row, head); 256 B per partial.
+// state_m must be pre-filled with -inf: partial slots nobody wrote are skipped, rows without any partial are left alone.
 // ----------------------------------------------------------------------------------------------------------------
 __global__ void attention_merge_kernel(const float* __restrict__ state_o, int64_t ld_o, int64_t stride_o,
                                        const float* __restrict__ state_m, int64_t stride_m, int n_part, int64_t rows,
-                                       int num_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+                                       int num_heads, float scale_log2, __nv_bfloat16* __restrict__ out, int64_t ldo,
+                                       int first_slot) {
   const int64_t wid = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= rows * num_heads) return;
   const int lane = threadIdx.x & 31;
-  const int64_t row = wid / num_heads;
-  const int h = static_cast<int>(wid - row * num_heads);
+  int64_t row;
+  int h;
+  if (first_slot < 0) {  // every (row, head)
+    if (wid >= rows * num_heads) return;
+    row = wid / num_heads;
+    h = static_cast<int>(wid - row * num_heads);
+  } else {  // only the rows of the (query block, head) slots >= first_slot (slot order of attention_fwd_v2_kernel, 1 sequence)
+    const int n_full = static_cast<int>(rows / (2 * ATT_BM));
+    const int n_slots = static_cast<int>((rows + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads;
+    const int64_t slot = first_slot + wid / (2 * ATT_BM);
+    if (slot >= n_slots) return;
+    int qb;
+    if (slot < static_cast<int64_t>(n_full) * num_heads) { qb = static_cast<int>(slot % n_full); h = static_cast<int>(slot / n_full); }
+    else { qb = n_full; h = static_cast<int>(slot - static_cast<int64_t>(n_full) * num_heads); }
+    row = static_cast<int64_t>(qb) * 2 * ATT_BM + wid % (2 * ATT_BM);
+    if (row >= rows) return;
+  }
   float mx = -INFINITY;
   for (int pidx = 0; pidx < n_part; ++pidx) mx = fmaxf(mx, state_m[pidx * stride_m + row * num_heads + h]);
+  if (mx == -INFINITY) return;  // no partial was written for this (row, head): its CTA stored the final output itself
   float ax = 0.f, ay = 0.f, wsum = 0.f;
   for (int pidx = 0; pidx < n_part; ++pidx) {
-    const float w = fast_exp2((state_m[pidx * stride_m + row * num_heads + h] - mx) * scale_log2);
+    const float mp = state_m[pidx * stride_m + row * num_heads + h];
+    if (mp == -INFINITY) continue;  // unused partial slot (state_m is pre-filled with -inf)
+    const float w = fast_exp2((mp - mx) * scale_log2);
     const float2 o = *reinterpret_cast<const float2*>(state_o + pidx * stride_o + row * ld_o + h * ATT_D + 2 * lane);
     ax = fmaf(w, o.x, ax);
     ay = fmaf(w, o.y, ay);
@@ -757,10 +785,18 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.num_seqs = num_seqs;
   p.flags = flags;
   p.kv_split = 1;
+  p.split_from = 0;
   p.split_stride_o = 0;
   p.split_stride_m = 0;
+  const int n_slots_host = ((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads * num_seqs;
+  int grid_ctas = n_slots_host;
   if (ext && ext->kv_split > 1) {
-    MA_REQUIRE((flags & MA_ATTN_STATE_OUT) && !(flags & MA_ATTN_STATE_IN), "ma_attention_fwd: kv_split needs STATE_OUT and no STATE_IN");
+    MA_REQUIRE(!(flags & MA_ATTN_STATE_IN), "ma_attention_fwd: kv_split cannot resume from a state");
+    MA_REQUIRE(ext->state_o && ext->state_m, "ma_attention_fwd: kv_split needs the partial-state buffers");
+    MA_REQUIRE(ext->kv_split_from >= 0 && ext->kv_split_from <= n_slots_host, "ma_attention_fwd: kv_split_from out of range");
+    p.state_o = ext->state_o; p.state_m = ext->state_m; p.ld_state_o = ext->ld_state_o;
+    p.split_from = ext->kv_split_from;
+    grid_ctas = p.split_from + (n_slots_host - p.split_from) * ext->kv_split;
     MA_REQUIRE(ext->kv_split <= p.n_kv_tiles, "ma_attention_fwd: kv_split %d exceeds the %d kv tiles", ext->kv_split, p.n_kv_tiles);
     MA_REQUIRE(ext->split_stride_o % 4 == 0, "ma_attention_fwd: split_stride_o must be a multiple of 4 floats");
     p.kv_split = ext->kv_split;
@@ -827,7 +863,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
       configured2 = true;
     }
-    dim3 grid(((q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads * num_seqs * p.kv_split);
+    dim3 grid(grid_ctas);
     attention_fwd_v2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   }
   MA_CHECK_CUDA(cudaGetLastError());
@@ -836,15 +872,21 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
 
 extern "C" int ma_attention_merge(const float* state_o, int64_t ld_state_o, int64_t split_stride_o, const float* state_m,
                                   int64_t split_stride_m, int n_partials, int64_t rows, int num_heads, float softmax_scale,
-                                  void* out, int64_t ldo, void* stream) {
+                                  void* out, int64_t ldo, int first_slot, void* stream) {
   using namespace ma;
   MA_REQUIRE(state_o && state_m && out && n_partials >= 1 && rows > 0 && num_heads > 0, "ma_attention_merge: bad arguments");
   MA_REQUIRE(ld_state_o % 2 == 0 && split_stride_o % 2 == 0 && ldo % 2 == 0, "ma_attention_merge: strides must be even");
-  const int64_t warps = rows * num_heads;
+  int64_t warps = rows * num_heads;
+  if (first_slot >= 0) {
+    const int64_t n_slots = ((rows + 2 * ATT_BM - 1) / (2 * ATT_BM)) * num_heads;
+    MA_REQUIRE(first_slot <= n_slots, "ma_attention_merge: first_slot out of range");
+    warps = (n_slots - first_slot) * 2 * ATT_BM;
+    if (warps == 0) return MA_OK;
+  }
   const int64_t blocks = (warps * 32 + 255) / 256;
   attention_merge_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       state_o, ld_state_o, split_stride_o, state_m, split_stride_m, n_partials, rows, num_heads,
-      softmax_scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo);
+      softmax_scale * 1.4426950408889634f, static_cast<__nv_bfloat16*>(out), ldo, first_slot);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

@@ -56,7 +56,7 @@ class AttnExt(C.Structure):
         ("ld_state_o", C.c_int64),
         ("state_m", C.c_void_p),
         ("kv_split", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("kv_split_from", C.c_int32),
         ("split_stride_o", C.c_int64),
         ("split_stride_m", C.c_int64),
     ]
@@ -74,7 +74,7 @@ SIGNATURES = {
                               _i64, _f, _p]),
     "ma_attention_fwd_ex": (_i, [_p, _i64, _i64, _i, _p, _i64, _i64, _i, _p, _i64, _i, _p, _i64, _i, _i, _i, _i, _i, _i64,
                                  _i64, _f, C.POINTER(AttnExt), _p]),
-    "ma_attention_merge": (_i, [_p, _i64, _i64, _p, _i64, _i, _i64, _i, _f, _p, _i64, _p]),
+    "ma_attention_merge": (_i, [_p, _i64, _i64, _p, _i64, _i, _i64, _i, _f, _p, _i64, _i, _p]),
     "ma_patchify": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ma_layernorm": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i, _i, _f, _i, _i64, _i64, _i64, _i64, _p]),
     "ma_set_rows": (_i, [_p, _i64, _i, _i64, _i64, _p, _p, _i, _p]),

@@ -241,9 +241,7 @@ class Engine:
 
         self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "2")))
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-        # measured on B200 (8 views, A/B in one run): splitting fills the last wave but the step time does not move (the
-        # chip is power-capped while the attention kernel runs) and the merge pass costs 0.5 ms -> off by default
-        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "0") == "1"
+        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "1") != "0"  # tail-wave splitting of long attention
         self.dpt_chunk = 4  # views per DPT pass (bounds the im2col scratch: ~0.62 GB per view at 518 px)
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -296,39 +294,32 @@ class Engine:
         self._pos_cache[key] = out
         return out
 
-    def _pick_kv_split(self, q_len: int, kv_len: int, heads: int) -> int:
-        """How many CTAs share one (query block, head) of a long single-sequence attention.  (query blocks x heads) CTAs of
-        equal cost fill the SMs in whole waves (8 views: 516 CTAs on 148 SMs = 3.49 -> 4 waves); cutting the key range in
-        S parts multiplies the CTA count (1032 -> 6.97 waves) at the price of S fp32 partial states + one merge pass."""
-        if not getattr(self, "kv_split_enabled", True):
-            return 1
+    def _pick_tail_split(self, q_len: int, kv_len: int, heads: int):
+        """(first split slot, parts) for a long single-sequence attention, or None.  The (query block x head) CTAs have
+        equal cost and fill the SMs in whole waves (8 views: 516 CTAs on 148 SMs = 3 full waves + 72 CTAs on half the
+        chip).  Only the slots of that last partial wave are cut into `parts` CTAs, each with a share of the key range and
+        a partial softmax state; ma_attention_merge joins them (touching those rows only)."""
+        if not self.kv_split_enabled:
+            return None
         sms = self.sm_count
         slots = -(-q_len // 256) * heads
-        tiles = -(-kv_len // 128)
-        t_core = 4.0 * q_len * kv_len * heads * 64 / 650e12
-        best, best_cost = 1, None
-        for S in (1, 2, 3, 4):
-            if S > 1 and tiles // S < 8:
-                break
-            waves = -(-slots * S // sms)
-            eff = slots * S / (waves * sms)
-            cost = t_core / eff * (1.0 + 0.02 * (S - 1))
-            if S > 1:
-                cost += q_len * heads * 64 * (8.0 * S + 2.0) / 5e12 + 4e-6
-            if best_cost is None or cost < best_cost:
-                best, best_cost = S, cost
-        return best
+        rem = slots % sms
+        if slots <= sms or rem == 0 or rem > 0.7 * sms:
+            return None
+        parts = min(4, sms // rem, (-(-kv_len // 128)) // 8)
+        return (slots - rem, parts) if parts >= 2 else None
 
     def _attention_one_sequence(self, q, k, v, out, heads: int, q_len: int, kv_len: int):
-        """Global attention over one long sequence, with the key range split over several CTAs when that fills the SMs."""
-        S = self._pick_kv_split(q_len, kv_len, heads)
-        if S == 1:
-            return ops.attention(q, k, v, out, num_heads=heads, num_seqs=1, q_len=q_len, kv_len=kv_len,
-                                 q_seq_stride=q_len, kv_seq_stride=kv_len)
-        state = (self._empty(S, q_len, heads * 64, dtype=torch.float32), self._empty(S, q_len, heads, dtype=torch.float32))
-        ops.attention(q, k, v, None, num_heads=heads, num_seqs=1, q_len=q_len, kv_len=kv_len, q_seq_stride=q_len,
-                      kv_seq_stride=kv_len, state=state, state_out=True, kv_split=S)
-        return ops.attention_merge(state, out, num_heads=heads)
+        """Global attention over one long sequence; the last partial wave of CTAs is split over the key range."""
+        common = dict(num_heads=heads, num_seqs=1, q_len=q_len, kv_len=kv_len, q_seq_stride=q_len, kv_seq_stride=kv_len)
+        pick = self._pick_tail_split(q_len, kv_len, heads)
+        if pick is None:
+            return ops.attention(q, k, v, out, **common)
+        first, parts = pick
+        so = self._empty(parts, q_len, heads * 64, dtype=torch.float32)
+        sm = torch.full((parts, q_len, heads), float("-inf"), device=self.device, dtype=torch.float32)
+        ops.attention(q, k, v, out, state=(so, sm), kv_split=parts, kv_split_from=first, **common)
+        return ops.attention_merge((so, sm), out, num_heads=heads, first_slot=first)
 
     def _block(self, x, bw: BlockW, rows: int, heads: int, num_seqs: int, seq_len: int, seq_stride: int):
         """One pre-LN transformer block, in place on the fp32 residual stream x[:rows]."""
@@ -371,17 +362,21 @@ class Engine:
             # partial softmax states: the local key range (runs while the all-gather is in flight) and the remote ranges
             # (after it landed), each cut into as many parts as fills the SMs; one merge pass joins them all
             kv_r = sum(l for _, l in remote)
-            s_l, s_r = self._pick_kv_split(rows, rows, heads), self._pick_kv_split(rows, kv_r, heads)
+            p_l, p_r = self._pick_tail_split(rows, rows, heads), self._pick_tail_split(rows, kv_r, heads)
+            n_slots = -(-rows // 256) * heads
+            f_l, s_l = p_l if p_l else (n_slots, 1)
+            f_r, s_r = p_r if p_r else (n_slots, 1)
             so, sm = state
             if so.shape[0] < s_l + s_r:
                 so = self._empty(s_l + s_r, rows, dim, dtype=torch.float32)
                 sm = self._empty(s_l + s_r, rows, heads, dtype=torch.float32)
                 bufs["state"] = (so, sm)
+            sm.fill_(float("-inf"))                          # unused partial slots are skipped by the merge
             ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=(so[:s_l], sm[:s_l]),
-                          state_out=True, kv_split=s_l, **common)
+                          state_out=True, kv_split=s_l, kv_split_from=f_l, **common)
             work.wait()                                      # current stream waits for the gathered slots
             ops.attention(q, K, Vv, None, kv_len=kv_r, kv_segments=remote, state=(so[s_l:s_l + s_r], sm[s_l:s_l + s_r]),
-                          state_out=True, kv_split=s_r, **common)
+                          state_out=True, kv_split=s_r, kv_split_from=f_r, **common)
             ops.attention_merge((so[:s_l + s_r], sm[:s_l + s_r]), a, num_heads=heads)
         else:
             work.wait()

@@ -191,6 +191,7 @@ def attention(
     state_in: bool = False,
     state_out: bool = False,
     kv_split: int = 1,
+    kv_split_from: int = 0,
 ) -> torch.Tensor:
     """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
 
@@ -201,7 +202,8 @@ def attention(
     state = (state_o fp32 [q_rows, heads*64], state_m fp32 [q_rows, heads]): with state_out the launch writes the
     online-softmax state instead of `out`; with state_in it resumes from it.  kv_split > 1 (with state_out): the key range
     is cut into kv_split parts, one CTA each, and `state` holds one partial per part: (fp32 [kv_split, q_rows, heads*64],
-    fp32 [kv_split, q_rows, heads]); join them with attention_merge.  See ma_attention_fwd_ex."""
+    fp32 [kv_split, q_rows, heads], the latter pre-filled with -inf); join them with attention_merge.  kv_split_from: only
+    (query block, head) slots from that index on are split (the others write `out` / part 0).  See ma_attention_fwd_ex."""
     for t in (q, k, v, out):
         if t is None:
             continue
@@ -216,10 +218,10 @@ def attention(
     lib = _lib.load()
     # Column offsets are folded into the base pointers; the tensor map width is the row stride, which
     # always covers [col0, col0 + heads*64) of the parent matrix when the view is a column slice of it.
-    if kv_split > 1 and not state_out:
-        raise ValueError("kv_split > 1 writes partial states: pass state=... and state_out=True")
+    if kv_split > 1 and state is None:
+        raise ValueError("kv_split > 1 writes partial states: pass state=...")
     ext = None
-    if kv_segments is not None or state_in or state_out:
+    if kv_segments is not None or state_in or state_out or kv_split > 1:
         ext = AttnExt()
         if kv_segments is not None:
             if len(kv_segments) > MA_ATTN_MAX_SEGMENTS:
@@ -227,7 +229,7 @@ def attention(
             ext.n_segments = len(kv_segments)
             for i, (r0, ln) in enumerate(kv_segments):
                 ext.seg_row0[i], ext.seg_len[i] = int(r0), int(ln)
-        if state_in or state_out:
+        if state_in or state_out or kv_split > 1:
             so, sm = state
             if so.dim() == 2:
                 so, sm = so.unsqueeze(0), sm.unsqueeze(0)
@@ -238,6 +240,7 @@ def attention(
             ext.flags = (MA_ATTN_STATE_IN if state_in else 0) | (MA_ATTN_STATE_OUT if state_out else 0)
             ext.state_o, ext.ld_state_o, ext.state_m = so.data_ptr(), so.stride(1), sm.data_ptr()
             ext.kv_split, ext.split_stride_o, ext.split_stride_m = kv_split, so.stride(0), sm.stride(0)
+            ext.kv_split_from = kv_split_from
     with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64, tag=f"{num_seqs}x{num_heads}x{q_len}x{kv_len}"):
         check(
             lib.ma_attention_fwd_ex(
@@ -253,7 +256,7 @@ def attention(
     return out
 
 
-def attention_merge(state, out: torch.Tensor, *, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:
+def attention_merge(state, out: torch.Tensor, *, num_heads: int, scale: Optional[float] = None, first_slot: int = -1) -> torch.Tensor:
     """Joins partial softmax states (fp32 [parts, rows, heads*64], fp32 [parts, rows, heads]) into bf16 out [rows, heads*64]
     (ma_attention_merge)."""
     so, sm = state
@@ -266,7 +269,7 @@ def attention_merge(state, out: torch.Tensor, *, num_heads: int, scale: Optional
         scale = 64 ** -0.5
     with launch("attention_merge"):
         check(_lib.load().ma_attention_merge(so.data_ptr(), so.stride(1), so.stride(0), sm.data_ptr(), sm.stride(0), parts, rows,
-                                             num_heads, float(scale), out.data_ptr(), out.stride(0), _stream()),
+                                             num_heads, float(scale), out.data_ptr(), out.stride(0), first_slot, _stream()),
               "ma_attention_merge")
     return out
 

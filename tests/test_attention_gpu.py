@@ -146,11 +146,24 @@ def test_attention_kv_split_and_merge(split):
     q = (torch.randn(Lq, D, device="cuda", generator=g) * 1.2).bfloat16()
     kv = (torch.randn(Lk, 2 * D, device="cuda", generator=g) * 1.2).bfloat16()
     ref = _ref_cross(q, kv[:, :D], kv[:, D:], H)
-    state = (torch.full((split, Lq, D), float("nan"), device="cuda"), torch.full((split, Lq, H), float("nan"), device="cuda"))
+    state = (torch.full((split, Lq, D), float("nan"), device="cuda"), torch.full((split, Lq, H), float("-inf"), device="cuda"))
     ops.attention(q, kv[:, :D], kv[:, D:], None, num_heads=H, num_seqs=1, q_len=Lq, kv_len=Lk, state=state, state_out=True,
                   kv_split=split)
     out = torch.empty(Lq, D, device="cuda", dtype=torch.bfloat16)
     ops.attention_merge(state, out, num_heads=H)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()
+    assert err < 2.5e-2, err
+
+    # tail-only: slots below `first` write the final output themselves, the others leave partial states
+    n_slots = -(-Lq // 256) * H
+    first = n_slots - 17
+    state = (torch.full((split, Lq, D), float("nan"), device="cuda"), torch.full((split, Lq, H), float("-inf"), device="cuda"))
+    out2 = torch.full((Lq, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, kv[:, :D], kv[:, D:], out2, num_heads=H, num_seqs=1, q_len=Lq, kv_len=Lk, state=state, kv_split=split,
+                  kv_split_from=first)
+    assert torch.isnan(out2.float()).any(), "split slots must not have written the output yet"
+    ops.attention_merge(state, out2, num_heads=H, first_slot=first)
+    assert torch.isfinite(out2.float()).all()
+    err = (out2.float() - ref).abs().max().item()
     assert err < 2.5e-2, err

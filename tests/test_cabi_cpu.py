@@ -1,0 +1,72 @@
+"""CPU checks of the drop-in boundary: the C-ABI shared library loads on a GPU-less box and exports every symbol that
+include/mapanything_b200.h declares (no compute calls here), the ctypes table matches the header, and the package refuses
+to run without a CUDA device instead of falling back."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "mapanything_b200.h"
+
+
+def _declared():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(ma_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mapanything_b200 import _lib
+
+    if not _lib.LIB_PATH.exists():
+        pytest.skip("library not built (python map-anything_b200/build.py)")
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    names = _declared()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    lib.ma_abi_version.restype = ctypes.c_int
+    assert lib.ma_abi_version() == 1
+    lib.ma_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.ma_last_error(), bytes)
+
+
+def test_ctypes_table_matches_header():
+    from mapanything_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_struct_layouts_match_header_sizes():
+    """ma_gemm_epilogue / ma_attn_ext field-for-field sizes (LP64): guards against a header edit without a binding edit."""
+    from mapanything_b200 import _lib
+
+    assert ctypes.sizeof(_lib.GemmEpilogue) == 8 + 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 8 + 4 * 4
+    assert ctypes.sizeof(_lib.AttnExt) == 4 + 4 + 64 + 64 + 8 + 8 + 8 + 4 + 4 + 8 + 8
+
+
+def test_bad_arguments_return_status_not_crash():
+    """Argument validation happens on the host before any CUDA call: usable without a GPU."""
+    from mapanything_b200 import _lib
+
+    if not _lib.LIB_PATH.exists():
+        pytest.skip("library not built")
+    lib = _lib.load()
+    rc = lib.ma_layernorm(None, 1, 0, None, 0, 0, None, None, 0, 0, 1e-6, 0, 0, 0, 0, 0, None)
+    assert rc == -1
+    assert b"ma_layernorm" in lib.ma_last_error()
+    ep = _lib.GemmEpilogue()
+    rc = lib.ma_gemm_bf16(None, 0, None, 0, 0, 0, 0, ctypes.byref(ep), 0, None)
+    assert rc == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from mapanything_b200 import MapAnything, tiny_config
+
+    model = MapAnything(**tiny_config()).eval()
+    views = [{"img": torch.randn(1, 3, 70, 70), "data_norm_type": ["dinov2"]} for _ in range(2)]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(views)
