@@ -247,3 +247,51 @@ def test_forward_full_size_two_views_hard_weights():
         amp = oracle([dict(v) for v in views], amp_bf16=True)
     got = model([{**v, "img": v["img"].cuda()} for v in views])
     _assert_hard(_metrics(got, ref), _metrics(amp, ref), "full-size C1 (V=2), hard weights")
+
+
+def test_non_square_input_matches_oracle():
+    """518-px aspect-ratio table of the reference (image.py:40-65) produces non-square inputs: bicubic pos-embed
+    interpolation (vision_transformer.py:214-242), ragged token grids through every stage."""
+    from oracle.config import tiny_config
+
+    oracle, model = _build(tiny_config, seed=4, init="reference")
+    g = torch.Generator().manual_seed(77)
+    views = [{"img": torch.randn(1, 3, 56, 98, generator=g), "data_norm_type": ["dinov2"]} for _ in range(3)]
+    with torch.no_grad():
+        ref = oracle([dict(v) for v in views])
+        amp = oracle([dict(v) for v in views], amp_bf16=True)  # the reference's own bf16-autocast numerics: the floor
+    got = model([{**v, "img": v["img"].cuda()} for v in views])
+    assert got[0]["pts3d"].shape == (1, 56, 98, 3)
+    _assert_within(_metrics(got, ref), "tiny, non-square 56x98, V=3", floor=_metrics(amp, ref))
+
+
+def test_memory_efficient_inference_is_identical():
+    """memory_efficient_inference only changes how many views the dense head processes at once (reference
+    model.py:1263-1300, :1355-1438): results are the same."""
+    from oracle.config import tiny_config
+
+    _, model = _build(tiny_config, seed=5, init="reference")
+    views = [{**v, "img": v["img"].cuda()} for v in _views(5, 70, seed=5)]
+    a = model([dict(v) for v in views], memory_efficient_inference=False)
+    b = model([dict(v) for v in views], memory_efficient_inference=True)
+    for x, y in zip(a, b):
+        for k in ("pts3d", "conf", "cam_quats", "metric_scaling_factor"):
+            assert torch.equal(x[k], y[k]), k
+
+
+def test_infer_confidence_mask_removes_requested_fraction():
+    """apply_confidence_mask=True (reference inference.py:393-415): per image, about `confidence_percentile` % of the pixels
+    fall below the quantile threshold and leave the final mask."""
+    from oracle.config import tiny_config
+
+    _, model = _build(tiny_config, seed=6, init="reference")
+    views = _views(2, 70, seed=6)
+    base = model.infer([dict(v) for v in views], mask_edges=False, apply_confidence_mask=False)
+    cm = model.infer([dict(v) for v in views], mask_edges=False, apply_confidence_mask=True, confidence_percentile=25)
+    for b, c in zip(base, cm):
+        conf = c["conf"][0].cpu()
+        thr = torch.quantile(conf.reshape(-1), 0.25)
+        want = b["mask"][0, ..., 0].cpu() & (conf > thr)
+        assert torch.equal(c["mask"][0, ..., 0].cpu(), want)
+        kept = (conf > thr).float().mean().item()
+        assert 0.70 <= kept <= 0.76
