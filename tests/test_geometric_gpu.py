@@ -163,3 +163,37 @@ def test_infer_ignore_flags_fall_back_to_image_only():
     b = model.infer([{"img": v["img"], "data_norm_type": v["data_norm_type"]} for v in views], apply_mask=False)
     for x, y in zip(a, b):
         assert torch.equal(x["pts3d"], y["pts3d"])
+
+
+def test_forward_full_size_multimodal_two_views():
+    """BASELINE config 3 at full width (ViT-L, D = 768, 518 px; 2 views to keep the CPU oracle affordable): intrinsics + depth +
+    poses through the full-size geometric encoders (588 / 196 -> 588 -> 768 -> 1024 convs, 592-channel padding, split-bf16
+    first conv and global MLPs).  Bound: the stated tolerances or 2x the reference's own bf16-autocast floor."""
+    from mapanything_b200.preprocess import preprocess_input_views_for_inference
+    from oracle import inference as I
+    from oracle.config import mapanything_config
+
+    oracle, model = _build(mapanything_config, seed=0, init="reference")
+    views = _multimodal_views(2, 518, seed=51)
+    on = {"overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0, "depth_prob": 1.0, "cam_prob": 1.0}
+    oracle.geometric_input_config.update(on)
+    model.geometric_input_config.update(on)
+    pv_cpu = I.preprocess_views([dict(v) for v in views])
+    with torch.no_grad():
+        ref, ref_int = oracle(pv_cpu, return_internals=True)
+        amp = oracle(pv_cpu, amp_bf16=True)
+        _, img_only = oracle([{"img": v["img"], "data_norm_type": v["data_norm_type"]} for v in views], return_internals=True)
+    pv = preprocess_input_views_for_inference(_cuda(views))
+    got = model(pv)
+    # the geometric inputs must actually move the fused features, and we must follow that move
+    eng = model.engine()
+    with torch.no_grad():
+        feat = eng.encode(torch.cat([v["img"] for v in pv]))
+        model._fuse_geometric_inputs(eng, feat, pv, 0, 37 * 37, None, None)
+        fused = eng.fuse_norm(feat)
+    want = ref_int["fused"].permute(0, 2, 3, 1).reshape(-1, fused.shape[1])
+    base = img_only["fused"].permute(0, 2, 3, 1).reshape(-1, fused.shape[1])
+    e, moved = _rel(fused, want), _rel(base, want)
+    print(f"\n[full-size multi-modal] fused features rel err {e:.3e}; geometric inputs move them by {moved:.3e}")
+    assert moved > 5 * e and e < 1.5e-2
+    _assert_within(_metrics(got, ref), "full-size multi-modal (V=2), reference-style init", floor=_metrics(amp, ref))
