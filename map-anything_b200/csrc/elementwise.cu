@@ -218,28 +218,30 @@ __global__ void pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ in, __nv_
 // bilinear resize, align_corners=True, NHWC bf16.  The scale is defined by the VIRTUAL output size (Hv, Wv);
 // only the top-left (Ho, Wo) window is produced (refinenet4: 19 -> 38, cropped to 37).
 // ----------------------------------------------------------------------------------------------
+// One block per output row (image i, row yo): the vertical taps / weights are block constants, the horizontal ones
+// come from one multiply per pixel, and consecutive threads walk (xo, 8-channel chunk) so that loads and stores are
+// fully coalesced 16-byte accesses.
 __global__ void bilinear_ac_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int n, int Hin,
                                    int Win, int C, int Hv, int Wv, int Ho, int Wo) {
   const int c8 = C >> 3;
-  const int64_t total = (int64_t)n * Ho * Wo * c8;
+  const int i = blockIdx.x / Ho, yo = blockIdx.x - i * Ho;
   const float sy = Hv > 1 ? (float)(Hin - 1) / (float)(Hv - 1) : 0.f;
   const float sx = Wv > 1 ? (float)(Win - 1) / (float)(Wv - 1) : 0.f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cc = static_cast<int>(idx % c8);
-    int64_t t = idx / c8;
-    const int xo = static_cast<int>(t % Wo);
-    t /= Wo;
-    const int yo = static_cast<int>(t % Ho);
-    const int i = static_cast<int>(t / Ho);
-    const float fy = yo * sy, fx = xo * sx;
-    const int y0 = min((int)fy, Hin - 1), x0 = min((int)fx, Win - 1);
-    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
-    const float wy = fy - y0, wx = fx - x0;
-    const __nv_bfloat16* base = in + (size_t)i * Hin * Win * C;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * Win + x0) * C) + cc);
-    const uint4 b = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y0 * Win + x1) * C) + cc);
-    const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * Win + x0) * C) + cc);
-    const uint4 d = __ldg(reinterpret_cast<const uint4*>(base + ((size_t)y1 * Win + x1) * C) + cc);
+  const float fy = yo * sy;
+  const int y0 = min((int)fy, Hin - 1);
+  const int y1 = min(y0 + 1, Hin - 1);
+  const float wy = fy - y0;
+  const uint4* row0 = reinterpret_cast<const uint4*>(in + ((size_t)i * Hin + y0) * Win * C);
+  const uint4* row1 = reinterpret_cast<const uint4*>(in + ((size_t)i * Hin + y1) * Win * C);
+  uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)i * Ho + yo) * Wo * C);
+  const int total = Wo * c8;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int xo = idx / c8, cc = idx - xo * c8;
+    const float fx = xo * sx;
+    const int x0 = min((int)fx, Win - 1), x1 = min(x0 + 1, Win - 1);
+    const float wx = fx - x0;
+    const uint4 a = __ldg(row0 + x0 * c8 + cc), b = __ldg(row0 + x1 * c8 + cc);
+    const uint4 c = __ldg(row1 + x0 * c8 + cc), d = __ldg(row1 + x1 * c8 + cc);
     const uint32_t aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
     const uint32_t cw[4] = {c.x, c.y, c.z, c.w}, dd[4] = {d.x, d.y, d.z, d.w};
     uint32_t o[4];
@@ -251,7 +253,7 @@ __global__ void bilinear_ac_kernel(const __nv_bfloat16* __restrict__ in, __nv_bf
       const float b1 = bf16_hi(cw[j]) + wx * (bf16_hi(dd[j]) - bf16_hi(cw[j]));
       o[j] = pack_bf16x2(t0 + wy * (b0 - t0), t1 + wy * (b1 - t1));
     }
-    reinterpret_cast<uint4*>(out)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    orow[idx] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -516,8 +518,8 @@ extern "C" int ma_pixel_shuffle(const void* in, void* out, int n, int h, int w, 
 extern "C" int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win, int C, int Hv, int Wv, int Ho,
                                          int Wo, void* stream) {
   MA_REQUIRE(in && out && n > 0 && C % 8 == 0 && Ho <= Hv && Wo <= Wv && Hin > 0 && Win > 0, "ma_bilinear_align_corners: bad arguments");
-  const int64_t total = (int64_t)n * Ho * Wo * (C / 8);
-  bilinear_ac_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MA_REQUIRE((int64_t)n * Ho < (1ll << 31), "ma_bilinear_align_corners: too many output rows");
+  bilinear_ac_kernel<<<n * Ho, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), n, Hin, Win, C, Hv, Wv, Ho, Wo);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;

@@ -67,3 +67,21 @@ def test_quantile_mask_matches_torch_quantile(pct):
     want = conf > thr
     got = quantile_mask(conf.cuda(), pct / 100.0).cpu()
     assert torch.equal(got, want), (got != want).sum().item()
+
+
+@pytest.mark.parametrize("n,Hin,Win,C,Ho,Wo,virt", [(2, 19, 19, 256, 37, 37, (38, 38)), (1, 37, 37, 256, 74, 74, None),
+                                                    (1, 40, 56, 128, 70, 98, None), (2, 5, 7, 64, 5, 7, None)])
+def test_bilinear_align_corners_matches_torch(n, Hin, Win, C, Ho, Wo, virt):
+    """F.interpolate(mode="bilinear", align_corners=True) over NHWC bf16, incl. the refinenet4 case (19 -> 38 cropped to 37)."""
+    import torch.nn.functional as F
+
+    from mapanything_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(Hin * 100 + Wo)
+    x = torch.randn(n, Hin, Win, C, device="cuda", generator=g).bfloat16()
+    out = torch.full((n, Ho, Wo, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.bilinear_ac(x, out, virtual_hw=virt)
+    Hv, Wv = virt if virt else (Ho, Wo)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Hv, Wv), mode="bilinear", align_corners=True)
+    ref = ref[:, :, :Ho, :Wo].permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
