@@ -359,18 +359,31 @@ attention_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const _
 //   * a 4-deep K and V ring shared by both query tiles (half the L2 -> smem traffic per query row).
 // Same interface / masking / segment / carried-state semantics as the v1 kernel above.
 // ================================================================================================================
-constexpr int A2_THREADS = 11 * 32;  // warp 0 TMA, warp 1 / warp 10 MMA issuers of query tile A / B, warps 2..9 softmax
-constexpr int A2_KV_STAGES = 4;
-constexpr int A2_SMEM_BYTES = (2 + 2 * A2_KV_STAGES) * ATT_TILE_BYTES + 512;
-constexpr int A2_TMEM_COLS = 512;  // S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512)
+// NQT = query tiles per CTA.  2: one CTA per SM, the layout described above (long sequences: K/V shared by 256 query
+// rows).  1: one tile per CTA and TWO CTAs per SM (half the TMEM / smem / warps each): the same two free-running softmax
+// streams per SM, but a CTA's prologue (TMEM allocation, Q / first K,V loads, pipeline ramp) and epilogue overlap the other
+// CTA's steady state, and work is scheduled in 128-row units -- better for the 11-tile sequences of a single view.
+template <int NQT>
+struct A2Cfg {
+  static constexpr int THREADS = NQT == 2 ? 11 * 32 : 6 * 32;  // warp 0 TMA, warp 1 (/10) MMA issuer of tile A (/B), then softmax
+  static constexpr int KV_STAGES = NQT == 2 ? 4 : 3;
+  static constexpr int SMEM_BYTES = (NQT + 2 * KV_STAGES) * ATT_TILE_BYTES + 512;
+  static constexpr int TMEM_COLS = NQT * 256;  // S tiles [0, 128 NQT), O tiles [128 NQT, 192 NQT), P tiles [192 NQT, 256 NQT)
+  static constexpr int O_COL0 = NQT * 128, P_COL0 = NQT * 192;
+  static constexpr int BMQ = NQT * ATT_BM;     // query rows per CTA
+};
 constexpr float A2_RESCALE_LOG2 = 8.0f;
 
-__global__ void __launch_bounds__(A2_THREADS, 1)
+template <int NQT>
+__global__ void __launch_bounds__(A2Cfg<NQT>::THREADS, NQT == 2 ? 1 : 2)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = A2Cfg<NQT>;
+  constexpr int A2_KV_STAGES = Cfg::KV_STAGES;
+  constexpr int A2_TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                     // [2] tiles
-  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                  // [stages]
+  uint8_t* sQ = smem;                                     // [NQT] tiles
+  uint8_t* sK = sQ + NQT * ATT_TILE_BYTES;                // [stages]
   uint8_t* sV = sK + A2_KV_STAGES * ATT_TILE_BYTES;       // [stages]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A2_KV_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;
@@ -389,9 +402,9 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   // 1-D grid over (query block, head, sequence).  All FULL 256-row query blocks come first, the ragged last block of
   // every (head, sequence) -- cheaper, often a single 128-row tile -- is scheduled at the end where it fills the tail
   // wave instead of occupying an SM slot for a full block's duration in the middle (1370-token views: 5 full + 1 ragged).
-  const int n_full = p.q_len / (2 * ATT_BM);
+  const int n_full = p.q_len / (Cfg::BMQ);
   const int hs_count = p.num_heads * p.num_seqs;
-  const int n_slots = ((p.q_len + 2 * ATT_BM - 1) / (2 * ATT_BM)) * hs_count;
+  const int n_slots = ((p.q_len + Cfg::BMQ - 1) / (Cfg::BMQ)) * hs_count;
   // slots [0, split_from) run as one CTA each; every later slot -- the ones that would form the badly filled last wave
   // of SMs -- is cut into kv_split CTAs that each take a share of the key range and leave a partial softmax state
   int bid = blockIdx.x, part = 0, nparts = 1;
@@ -410,13 +423,13 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     qb = n_full;
     hs = bid - n_full * hs_count;
   }
-  const int q0 = qb * 2 * ATT_BM;
+  const int q0 = qb * Cfg::BMQ;
   const int head = hs % p.num_heads;
   const int seq = hs / p.num_heads;
   const int kv_tile0 = static_cast<int>((static_cast<int64_t>(part) * p.n_kv_tiles) / nparts);
   const int n_kv_tiles = static_cast<int>((static_cast<int64_t>(part + 1) * p.n_kv_tiles) / nparts) - kv_tile0;
   const bool write_state = (p.flags & MA_ATTN_STATE_OUT) != 0 || nparts > 1;
-  const int n_qt = (q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
+  const int n_qt = (NQT == 2 && q0 + ATT_BM < p.q_len) ? 2 : 1;  // query tile B is skipped when it lies past the sequence
   const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -458,9 +471,9 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     if (lane == 0) {
       const int q_row = static_cast<int>(seq * p.q_seq_stride) + q0;
       const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
-      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      mbar_arrive_expect_tx(q_full, NQT * ATT_TILE_BYTES);
       tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
-      tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row + ATT_BM);
+      if (NQT == 2) tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row + ATT_BM);
       KvCursor cur;
       cur.skip(p, kv_tile0);
       for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
@@ -484,8 +497,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(sQ + t * ATT_TILE_BYTES);
       const uint32_t tmem_s = tmem_base + t * ATT_BN;
-      const uint32_t tmem_o = tmem_base + 256 + t * ATT_D;
-      const uint32_t p_tmem = tmem_base + 384 + t * 64;  // 128 kv x bf16 = 64 columns, 8 columns per K = 16 step
+      const uint32_t tmem_o = tmem_base + Cfg::O_COL0 + t * ATT_D;
+      const uint32_t p_tmem = tmem_base + Cfg::P_COL0 + t * 64;  // 128 kv x bf16 = 64 columns, 8 columns per K = 16 step
       auto issue_qk = [&](int j) {
         const int st = j % A2_KV_STAGES;
         const uint32_t ph = (j / A2_KV_STAGES) & 1;
@@ -526,8 +539,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const int row = quarter * 32 + lane;
       const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t tmem_s = tmem_base + lane_base + t * ATT_BN;
-      const uint32_t tmem_o = tmem_base + lane_base + 256 + t * ATT_D;
-      const uint32_t tmem_p = tmem_base + lane_base + 384 + t * 64;
+      const uint32_t tmem_o = tmem_base + lane_base + Cfg::O_COL0 + t * ATT_D;
+      const uint32_t tmem_p = tmem_base + lane_base + Cfg::P_COL0 + t * 64;
       const int q_idx = q0 + t * ATT_BM + row;
       const bool q_ok = q_idx < p.q_len;
       const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
@@ -860,11 +873,24 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   } else {
     static bool configured2 = false;
     if (!configured2) {
-      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES));
+      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Cfg<2>::SMEM_BYTES));
+      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Cfg<1>::SMEM_BYTES));
       configured2 = true;
     }
-    dim3 grid(grid_ctas);
-    attention_fwd_v2_kernel<<<grid, A2_THREADS, A2_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    // one query tile per CTA, two CTAs per SM: measured faster than two tiles per CTA on every shape of the path (B200,
+    // same-box A/B: encoder 521-571 vs 446-462, frame 535-540 vs 482, 8-view global 765 vs 709 TFLOP/s); the two-tile
+    // form is kept for the kv-split mode and for A/B runs (MA_ATTN_NQT=2)
+    static const int nqt_env = [] {
+      const char* e = getenv("MA_ATTN_NQT");
+      return e ? atoi(e) : 0;
+    }();
+    const int nqt = p.kv_split > 1 ? 2 : (nqt_env == 1 || nqt_env == 2) ? nqt_env : 1;
+    if (nqt == 2) {
+      attention_fwd_v2_kernel<2><<<dim3(grid_ctas), A2Cfg<2>::THREADS, A2Cfg<2>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    } else {
+      const int ctas = ((q_len + ATT_BM - 1) / ATT_BM) * num_heads * num_seqs;
+      attention_fwd_v2_kernel<1><<<dim3(ctas), A2Cfg<1>::THREADS, A2Cfg<1>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    }
   }
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
