@@ -40,6 +40,11 @@ typedef enum ma_act { MA_ACT_NONE = 0, MA_ACT_GELU = 1, MA_ACT_RELU = 2 } ma_act
 const char* ma_last_error(void);
 int ma_abi_version(void);
 int ma_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Programmatic dependent launch of the chained GEMM / attention / LayerNorm kernels (the next kernel's prologue overlaps
+ * the previous kernel's last wave; results are identical).  enabled: 0 / 1, or -1 to query only.  Returns the previous
+ * setting.  Initial value: environment variable MA_PDL, else the build default.  The reference has no counterpart (it
+ * relies on the PyTorch stream order, model.py:1477-1909). */
+int ma_set_pdl(int enabled);
 
 /* ---- GEMM: Y = epilogue(X . W^T) ------------------------------------------------------------
  * Replaces every nn.Linear / 1x1 conv / im2col'ed conv on the path (cuBLASLt / cuDNN calls in the

@@ -466,6 +466,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // prologue above overlaps the previous kernel's tail; no global memory access before this point
 
   if (warp == 0) {
     if (lane == 0) {
@@ -886,10 +887,12 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     }();
     const int nqt = p.kv_split > 1 ? 2 : (nqt_env == 1 || nqt_env == 2) ? nqt_env : 1;
     if (nqt == 2) {
-      attention_fwd_v2_kernel<2><<<dim3(grid_ctas), A2Cfg<2>::THREADS, A2Cfg<2>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+      MA_CHECK_CUDA(launch_kernel(attention_fwd_v2_kernel<2>, dim3(grid_ctas), dim3(A2Cfg<2>::THREADS), A2Cfg<2>::SMEM_BYTES,
+                                  static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));
     } else {
       const int ctas = ((q_len + ATT_BM - 1) / ATT_BM) * num_heads * num_seqs;
-      attention_fwd_v2_kernel<1><<<dim3(ctas), A2Cfg<1>::THREADS, A2Cfg<1>::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+      MA_CHECK_CUDA(launch_kernel(attention_fwd_v2_kernel<1>, dim3(ctas), dim3(A2Cfg<1>::THREADS), A2Cfg<1>::SMEM_BYTES,
+                                  static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));
     }
   }
   MA_CHECK_CUDA(cudaGetLastError());

@@ -116,6 +116,7 @@ __global__ void layernorm_kernel(const LnParams p) {
 // (two-pass, like nn.LayerNorm), the bf16 / fp32 result is written once: 4C B in + 2C (or 4C) B out per row.
 template <int NV4, typename TOut>
 __global__ void layernorm_f32_reg_kernel(const LnParams p) {
+  pdl_sync();  // may be launched programmatically behind the GEMM that produced p.in
   const int warps_per_block = blockDim.x >> 5;
   const int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (r >= p.rows) return;
@@ -475,10 +476,10 @@ extern "C" int ma_layernorm(const void* in, int in_dtype, int64_t ld_in, void* o
   const int grid = (rows + wpb - 1) / wpb;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool vec_ok = in_dtype == MA_F32 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-  if (vec_ok && C == 1024 && out_dtype == MA_BF16) layernorm_f32_reg_kernel<8, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
-  else if (vec_ok && C == 768 && out_dtype == MA_BF16) layernorm_f32_reg_kernel<6, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
-  else if (vec_ok && C == 1024 && out_dtype == MA_F32) layernorm_f32_reg_kernel<8, float><<<grid, wpb * 32, 0, s>>>(p);
-  else if (vec_ok && C == 768 && out_dtype == MA_F32) layernorm_f32_reg_kernel<6, float><<<grid, wpb * 32, 0, s>>>(p);
+  if (vec_ok && C == 1024 && out_dtype == MA_BF16) MA_CHECK_CUDA(launch_kernel(layernorm_f32_reg_kernel<8, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, pdl_enabled(), p));
+  else if (vec_ok && C == 768 && out_dtype == MA_BF16) MA_CHECK_CUDA(launch_kernel(layernorm_f32_reg_kernel<6, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, s, pdl_enabled(), p));
+  else if (vec_ok && C == 1024 && out_dtype == MA_F32) MA_CHECK_CUDA(launch_kernel(layernorm_f32_reg_kernel<8, float>, dim3(grid), dim3(wpb * 32), 0, s, pdl_enabled(), p));
+  else if (vec_ok && C == 768 && out_dtype == MA_F32) MA_CHECK_CUDA(launch_kernel(layernorm_f32_reg_kernel<6, float>, dim3(grid), dim3(wpb * 32), 0, s, pdl_enabled(), p));
   else if (in_dtype == MA_F32 && out_dtype == MA_BF16) layernorm_kernel<float, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);
   else if (in_dtype == MA_F32 && out_dtype == MA_F32) layernorm_kernel<float, float><<<grid, wpb * 32, 0, s>>>(p);
   else if (in_dtype == MA_BF16 && out_dtype == MA_BF16) layernorm_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(p);

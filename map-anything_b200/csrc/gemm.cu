@@ -74,6 +74,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // prologue above overlaps the previous kernel's tail; no global memory access before this point
 
   const int tiles_per_img = cg.tiles_x * cg.tiles_y;
   const int tiles_m = cg.mode ? (M / (cg.H * cg.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;
@@ -211,8 +212,8 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUten
   const int tiles_m = cg.mode ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = tiles_m * ((N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_bf16_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, tout, ep, M, N, K, cg, epi_mode);
-  MA_CHECK_CUDA(cudaGetLastError());
+  MA_CHECK_CUDA(launch_kernel(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, pdl_enabled(), tx, tw,
+                              tout, ep, M, N, K, cg, epi_mode));
   return MA_OK;
 }
 

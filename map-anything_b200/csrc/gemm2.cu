@@ -77,6 +77,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   cluster_sync_all();  // barriers of both CTAs initialised before any remote signal; TMEM allocated in both
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // prologue above overlaps the previous kernel's tail; no global memory access before this point
 
   const int tiles_per_img = cg.tiles_x * cg.tiles_y;
   const int rows_tiles = cg.mode ? (M / (cg.H * cg.W)) * tiles_per_img : (M + GEMM_BM - 1) / GEMM_BM;  // 128-row tiles
@@ -216,8 +217,8 @@ static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
   const int tiles = ((rows_tiles + 1) / 2) * ((N + BN - 1) / BN);
   const int max_clusters = device_sm_count() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  gemm_bf16_2cta_kernel<BN><<<2 * clusters, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tx, tw, tout, ep, M, N, K, cg, epi_mode);
-  MA_CHECK_CUDA(cudaGetLastError());
+  MA_CHECK_CUDA(launch_kernel(gemm_bf16_2cta_kernel<BN>, dim3(2 * clusters), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, pdl_enabled(), tx,
+                              tw, tout, ep, M, N, K, cg, epi_mode));
   return MA_OK;
 }
 

@@ -3,9 +3,15 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
+
+// Default of MA_PDL (programmatic dependent launch of the chained kernels); see DESIGN.md section 5 for the A/B numbers.
+#ifndef MA_PDL_DEFAULT
+#define MA_PDL_DEFAULT 0
+#endif
 
 namespace ma {
 
@@ -77,6 +83,17 @@ int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uin
   return MA_OK;
 }
 
+static int g_pdl_mode = -1;
+
+bool pdl_enabled() {
+  int& mode = g_pdl_mode;
+  if (mode < 0) {
+    const char* e = getenv("MA_PDL");
+    mode = e ? (e[0] != '0') : MA_PDL_DEFAULT;
+  }
+  return mode != 0;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -92,6 +109,12 @@ int device_sm_count() {
 extern "C" const char* ma_last_error(void) { return ma::g_last_error; }
 
 extern "C" int ma_abi_version(void) { return MA_ABI_VERSION; }
+
+extern "C" int ma_set_pdl(int enabled) {
+  const int before = ma::pdl_enabled() ? 1 : 0;
+  if (enabled >= 0) ma::g_pdl_mode = enabled ? 1 : 0;
+  return before;
+}
 
 extern "C" int ma_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

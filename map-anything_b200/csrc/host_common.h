@@ -42,4 +42,27 @@ int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uin
 
 int device_sm_count();
 
+// Programmatic dependent launch of the chained hot-path kernels (GEMM, attention, LayerNorm): MA_PDL=0/1, see ptx.cuh.
+bool pdl_enabled();
+
+// cudaLaunchKernelEx wrapper; with pdl = true the kernel may start before the previous kernel of the stream has
+// completed, and MUST execute pdl_wait() before its first global memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (pdl) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace ma

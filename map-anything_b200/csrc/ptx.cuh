@@ -19,6 +19,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ----------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A kernel launched with the programmatic-stream-serialization attribute
+// (host_common.h: launch_kernel) may START while the previous kernel of the stream is still draining: its prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) then overlaps the predecessor's last wave.  pdl_wait() blocks
+// until the predecessor has completed and its memory operations are visible; no global memory may be touched before it.
+// pdl_launch_dependents() lets the NEXT kernel of the stream be scheduled as soon as SM resources free up (it will
+// block in its own pdl_wait()).  Both are no-ops for a kernel launched without the attribute.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -54,6 +54,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def set_pdl(enabled: Optional[bool]) -> bool:
+    """Programmatic dependent launch of the chained GEMM / attention / LayerNorm kernels (include/mapanything_b200.h:
+    ma_set_pdl).  None queries.  Returns the previous setting."""
+    return bool(_lib.load().ma_set_pdl(-1 if enabled is None else int(bool(enabled))))
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return MA_BF16
