@@ -253,6 +253,33 @@ int ma_fuse_add(float* feat, int V, int N, int C, const float* dense_a, const in
                 const int* b_slot, const float* g0, const float* g1, const float* g2, const float* g3, const float* gw,
                 void* stream);
 
+/* ---- input side: load_images() (reference mapanything/utils/image.py:134-332) -------------------------------------
+ * The reference resizes every decoded RGB image with PIL.Image.resize (LANCZOS when shrinking, BICUBIC when enlarging:
+ * cropping.py:188-275), centre-crops it to the target resolution (cropping.py:385-467) and applies torchvision
+ * ToTensor + Normalize (image.py:291-296, :312).  PIL's 8-bit resize is integer arithmetic (22-bit fixed-point
+ * coefficients, byte-rounded horizontal pass feeding the vertical pass); these entry points reproduce it BIT-EXACTLY. */
+#define MA_FILTER_LANCZOS 1 /* = PIL.Image.Resampling.LANCZOS */
+#define MA_FILTER_BICUBIC 3 /* = PIL.Image.Resampling.BICUBIC */
+
+/* HOST function (no CUDA): Pillow's resampling windows for one axis, in_size -> out_size.  bounds: int32 [out_size][2] =
+ * (first source index, tap count); coeffs: int32 [ksize][out_size] (tap-major), 22-bit fixed point.  *ksize_out is always
+ * written; pass bounds = coeffs = NULL to query it.  in_size == out_size gives identity taps (PIL skips that pass). */
+int ma_resample_coeffs(int in_size, int out_size, int filter, int* ksize_out, int32_t* bounds, int32_t* coeffs);
+
+/* Horizontal pass.  src: device u8 RGB, interleaved, row stride in bytes; source rows [y0, y0+rows), source columns
+ * [sx0, sx1) are read (sx0/sx1 = the window span of output columns [x0, x0+cols)); bounds / coeffs: device copies of the
+ * tables for the horizontal axis (out_size columns).  tmp: device u8 [rows][cols][3]. */
+int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int y0, int rows, int sx0, int sx1,
+                        const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols, uint8_t* tmp,
+                        void* stream);
+
+/* Vertical pass + crop + normalise.  tmp: [rows][cols][3] u8 whose row 0 is source row y0; output rows
+ * [top, top+th) of the resampled image (out_size rows).  out_chw: fp32 (3, th, cols) = ((u/255) - mean) / std in
+ * torchvision's rounding order (mean / std: 3 HOST floats), may be NULL; out_u8: u8 [th][cols][3], may be NULL. */
+int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int cols, int y0, const int32_t* bounds, const int32_t* coeffs,
+                             int out_size, int top, int th, const float* mean_host, const float* std_host, float* out_chw,
+                             uint8_t* out_u8, void* stream);
+
 /* ---- infer() post-processing (reference mapanything/utils/inference.py:294-480, host numpy there) ---- */
 
 /* img_no_norm: clip(img * std + mean, 0, 1), (n,3,H,W) -> (n,H,W,3) fp32 (image.py:93-131). mean/std: 3 HOST floats. */

@@ -267,6 +267,67 @@ def golden_inference():
     np.savez_compressed(OUT / "inference.npz", **out)
 
 
+IMAGE_CASES = {
+    # name: (source sizes (W, H), load_images kwargs)
+    "fixed": ([(200, 150), (180, 135), (240, 180)], dict(resize_mode="fixed_size", size=(140, 98))),
+    "square": ([(90, 160), (100, 150)], dict(resize_mode="square", size=112)),
+    "longest": ([(64, 48), (80, 52)], dict(resize_mode="longest_side", size=154)),
+    "mapping": ([(320, 240), (300, 235)], dict(resize_mode="fixed_mapping")),
+}
+
+
+def synth_image(w: int, h: int, seed: int) -> np.ndarray:
+    """Smooth colour gradients + blobs + noise, (h, w, 3) uint8 -- stands in for a photograph."""
+    rng = np.random.default_rng(seed)
+    ys, xs = np.meshgrid(np.linspace(0, 1, h), np.linspace(0, 1, w), indexing="ij")
+    img = np.stack([xs, ys, 0.5 + 0.5 * np.sin(6 * xs + 4 * ys)], -1) * 200
+    for _ in range(4):
+        cx, cy, r = rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0.05, 0.3)
+        img += (((xs - cx) ** 2 + (ys - cy) ** 2) < r * r)[..., None] * rng.uniform(-80, 80, 3)
+    img += rng.normal(0, 12, img.shape)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def golden_image():
+    """load_images (mapanything/utils/image.py:134-332) on synthetic PNG files written to a temporary folder."""
+    import tempfile
+
+    import PIL.Image
+    from mapanything.utils import image as RIM
+
+    from oracle import image as OI
+
+    out = {}
+    for ci, (name, (sizes, kw)) in enumerate(IMAGE_CASES.items()):
+        with tempfile.TemporaryDirectory() as d:
+            for i, (w, h) in enumerate(sizes):
+                src = synth_image(w, h, 100 * ci + i)
+                PIL.Image.fromarray(src).save(f"{d}/img_{i:02d}.png")
+                out[f"{name}_src{i}"] = src
+            (Path(d) / "notes.txt").write_text("not an image")  # skipped by extension
+            ref = RIM.load_images(d, **kw)
+            mine = OI.load_images(d, **kw)
+        assert len(ref) == len(mine) == len(sizes)
+        for i, (rv, mv) in enumerate(zip(ref, mine)):
+            assert set(rv.keys()) == set(mv.keys())
+            assert rv["img"].dtype == torch.float32 and rv["img"].shape == mv["img"].shape, (rv["img"].shape, mv["img"].shape)
+            assert torch.equal(rv["img"], mv["img"]), f"load_images[{name}] view {i}: oracle differs from the reference"
+            assert (rv["true_shape"] == mv["true_shape"]).all() and rv["idx"] == mv["idx"] and rv["instance"] == mv["instance"]
+            assert rv["data_norm_type"] == mv["data_norm_type"]
+            img = rv["img"].numpy()
+            if name != "fixed":  # keep the fixture small: a strided sample and exact per-channel sums
+                st = 7 if name == "mapping" else 3
+                out[f"{name}_img{i}_sample"] = img[:, :, ::st, ::st].copy()
+                out[f"{name}_img{i}_stride"] = np.array(st)
+                out[f"{name}_img{i}_sum"] = img.astype(np.float64).sum(axis=(0, 2, 3))
+                out[f"{name}_img{i}_shape"] = np.array(img.shape)
+            else:
+                out[f"{name}_img{i}"] = img
+            out[f"{name}_true_shape{i}"] = rv["true_shape"]
+        print(f"  oracle vs reference  load_images[{name:<8s}] {tuple(ref[0]['img'].shape)}            bit-exact")
+    np.savez_compressed(OUT / "image.npz", **out)
+
+
 def main():
     assert REF.exists(), "this script needs /root/reference (build container only)"
     _install_reference_stubs()
@@ -276,6 +337,8 @@ def main():
     golden_geometry()
     print("inference pre/post:")
     golden_inference()
+    print("load_images:")
+    golden_image()
     print("DINOv2 ViT:")
     golden_vit()
     for f in sorted(OUT.glob("*.npz")):

@@ -1,0 +1,128 @@
+"""Input side (load_images): the numpy restatement of the reference path (oracle/image.py) against
+  * tests/golden/image.npz -- outputs of the reference's own load_images (oracle/make_golden.py), and
+  * the installed Pillow (the third-party library whose 8-bit resampling the reference calls), bit for bit;
+and the HOST entry point ma_resample_coeffs of the C-ABI library against the same coefficient tables.  No GPU needed."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import image as OI
+
+GOLD = Path(__file__).parent / "golden" / "image.npz"
+CASES = {
+    "fixed": dict(resize_mode="fixed_size", size=(140, 98)),
+    "square": dict(resize_mode="square", size=112),
+    "longest": dict(resize_mode="longest_side", size=154),
+    "mapping": dict(resize_mode="fixed_mapping"),
+}
+
+
+def write_case(gold, name, folder):
+    import PIL.Image
+
+    i = 0
+    while f"{name}_src{i}" in gold:
+        PIL.Image.fromarray(gold[f"{name}_src{i}"]).save(folder / f"img_{i:02d}.png")
+        i += 1
+    (folder / "notes.txt").write_text("not an image")
+    return i
+
+
+def check_view(gold, name, i, view):
+    img = view["img"].cpu().numpy()
+    if f"{name}_img{i}" in gold:
+        assert np.array_equal(img, gold[f"{name}_img{i}"])
+    else:
+        st = int(gold[f"{name}_img{i}_stride"])
+        assert tuple(img.shape) == tuple(gold[f"{name}_img{i}_shape"])
+        assert np.array_equal(img[:, :, ::st, ::st], gold[f"{name}_img{i}_sample"])
+        assert np.array_equal(img.astype(np.float64).sum(axis=(0, 2, 3)), gold[f"{name}_img{i}_sum"])
+    assert (view["true_shape"] == gold[f"{name}_true_shape{i}"]).all()
+    assert view["idx"] == i and view["instance"] == str(i) and view["data_norm_type"] == ["dinov2"]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_load_images_matches_reference_golden(name, tmp_path):
+    gold = np.load(GOLD)
+    n = write_case(gold, name, tmp_path)
+    views = OI.load_images(str(tmp_path), **CASES[name])
+    assert len(views) == n
+    for i, v in enumerate(views):
+        assert v["img"].dtype == torch.float32
+        check_view(gold, name, i, v)
+
+
+@pytest.mark.parametrize("W,H,ow,oh,filt", [
+    (640, 480, 518, 389, OI.LANCZOS), (97, 131, 140, 189, OI.BICUBIC), (1000, 333, 518, 173, OI.LANCZOS),
+    (300, 300, 518, 518, OI.BICUBIC), (640, 480, 640, 300, OI.LANCZOS), (37, 53, 37, 80, OI.BICUBIC), (5, 4, 14, 14, OI.BICUBIC),
+])
+def test_oracle_resize_matches_pillow(W, H, ow, oh, filt):
+    import PIL.Image
+
+    img = np.random.default_rng(W + H).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    ref = np.asarray(PIL.Image.fromarray(img).resize((ow, oh), resample=filt))
+    assert np.array_equal(OI.pil_resize_u8(img, (ow, oh), filt), ref)
+
+
+def test_resize_plan_and_target_sizes():
+    assert OI.find_closest_aspect_ratio(4 / 3, 518) == (518, 392)
+    assert OI.find_closest_aspect_ratio(0.5, 518) == (252, 518)
+    assert OI.find_closest_aspect_ratio(16 / 9, 512) == (512, 288)
+    assert OI.target_size_for([1.5, 1.3], "longest_side", 518, 14, 518) == (518, 364)
+    assert OI.target_size_for([0.75], "longest_side", 518, 14, 518) == (392, 518)
+    rw, rh, filt, left, top = OI.resize_plan(1920, 1080, (518, 294))
+    assert (rw, rh, filt) == (522, 294, OI.LANCZOS) and (left, top) == (2, 0)
+    rw, rh, filt, left, top = OI.resize_plan(100, 80, (140, 140))
+    assert filt == OI.BICUBIC and rh == 140 and rw == 175 and (left, top) == (17, 0)
+
+
+def _lib():
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "map-anything_b200"))
+    from mapanything_b200 import _lib
+
+    return _lib.load()
+
+
+@pytest.mark.parametrize("i,o,filt", [(1920, 921, 1), (480, 389, 1), (97, 140, 3), (300, 518, 3), (64, 64, 1), (7, 3, 1)])
+def test_cabi_resample_coeffs_host(i, o, filt):
+    """ma_resample_coeffs is a host function of the shared library: same windows and 22-bit coefficients as the oracle."""
+    lib = _lib()
+    ks = C.c_int(0)
+    assert lib.ma_resample_coeffs(i, o, filt, C.byref(ks), None, None) == 0
+    bounds = np.zeros((o, 2), np.int32)
+    coeffs = np.zeros((ks.value, o), np.int32)
+    assert lib.ma_resample_coeffs(i, o, filt, C.byref(ks), bounds.ctypes.data, coeffs.ctypes.data) == 0
+    if i == o:
+        assert ks.value == 1 and (bounds[:, 0] == np.arange(o)).all() and (coeffs == 1 << 22).all()
+        return
+    b2, k2 = OI.resample_coeffs(i, o, filt)
+    assert ks.value == k2.shape[1]
+    assert np.array_equal(bounds, b2) and np.array_equal(coeffs.T, k2)
+    assert lib.ma_resample_coeffs(0, o, filt, C.byref(ks), None, None) != 0  # bad size -> status + message
+    assert b"bad sizes" in lib.ma_last_error()
+
+
+def test_load_images_validation_errors_need_no_gpu():
+    """Argument validation of the drop-in load_images happens before any device work, with the reference's messages."""
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "map-anything_b200"))
+    from mapanything_b200.image import load_images
+
+    with pytest.raises(ValueError, match="Resize_mode must be one of"):
+        load_images([], resize_mode="bogus")
+    with pytest.raises(ValueError, match="Size parameter is required"):
+        load_images([], resize_mode="square")
+    with pytest.raises(ValueError, match="Size must be an int"):
+        load_images([], resize_mode="longest_side", size=(1, 2))
+    with pytest.raises(ValueError, match=r"tuple/list of \(width, height\)"):
+        load_images([], resize_mode="fixed_size", size=5)
+    with pytest.raises(ValueError, match="Bad folder_or_list"):
+        load_images(42)
+    with pytest.raises(ValueError, match="Unknown image normalization type"):
+        load_images([], norm_type="nope")
