@@ -280,6 +280,15 @@ int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int cols, int y0, const int32_t
                              int out_size, int top, int th, const float* mean_host, const float* std_host, float* out_chw,
                              uint8_t* out_u8, void* stream);
 
+/* preprocess_inputs() (image.py:335-675) resizes depth maps with cv2.resize(INTER_NEAREST) and slices the crop
+ * (cropping.py:248-255, :339): out[y][x] = src[y_idx[y]][x_idx[x]], th x tw; y_idx / x_idx: device int32 source offsets
+ * of the cropped window (OpenCV resizeNN: min(floor(i * (1 / (dst / src))), src - 1), computed on the host). */
+int ma_gather_rows_cols_f32(const float* src, int64_t src_row_stride, const int32_t* y_idx, const int32_t* x_idx, int th,
+                            int tw, float* out, void* stream);
+
+/* Float image -> bytes as image.py:503-506 does with torch: (in * scale).clamp(0, 255).byte(); n elements. */
+int ma_f32_to_u8(const float* in, int64_t n, float scale, uint8_t* out, void* stream);
+
 /* ---- infer() post-processing (reference mapanything/utils/inference.py:294-480, host numpy there) ---- */
 
 /* img_no_norm: clip(img * std + mean, 0, 1), (n,3,H,W) -> (n,H,W,3) fp32 (image.py:93-131). mean/std: 3 HOST floats. */

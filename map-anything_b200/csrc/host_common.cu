@@ -10,7 +10,7 @@
 
 // Default of MA_PDL (programmatic dependent launch of the chained kernels); see DESIGN.md section 5 for the A/B numbers.
 #ifndef MA_PDL_DEFAULT
-#define MA_PDL_DEFAULT 0
+#define MA_PDL_DEFAULT 1
 #endif
 
 namespace ma {

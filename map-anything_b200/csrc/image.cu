@@ -115,9 +115,43 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int cols
   }
 }
 
+// out[y][x] = src[y_idx[y]][x_idx[x]]: cv2.resize(INTER_NEAREST) + crop of a float map as one gather (index arrays are
+// OpenCV's resizeNN offsets of the cropped window, computed on the host in double precision).
+__global__ void gather_rows_cols_f32_kernel(const float* __restrict__ src, int64_t row_stride, const int32_t* __restrict__ y_idx,
+                                            const int32_t* __restrict__ x_idx, int tw, float* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= tw) return;
+  const int y = blockIdx.y;
+  out[static_cast<int64_t>(y) * tw + x] = __ldg(src + static_cast<int64_t>(y_idx[y]) * row_stride + x_idx[x]);
+}
+
+// torch: (img * scale).clamp(0, 255).byte()  (image.py:503-506); scale = 255 for images in [0, 1], else 1
+__global__ void f32_to_u8_kernel(const float* __restrict__ in, int64_t n, float scale, uint8_t* __restrict__ out) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fminf(fmaxf(__fmul_rn(in[i], scale), 0.f), 255.f);
+  out[i] = static_cast<uint8_t>(static_cast<int>(v));  // truncation, like the C cast behind .byte()
+}
+
 }  // namespace ma
 
 using namespace ma;
+
+extern "C" int ma_gather_rows_cols_f32(const float* src, int64_t src_row_stride, const int32_t* y_idx, const int32_t* x_idx,
+                                       int th, int tw, float* out, void* stream) {
+  MA_REQUIRE(src && y_idx && x_idx && out && th > 0 && tw > 0, "ma_gather_rows_cols_f32: bad arguments (th=%d tw=%d)", th, tw);
+  dim3 grid((tw + 127) / 128, th);
+  gather_rows_cols_f32_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(src, src_row_stride, y_idx, x_idx, tw, out);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_f32_to_u8(const float* in, int64_t n, float scale, uint8_t* out, void* stream) {
+  MA_REQUIRE(in && out && n > 0, "ma_f32_to_u8: bad arguments");
+  f32_to_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, n, scale, out);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
 
 extern "C" int ma_resample_coeffs(int in_size, int out_size, int filter, int* ksize_out, int32_t* bounds, int32_t* coeffs) {
   MA_REQUIRE(in_size > 0 && out_size > 0 && ksize_out, "ma_resample_coeffs: bad sizes (%d -> %d)", in_size, out_size);

@@ -95,15 +95,20 @@ def resize_plan(W1: int, H1: int, target: Tuple[int, int]) -> Tuple[int, int, in
 
 
 def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_type: Optional[str] = "dinov2",
-                          return_u8: bool = False):
+                          return_u8: bool = False, crop_offset: Optional[Tuple[int, int]] = None):
     """img_u8: CUDA uint8 (H, W, 3), rows contiguous -> fp32 (1, 3, th, tw) normalised image (and / or the uint8
-    (th, tw, 3) image when return_u8), bit-exact with PIL resize + crop + torchvision ToTensor/Normalize."""
+    (th, tw, 3) image when return_u8), bit-exact with PIL resize + crop + torchvision ToTensor/Normalize.
+    crop_offset = (left, top) in the resized image; default: the centred crop of the image-only path."""
     if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3 or img_u8.stride(2) != 1 \
             or img_u8.stride(1) != 3:
         raise ValueError("resize_crop_normalize expects a CUDA uint8 (H, W, 3) tensor with packed RGB pixels")
     H1, W1, _ = img_u8.shape
     tw, th = int(target[0]), int(target[1])
     rw, rh, filt, left, top = resize_plan(W1, H1, (tw, th))
+    if crop_offset is not None:
+        left, top = int(crop_offset[0]), int(crop_offset[1])
+    if left < 0 or top < 0 or left + tw > rw or top + th > rh:
+        raise ValueError(f"crop box ({left}, {top}, {left + tw}, {top + th}) leaves the resized image {rw}x{rh}")
     dev = img_u8.device
     th_, tv_ = _tables(W1, rw, filt, dev), _tables(H1, rh, filt, dev)
     y0 = int(tv_.bounds[top, 0])
@@ -273,3 +278,236 @@ def load_images(
     if verbose:
         print(f" (Found {len(imgs)} images)")
     return imgs
+
+
+# ------------------------------------------------------------------------------------------------ preprocess_inputs
+def _nearest_indices(src: int, dst: int) -> np.ndarray:
+    """Source offsets of cv2.resize(INTER_NEAREST) for one axis (OpenCV resizeNN), the resize the reference applies to
+    depth maps (cropping.py:248-255)."""
+    inv = 1.0 / (float(dst) / float(src))
+    return np.minimum(np.floor(np.arange(dst) * inv).astype(np.int64), src - 1).astype(np.int32)
+
+
+def _camera_matrix_of_crop(K: np.ndarray, input_resolution, output_resolution, scaling=1, offset_factor=0.5) -> np.ndarray:
+    """Intrinsics after scaling by `scaling` and removing `offset_factor` of the margins (cropping.py:278-318); the same
+    numpy operations in the same order and dtype as the reference, because the crop box is rounded from its result."""
+    margins = np.asarray(input_resolution) * scaling - output_resolution
+    assert np.all(margins >= 0.0)
+    offset = offset_factor * margins
+    out = K.copy()
+    out[0, 2] += 0.5   # OpenCV -> COLMAP pixel-centre convention
+    out[1, 2] += 0.5
+    out[:2, :] *= scaling
+    out[:2, 2] -= offset
+    out[0, 2] -= 0.5   # and back
+    out[1, 2] -= 0.5
+    return out
+
+
+def _image_to_device_u8(img, view_idx: int, dev: torch.device, up: _Uploader) -> torch.Tensor:
+    """The image forms preprocess_inputs accepts (image.py:493-521) as a CUDA uint8 (H, W, 3) tensor.  Host inputs are
+    converted with the reference's own expressions; CUDA float tensors with ma_f32_to_u8."""
+    import PIL.Image
+
+    if isinstance(img, torch.Tensor):
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError(f"Expected tensor shape (H, W, 3) for img in view {view_idx}, got {img.shape}")
+        if not img.is_cuda:
+            if img.max() <= 1.0:
+                return up.upload((img * 255).clamp(0, 255).byte().numpy())
+            return up.upload(img.clamp(0, 255).byte().numpy())
+        img = img.to(dev)
+        if img.dtype == torch.uint8:
+            return img.contiguous()
+        x = img.contiguous().float()
+        out = torch.empty(x.shape, device=dev, dtype=torch.uint8)
+        scale = 255.0 if float(x.max()) <= 1.0 else 1.0
+        check(_lib.load().ma_f32_to_u8(x.data_ptr(), x.numel(), scale, out.data_ptr(), torch.cuda.current_stream().cuda_stream),
+              "ma_f32_to_u8")
+        ops._count()
+        return out
+    if isinstance(img, np.ndarray):
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError(f"Expected array shape (H, W, 3) for img in view {view_idx}, got {img.shape}")
+        if img.dtype != np.uint8:
+            img = (img * 255).clip(0, 255).astype(np.uint8)
+        return up.upload(img)
+    if isinstance(img, PIL.Image.Image):
+        return up.upload(np.asarray(img))
+    raise ValueError(f"Unsupported image type in view {view_idx}: {type(img)}")
+
+
+def _image_hw(img, view_idx: int) -> Tuple[int, int]:
+    import PIL.Image
+
+    if isinstance(img, torch.Tensor):
+        if img.ndim == 3 and img.shape[2] == 3:
+            return img.shape[0], img.shape[1]
+        raise ValueError(f"Expected tensor shape (H, W, 3) for img in view {view_idx}, got {img.shape}")
+    if isinstance(img, PIL.Image.Image):
+        return img.size[1], img.size[0]
+    if isinstance(img, np.ndarray):
+        if img.ndim == 3 and img.shape[2] == 3:
+            return img.shape[0], img.shape[1]
+        raise ValueError(f"Expected array shape (H, W, 3) for img in view {view_idx}, got {img.shape}")
+    raise ValueError(f"Unsupported image type in view {view_idx}: {type(img)}")
+
+
+def _to_host_array(data, expected_shape, name: str, view_idx: int) -> np.ndarray:
+    if isinstance(data, torch.Tensor):
+        data = data.cpu().numpy()
+    if not isinstance(data, np.ndarray):
+        raise ValueError(f"Expected tensor or array for {name} in view {view_idx}, got {type(data)}")
+    if expected_shape is not None and data.shape != expected_shape:
+        raise ValueError(f"Expected shape {expected_shape} for {name} in view {view_idx}, got {data.shape}")
+    return data
+
+
+def _resize_crop_depth(depth, H1: int, W1: int, rw: int, rh: int, left: int, top: int, tw: int, th: int, dev) -> torch.Tensor:
+    """depth (H1, W1) float -> CUDA fp32 (1, th, tw): nearest resize to (rh, rw) and crop, one gather kernel."""
+    if isinstance(depth, torch.Tensor):
+        d = depth.to(dev, torch.float32).contiguous()
+    else:
+        d = torch.from_numpy(np.ascontiguousarray(depth, dtype=np.float32)).to(dev)
+    yi = torch.from_numpy(_nearest_indices(H1, rh)[top:top + th].copy()).to(dev)
+    xi = torch.from_numpy(_nearest_indices(W1, rw)[left:left + tw].copy()).to(dev)
+    out = torch.empty(1, th, tw, device=dev, dtype=torch.float32)
+    check(_lib.load().ma_gather_rows_cols_f32(d.data_ptr(), d.stride(0), yi.data_ptr(), xi.data_ptr(), th, tw, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "ma_gather_rows_cols_f32")
+    ops._count()
+    return out
+
+
+def preprocess_inputs(
+    input_views,
+    resize_mode="fixed_mapping",
+    size=None,
+    norm_type="dinov2",
+    patch_size=14,
+    resolution_set=518,
+    verbose=False,
+    device=None,
+):
+    """Same contract as the reference `preprocess_inputs` (image.py:335-675): brings the images AND the optional
+    multi-modal inputs of every view (intrinsics or ray directions, depth_z, camera poses) to one target resolution.
+    Images are resampled like load_images; depth with nearest neighbour; intrinsics follow the scale and a
+    principal-point preserving crop (cropping.py:278-318, :362-381).  `img` and `depth_z` are returned on `device`."""
+    valid_resize_modes = ["fixed_mapping", "longest_side", "square", "fixed_size"]
+    if resize_mode not in valid_resize_modes:
+        raise ValueError(f"Resize_mode must be one of {valid_resize_modes}, got '{resize_mode}'")
+    if resize_mode in ["longest_side", "square", "fixed_size"] and size is None:
+        raise ValueError(f"Size parameter is required for resize_mode='{resize_mode}'")
+    if resize_mode in ["longest_side", "square"]:
+        if not isinstance(size, int):
+            raise ValueError(f"Size must be an int for resize_mode='{resize_mode}', got {type(size)}")
+    elif resize_mode == "fixed_size":
+        if not isinstance(size, (tuple, list)) or len(size) != 2:
+            raise ValueError(f"Size must be a tuple/list of (width, height) for resize_mode='fixed_size', got {size}")
+        if not all(isinstance(x, int) for x in size):
+            raise ValueError(f"Size values must be integers for resize_mode='fixed_size', got {size}")
+    if not input_views:
+        raise ValueError("input_views cannot be empty")
+
+    aspect_ratios = []
+    for view_idx, view in enumerate(input_views):
+        if "img" not in view:
+            if verbose:
+                print(f"Warning: View {view_idx} has no 'img' key, skipping for aspect ratio calculation")
+            continue
+        H, W = _image_hw(view["img"], view_idx)
+        aspect_ratios.append(W / H)
+    if not aspect_ratios:
+        raise ValueError("No valid images found in input_views")
+    target_size = _target_size(aspect_ratios, resize_mode, size, patch_size, resolution_set, verbose)
+    tw, th = target_size
+    if verbose:
+        print(f"Using target resolution {target_size[0]}x{target_size[1]} (W x H) for all views")
+    if norm_type not in IMAGE_NORMALIZATION_DICT:
+        raise ValueError(
+            f"Unknown image normalization type: {norm_type}. Available options: {list(IMAGE_NORMALIZATION_DICT.keys())}"
+        )
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError("mapanything_b200.preprocess_inputs resizes on the GPU: pass a CUDA device")
+
+    up = _Uploader(dev)
+    processed_views = []
+    with torch.cuda.device(dev):
+        for view_idx, view in enumerate(input_views):
+            if "img" not in view:
+                raise ValueError(f"View {view_idx} missing required 'img' key")
+            d_img = _image_to_device_u8(view["img"], view_idx, dev, up)
+            H1, W1 = d_img.shape[0], d_img.shape[1]
+
+            depthmap = None
+            if "depth_z" in view:
+                depthmap = view["depth_z"]
+                if depthmap.ndim != 2:
+                    raise ValueError(f"Expected shape (H, W) for depth_z in view {view_idx}, got {depthmap.shape}")
+                assert tuple(depthmap.shape[:2]) == (H1, W1)
+            has_intrinsics, has_ray_directions = "intrinsics" in view, "ray_directions" in view
+            if has_intrinsics and has_ray_directions:
+                raise ValueError(
+                    f"View {view_idx} cannot have both 'intrinsics' and 'ray_directions'. "
+                    "Please provide only one as they are redundant (ray_directions can be used to recover intrinsics)."
+                )
+            intrinsics = None
+            if has_intrinsics:
+                intrinsics = _to_host_array(view["intrinsics"], (3, 3), "intrinsics", view_idx)
+            if has_ray_directions:
+                rays = view["ray_directions"]
+                if rays.ndim != 3 or rays.shape[2] != 3:
+                    raise ValueError(f"Expected shape (H, W, 3) for ray_directions in view {view_idx}, got {rays.shape}")
+                from .inference import intrinsics_from_rays
+
+                rays_t = rays if isinstance(rays, torch.Tensor) else torch.from_numpy(rays)
+                intrinsics = intrinsics_from_rays(rays_t.to(dev, torch.float32)[None])[0].cpu().numpy()
+
+            # rescale so that the image contains the crop, then crop (cropping.py:236-275, :425-458)
+            rw, rh, _, left, top = resize_plan(W1, H1, target_size)
+            if intrinsics is not None:
+                in_res, res = np.array((W1, H1)), np.array((rw, rh))
+                scale_final = max(np.array(target_size) / in_res) + 1e-8
+                intrinsics = _camera_matrix_of_crop(intrinsics, in_res, res, scaling=scale_final)
+                new_intrinsics = _camera_matrix_of_crop(intrinsics, (rw, rh), target_size, offset_factor=0.5)
+                left, top = (int(v) for v in np.int32(np.round(intrinsics[:2, 2] - new_intrinsics[:2, 2])))
+                intrinsics = intrinsics.copy()
+                intrinsics[0, 2] -= left
+                intrinsics[1, 2] -= top
+
+            processed_view = {
+                "img": resize_crop_normalize(d_img, target_size, norm_type, crop_offset=(left, top)),
+                "data_norm_type": [norm_type],
+            }
+            if depthmap is not None:
+                processed_view["depth_z"] = _resize_crop_depth(depthmap, H1, W1, rw, rh, left, top, tw, th, dev)
+            if intrinsics is not None:
+                processed_view["intrinsics"] = torch.from_numpy(intrinsics)[None]
+
+            if "camera_poses" in view:
+                camera_poses = view["camera_poses"]
+                if isinstance(camera_poses, tuple):
+                    def batched(c):
+                        if isinstance(c, torch.Tensor):
+                            return c[None]
+                        return torch.from_numpy(c)[None] if isinstance(c, np.ndarray) else torch.tensor(c)[None]
+
+                    quats, trans = camera_poses
+                    processed_view["camera_poses"] = (batched(quats), batched(trans))
+                elif isinstance(camera_poses, torch.Tensor):
+                    processed_view["camera_poses"] = camera_poses[None]
+                elif isinstance(camera_poses, np.ndarray):
+                    processed_view["camera_poses"] = torch.from_numpy(camera_poses)[None]
+                else:
+                    raise ValueError(
+                        f"Unsupported camera_poses format: {type(camera_poses)}. Expected tuple (quats, trans) or matrix (tensor/array)."
+                    )
+            for key, value in view.items():
+                if key not in ["img", "depth_z", "intrinsics", "ray_directions", "camera_poses"]:
+                    processed_view[key] = value
+            processed_views.append(processed_view)
+            if verbose:
+                print(f"Processed view {view_idx} with keys: {list(processed_view.keys())}")
+    if verbose:
+        print(f"Successfully processed {len(processed_views)} views")
+    return processed_views

@@ -328,6 +328,80 @@ def golden_image():
     np.savez_compressed(OUT / "image.npz", **out)
 
 
+PREPROCESS_CASES = {
+    "fixed": dict(resize_mode="fixed_size", size=(140, 98)),
+    "square": dict(resize_mode="square", size=112),
+    "longest": dict(resize_mode="longest_side", size=154),
+}
+
+
+def synth_multimodal_views(seed: int = 5):
+    """Four views covering every input form preprocess_inputs accepts (image.py:345-356): uint8 / float arrays, float
+    tensors, PIL images; intrinsics (float32 array, tensor, float64), ray directions, depth (array / tensor), poses as a
+    matrix and as a (quats, trans) tuple, pass-through keys."""
+    import PIL.Image
+
+    from oracle.geometry import rays_from_intrinsics
+
+    rng = np.random.default_rng(seed)
+    views = []
+    W, H = 200, 150
+    views.append(dict(img=synth_image(W, H, 1), intrinsics=np.array([[180.0, 0, 101.3], [0, 182.0, 73.9], [0, 0, 1]], np.float32),
+                      depth_z=rng.uniform(1, 4, (H, W)).astype(np.float32), camera_poses=np.eye(4, dtype=np.float32),
+                      is_metric_scale=torch.tensor([True])))
+    W, H = 180, 135
+    views.append(dict(img=torch.from_numpy(synth_image(W, H, 2)).float() / 255,
+                      intrinsics=torch.tensor([[170.0, 0, 88.0], [0, 170.0, 70.0], [0, 0, 1]]),
+                      camera_poses=(torch.tensor([0, 0, 0, 1.0]), np.array([0.1, 0.2, 0.3], np.float32))))
+    W, H = 240, 181
+    rays = rays_from_intrinsics(torch.tensor([[[210.0, 0, 119.5], [0, 209.0, 90.2], [0, 0, 1]]]), H, W)[0]
+    views.append(dict(img=PIL.Image.fromarray(synth_image(W, H, 3)), ray_directions=rays,
+                      depth_z=torch.from_numpy(rng.uniform(1, 4, (H, W)).astype(np.float32))))
+    views.append(dict(img=synth_image(161, 120, 4).astype(np.float32) / 255.0, instance="x"))
+    W, H = 210, 140
+    views.append(dict(img=torch.from_numpy(synth_image(W, H, 6)).float(),  # float tensor in [0, 255]
+                      intrinsics=np.array([[190.0, 0, 104.5], [0, 190.0, 69.5], [0, 0, 1]], np.float64),
+                      depth_z=rng.uniform(0, 3, (H, W)).astype(np.float32)))
+    return views
+
+
+def golden_preprocess_inputs():
+    """preprocess_inputs (mapanything/utils/image.py:335-675) on synthetic multi-modal views."""
+    from mapanything.utils import geometry as RG
+    from mapanything.utils import image as RIM
+
+    from oracle import image as OI
+
+    out = {}
+    for name, kw in PREPROCESS_CASES.items():
+        ref = RIM.preprocess_inputs(synth_multimodal_views(), **kw)
+        mine = OI.preprocess_inputs(synth_multimodal_views(), **kw)
+        for i, (rv, mv) in enumerate(zip(ref, mine)):
+            assert set(rv.keys()) == set(mv.keys()), (rv.keys(), mv.keys())
+            for key in rv:
+                if key == "camera_poses" and isinstance(rv[key], tuple):
+                    assert all(torch.equal(a, b) for a, b in zip(rv[key], mv[key]))
+                    out[f"{name}_v{i}_pose_q"], out[f"{name}_v{i}_pose_t"] = rv[key][0].numpy(), rv[key][1].numpy()
+                elif torch.is_tensor(rv[key]):
+                    assert rv[key].dtype == mv[key].dtype and rv[key].shape == mv[key].shape, (name, i, key)
+                    if "ray_directions" in synth_multimodal_views()[i] and key == "intrinsics":
+                        # recovered from rays by least squares: the oracle's own solver, tolerance instead of bits
+                        _assert_close(mv[key], rv[key], 2e-3, f"preprocess_inputs[{name}] v{i} intrinsics (from rays)")
+                    else:
+                        assert torch.equal(rv[key], mv[key]), f"preprocess_inputs[{name}] view {i} {key}: oracle differs"
+                    arr = rv[key].numpy()
+                    if key == "img" and name != "fixed":  # keep the fixture small: strided sample + exact sums
+                        out[f"{name}_v{i}_img_sample"] = arr[:, :, ::3, ::3].copy()
+                        out[f"{name}_v{i}_img_sum"] = arr.astype(np.float64).sum(axis=(0, 2, 3))
+                        out[f"{name}_v{i}_img_shape"] = np.array(arr.shape)
+                    else:
+                        out[f"{name}_v{i}_{key}"] = arr
+                else:
+                    assert rv[key] == mv[key]
+        print(f"  oracle vs reference  preprocess_inputs[{name:<8s}] {len(ref)} views                      bit-exact")
+    np.savez_compressed(OUT / "preprocess_inputs.npz", **out)
+
+
 def main():
     assert REF.exists(), "this script needs /root/reference (build container only)"
     _install_reference_stubs()
@@ -339,6 +413,8 @@ def main():
     golden_inference()
     print("load_images:")
     golden_image()
+    print("preprocess_inputs:")
+    golden_preprocess_inputs()
     print("DINOv2 ViT:")
     golden_vit()
     for f in sorted(OUT.glob("*.npz")):

@@ -126,3 +126,71 @@ def test_load_images_validation_errors_need_no_gpu():
         load_images(42)
     with pytest.raises(ValueError, match="Unknown image normalization type"):
         load_images([], norm_type="nope")
+
+
+# ------------------------------------------------------------------------------------------------ preprocess_inputs
+PGOLD = Path(__file__).parent / "golden" / "preprocess_inputs.npz"
+
+
+def check_preprocessed(gold, name, views, rays_tol=2e-3, source_views=None):
+    """views: output of a preprocess_inputs implementation on oracle.make_golden.synth_multimodal_views()."""
+    assert len(views) == 5
+    for i, v in enumerate(views):
+        assert v["data_norm_type"] == ["dinov2"]
+        img = v["img"].cpu().numpy()
+        if f"{name}_v{i}_img" in gold:
+            assert np.array_equal(img, gold[f"{name}_v{i}_img"])
+        else:
+            assert tuple(img.shape) == tuple(gold[f"{name}_v{i}_img_shape"])
+            assert np.array_equal(img[:, :, ::3, ::3], gold[f"{name}_v{i}_img_sample"])
+            assert np.array_equal(img.astype(np.float64).sum(axis=(0, 2, 3)), gold[f"{name}_v{i}_img_sum"])
+        for key in ("depth_z", "intrinsics", "camera_poses", "is_metric_scale"):
+            gk = f"{name}_v{i}_{key}"
+            if key == "camera_poses" and f"{name}_v{i}_pose_q" in gold:
+                q, t = v["camera_poses"]
+                assert np.array_equal(q.cpu().numpy(), gold[f"{name}_v{i}_pose_q"])
+                assert np.array_equal(t.cpu().numpy(), gold[f"{name}_v{i}_pose_t"])
+                continue
+            if gk not in gold:
+                assert key not in v, (i, key)
+                continue
+            got = v[key].cpu().numpy()
+            assert got.shape == gold[gk].shape and got.dtype == gold[gk].dtype, (i, key, got.dtype, gold[gk].dtype)
+            if key == "intrinsics" and i == 2:  # recovered from ray directions (least squares): tolerance, not bits
+                assert np.abs(got - gold[gk]).max() <= rays_tol * np.abs(gold[gk]).max()
+            else:
+                assert np.array_equal(got, gold[gk]), (i, key)
+        assert "ray_directions" not in v
+    assert views[3]["instance"] == "x"
+
+
+@pytest.mark.parametrize("name", ["fixed", "square", "longest"])
+def test_oracle_preprocess_inputs_matches_reference_golden(name):
+    from oracle.make_golden import PREPROCESS_CASES, synth_multimodal_views
+
+    gold = np.load(PGOLD)
+    check_preprocessed(gold, name, OI.preprocess_inputs(synth_multimodal_views(), **PREPROCESS_CASES[name]))
+
+
+def test_oracle_nearest_matches_opencv():
+    import cv2
+
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        sh, sw, dh, dw = (int(v) for v in rng.integers(5, 400, 4))
+        a = rng.random((sh, sw), dtype=np.float32)
+        ref = cv2.resize(a, (dw, dh), interpolation=cv2.INTER_NEAREST)
+        assert np.array_equal(a[OI.nearest_indices(sh, dh)][:, OI.nearest_indices(sw, dw)], ref)
+
+
+def test_preprocess_inputs_validation_errors_need_no_gpu():
+    from mapanything_b200.image import preprocess_inputs
+
+    with pytest.raises(ValueError, match="input_views cannot be empty"):
+        preprocess_inputs([])
+    with pytest.raises(ValueError, match="No valid images found"):
+        preprocess_inputs([{"depth_z": np.zeros((4, 4), np.float32)}])
+    with pytest.raises(ValueError, match=r"Expected array shape \(H, W, 3\)"):
+        preprocess_inputs([{"img": np.zeros((4, 4), np.uint8)}])
+    with pytest.raises(ValueError, match="Unsupported image type"):
+        preprocess_inputs([{"img": "file.png"}])
