@@ -317,6 +317,12 @@ int ma_apply_mask(const float* in, int in_stride, int in_offset, const uint8_t* 
  * arithmetic of torch) by exact radix selection, mask = conf > thr (1 byte bool).  thr_out [n] optional. */
 int ma_quantile_mask(const float* conf, uint8_t* mask, float* thr_out, int n, int64_t per_image, float q, void* stream);
 
+/* depthmap_to_camera_frame / depthmap_to_world_frame (geometry.py:18-114; what every demo calls on infer()'s depth_z,
+ * intrinsics and camera_poses: scripts/demo_images_only_inference.py:179): depth (n,H,W), K (n,3,3), pose (n,4,4)
+ * cam2world or NULL (camera frame) -> pts (n,H,W,3), valid (n,H,W) bytes = depth > 0 (may be NULL). */
+int ma_depthmap_to_world(const float* depth, const float* K, const float* pose, float* pts, uint8_t* valid, int n, int H,
+                         int W, void* stream);
+
 /* out = a & b over n bool bytes. */
 int ma_mask_and(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t n, void* stream);
 

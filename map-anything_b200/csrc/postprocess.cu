@@ -351,9 +351,49 @@ __global__ void quantile_mask_kernel(const float* __restrict__ conf, uint8_t* __
   for (int64_t i = threadIdx.x; i < per_image; i += blockDim.x) m[i] = x[i] > thr ? 1 : 0;
 }
 
+// depthmap_to_camera_frame / depthmap_to_world_frame (geometry.py:18-114): one thread per pixel.  The camera-frame point
+// uses the reference's operation order ((x - cx) * z) / fx with IEEE roundings (bit-exact); the optional cam2world
+// transform is the 3x4 part of the homogeneous product.
+__global__ void depthmap_to_world_kernel(const float* __restrict__ depth, const float* __restrict__ K, const float* __restrict__ pose,
+                                         float* __restrict__ pts, uint8_t* __restrict__ valid, int H, int W) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  const float* k = K + b * 9;
+  const float fx = k[0], fy = k[4], cx = k[2], cy = k[5];
+  const float z = depth[static_cast<int64_t>(b) * H * W + i];
+  const float xg = static_cast<float>(i % W), yg = static_cast<float>(i / W);
+  float x = __fdiv_rn(__fmul_rn(__fsub_rn(xg, cx), z), fx);
+  float y = __fdiv_rn(__fmul_rn(__fsub_rn(yg, cy), z), fy);
+  float zz = z;
+  if (pose) {
+    const float* p = pose + b * 16;
+    const float wx = p[0] * x + p[1] * y + p[2] * z + p[3];
+    const float wy = p[4] * x + p[5] * y + p[6] * z + p[7];
+    const float wz = p[8] * x + p[9] * y + p[10] * z + p[11];
+    x = wx;
+    y = wy;
+    zz = wz;
+  }
+  float* o = pts + (static_cast<int64_t>(b) * H * W + i) * 3;
+  o[0] = x;
+  o[1] = y;
+  o[2] = zz;
+  if (valid) valid[static_cast<int64_t>(b) * H * W + i] = z > 0.0f ? 1 : 0;
+}
+
 }  // namespace ma
 
 using namespace ma;
+
+extern "C" int ma_depthmap_to_world(const float* depth, const float* K, const float* pose, float* pts, uint8_t* valid, int n,
+                                    int H, int W, void* stream) {
+  MA_REQUIRE(depth && K && pts && n > 0 && H > 0 && W > 0, "ma_depthmap_to_world: bad arguments");
+  dim3 grid((H * W + 255) / 256, n);
+  depthmap_to_world_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(depth, K, pose, pts, valid, H, W);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
 
 extern "C" int ma_denorm_image(const float* img, float* out, int n, int H, int W, const float* mean_host, const float* std_host,
                                void* stream) {

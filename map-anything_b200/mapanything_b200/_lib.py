@@ -102,6 +102,7 @@ SIGNATURES = {
     "ma_apply_mask": (_i, [_p, _i, _i, _p, _p, _i64, _i, _p]),
     "ma_quantile_mask": (_i, [_p, _p, _p, _i, _i64, _f, _p]),
     "ma_mask_and": (_i, [_p, _p, _p, _i64, _p]),
+    "ma_depthmap_to_world": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "ma_resample_coeffs": (_i, [_i, _i, _i, C.POINTER(_i), _p, _p]),
     "ma_resample_h_u8rgb": (_i, [_p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p]),
     "ma_gather_rows_cols_f32": (_i, [_p, _i64, _p, _p, _i, _i, _p, _p]),

@@ -254,3 +254,23 @@ def normals_edge(normals: np.ndarray, tol_deg: float, mask: np.ndarray) -> np.nd
         ang = np.where(mwin, np.arccos(dots), 0).max(axis=0)
         ang = _nanmax_pool3(ang)
         return ang > np.deg2rad(tol_deg)
+
+
+def depthmap_to_camera_frame(depthmap: torch.Tensor, intrinsics: torch.Tensor):
+    """reference geometry.py:18-73: (B,H,W) depth + (B,3,3) intrinsics -> (B,H,W,3) camera-frame points, valid mask."""
+    B, H, W = depthmap.shape
+    xg, yg = torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing="xy")
+    fx, fy = intrinsics[:, 0, 0].view(-1, 1, 1), intrinsics[:, 1, 1].view(-1, 1, 1)
+    cx, cy = intrinsics[:, 0, 2].view(-1, 1, 1), intrinsics[:, 1, 2].view(-1, 1, 1)
+    xx = (xg[None] - cx) * depthmap / fx
+    yy = (yg[None] - cy) * depthmap / fy
+    return torch.stack((xx, yy, depthmap), dim=-1), depthmap > 0.0
+
+
+def depthmap_to_world_frame(depthmap: torch.Tensor, intrinsics: torch.Tensor, camera_pose=None):
+    """reference geometry.py:76-114."""
+    pts, valid = depthmap_to_camera_frame(depthmap, intrinsics)
+    if camera_pose is not None:
+        homo = torch.cat([pts, torch.ones_like(pts[..., :1])], dim=-1)
+        pts = torch.einsum("bik,bhwk->bhwi", camera_pose, homo)[..., :3]
+    return pts, valid

@@ -402,6 +402,35 @@ def golden_preprocess_inputs():
     np.savez_compressed(OUT / "preprocess_inputs.npz", **out)
 
 
+def golden_depthmap():
+    """depthmap_to_camera_frame / depthmap_to_world_frame (mapanything/utils/geometry.py:18-114)."""
+    from mapanything.utils import geometry as RG
+
+    from oracle import geometry as G
+
+    g = torch.Generator().manual_seed(21)
+    b, h, w = 2, 24, 32
+    depth = torch.rand(b, h, w, generator=g) * 3
+    depth[0, 3:6, 4:9] = 0.0  # invalid pixels
+    K = torch.tensor([[[30.0, 0, 15.5], [0, 31.0, 11.5], [0, 0, 1]], [[28.0, 0, 16.2], [0, 28.5, 12.3], [0, 0, 1]]])
+    q = torch.randn(b, 4, generator=g)
+    q = q / q.norm(dim=-1, keepdim=True)
+    pose = torch.eye(4).repeat(b, 1, 1)
+    pose[:, :3, :3] = RG.quaternion_to_rotation_matrix(q)
+    pose[:, :3, 3] = torch.randn(b, 3, generator=g)
+    out = dict(depth=depth.numpy(), K=K.numpy(), pose=pose.numpy())
+    rc, rv = RG.depthmap_to_camera_frame(depth, K)
+    mc, mv = G.depthmap_to_camera_frame(depth, K)
+    assert torch.equal(rc, mc) and torch.equal(rv, mv)
+    rw, rv2 = RG.depthmap_to_world_frame(depth, K, pose)
+    mw, _ = G.depthmap_to_world_frame(depth, K, pose)
+    _assert_close(mw, rw, 1e-6, "depthmap_to_world_frame")
+    r1, v1 = RG.depthmap_to_world_frame(depth[0], K[0], pose[0])  # un-batched form
+    assert torch.equal(r1, rw[0]) or (r1 - rw[0]).abs().max() < 1e-6
+    out.update(pts_cam=rc.numpy(), valid=rv.numpy(), pts_world=rw.numpy())
+    np.savez_compressed(OUT / "depthmap.npz", **out)
+
+
 def main():
     assert REF.exists(), "this script needs /root/reference (build container only)"
     _install_reference_stubs()
@@ -411,6 +440,8 @@ def main():
     golden_geometry()
     print("inference pre/post:")
     golden_inference()
+    print("depthmap:")
+    golden_depthmap()
     print("load_images:")
     golden_image()
     print("preprocess_inputs:")

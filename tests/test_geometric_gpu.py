@@ -197,3 +197,23 @@ def test_forward_full_size_multimodal_two_views():
     print(f"\n[full-size multi-modal] fused features rel err {e:.3e}; geometric inputs move them by {moved:.3e}")
     assert moved > 5 * e and e < 1.5e-2
     _assert_within(_metrics(got, ref), "full-size multi-modal (V=2), reference-style init", floor=_metrics(amp, ref))
+
+
+def test_depthmap_to_world_frame_matches_reference_golden():
+    """ma_depthmap_to_world vs the reference's own outputs (tests/golden/depthmap.npz): the camera-frame points are
+    bit-exact (same operation order, IEEE roundings), the world-frame points within 1e-6 (sum order of the 4-vector product)."""
+    from pathlib import Path
+
+    import numpy as np
+
+    from mapanything_b200.geometry import depthmap_to_camera_frame, depthmap_to_world_frame
+
+    gold = np.load(Path(__file__).parent / "golden" / "depthmap.npz")
+    depth, K, pose = (torch.from_numpy(gold[k]).cuda() for k in ("depth", "K", "pose"))
+    pc, valid = depthmap_to_camera_frame(depth, K)
+    assert np.array_equal(pc.cpu().numpy(), gold["pts_cam"])
+    assert valid.dtype == torch.bool and np.array_equal(valid.cpu().numpy(), gold["valid"])
+    pw, valid2 = depthmap_to_world_frame(depth, K, pose)
+    assert np.abs(pw.cpu().numpy() - gold["pts_world"]).max() < 1e-6 and torch.equal(valid, valid2)
+    p1, v1 = depthmap_to_world_frame(depth[1], K[1], pose[1])  # un-batched form
+    assert p1.shape == (24, 32, 3) and torch.equal(p1, pw[1]) and torch.equal(v1, valid[1])

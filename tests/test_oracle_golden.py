@@ -170,3 +170,14 @@ def test_vit_large_matches_reference_518():
     assert torch.allclose(out[0, rows], _t(g["vitl_tokens"]), atol=5e-4)
     assert torch.allclose(out[0].mean(0), _t(g["vitl_col_mean"]), atol=5e-4)
     assert out.abs().mean().item() == pytest.approx(float(g["vitl_mean_abs"]), rel=1e-3)
+
+
+def test_depthmap_to_world_frame_matches_reference():
+    from oracle import geometry as G
+
+    gold = np.load(GOLD / "depthmap.npz")
+    depth, K, pose = (torch.from_numpy(gold[k]) for k in ("depth", "K", "pose"))
+    pc, valid = G.depthmap_to_camera_frame(depth, K)
+    assert np.array_equal(pc.numpy(), gold["pts_cam"]) and np.array_equal(valid.numpy(), gold["valid"])
+    pw, _ = G.depthmap_to_world_frame(depth, K, pose)
+    assert np.abs(pw.numpy() - gold["pts_world"]).max() < 1e-6
