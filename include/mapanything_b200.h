@@ -266,19 +266,20 @@ int ma_fuse_add(float* feat, int V, int N, int C, const float* dense_a, const in
  * written; pass bounds = coeffs = NULL to query it.  in_size == out_size gives identity taps (PIL skips that pass). */
 int ma_resample_coeffs(int in_size, int out_size, int filter, int* ksize_out, int32_t* bounds, int32_t* coeffs);
 
-/* Horizontal pass.  src: device u8 RGB, interleaved, row stride in bytes; source rows [y0, y0+rows), source columns
- * [sx0, sx1) are read (sx0/sx1 = the window span of output columns [x0, x0+cols)); bounds / coeffs: device copies of the
- * tables for the horizontal axis (out_size columns).  tmp: device u8 [rows][cols][3]. */
-int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int y0, int rows, int sx0, int sx1,
-                        const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols, uint8_t* tmp,
-                        void* stream);
+/* Horizontal pass over n frames of the same size.  src: device u8 RGB, interleaved; row / frame strides in bytes;
+ * source rows [y0, y0+rows) and source columns [sx0, sx1) are read (sx0/sx1 = the window span of output columns
+ * [x0, x0+cols)); bounds / coeffs: device copies of the tables for the horizontal axis (out_size columns).
+ * tmp: device u8 [n][rows][cols][3]. */
+int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int64_t src_frame_stride, int n, int y0, int rows,
+                        int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols,
+                        uint8_t* tmp, void* stream);
 
-/* Vertical pass + crop + normalise.  tmp: [rows][cols][3] u8 whose row 0 is source row y0; output rows
- * [top, top+th) of the resampled image (out_size rows).  out_chw: fp32 (3, th, cols) = ((u/255) - mean) / std in
- * torchvision's rounding order (mean / std: 3 HOST floats), may be NULL; out_u8: u8 [th][cols][3], may be NULL. */
-int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int cols, int y0, const int32_t* bounds, const int32_t* coeffs,
-                             int out_size, int top, int th, const float* mean_host, const float* std_host, float* out_chw,
-                             uint8_t* out_u8, void* stream);
+/* Vertical pass + crop + normalise.  tmp: [n][rows][cols][3] u8 whose row 0 is source row y0; output rows
+ * [top, top+th) of the resampled image (out_size rows).  out_chw: fp32 (n, 3, th, cols) = ((u/255) - mean) / std in
+ * torchvision's rounding order (mean / std: 3 HOST floats), may be NULL; out_u8: u8 [n][th][cols][3], may be NULL. */
+int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int n, int rows, int cols, int y0, const int32_t* bounds,
+                             const int32_t* coeffs, int out_size, int top, int th, const float* mean_host,
+                             const float* std_host, float* out_chw, uint8_t* out_u8, void* stream);
 
 /* preprocess_inputs() (image.py:335-675) resizes depth maps with cv2.resize(INTER_NEAREST) and slices the crop
  * (cropping.py:248-255, :339): out[y][x] = src[y_idx[y]][x_idx[x]], th x tw; y_idx / x_idx: device int32 source offsets

@@ -46,12 +46,13 @@ __device__ __forceinline__ uint8_t clip8(int v) {
   return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// One block per source row [y0 + blockIdx.x]; output columns [x0, x0 + cols) of the resampled row.
-__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int y0, int sx0, int sx1,
-                                  const int32_t* __restrict__ bounds, const int32_t* __restrict__ coeffs, int out_size, int x0,
-                                  int cols, uint8_t* __restrict__ tmp) {
+// One block per source row [y0 + blockIdx.x] of frame blockIdx.y; output columns [x0, x0 + cols) of the resampled row.
+__global__ void resample_h_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int y0, int sx0,
+                                  int sx1, const int32_t* __restrict__ bounds, const int32_t* __restrict__ coeffs, int out_size,
+                                  int x0, int cols, uint8_t* __restrict__ tmp) {
   extern __shared__ __align__(16) uint8_t srow[];
-  const uint8_t* row = src + (y0 + static_cast<int64_t>(blockIdx.x)) * row_stride + static_cast<int64_t>(sx0) * 3;
+  const uint8_t* row = src + blockIdx.y * frame_stride + (y0 + static_cast<int64_t>(blockIdx.x)) * row_stride +
+                       static_cast<int64_t>(sx0) * 3;
   const int nbytes = (sx1 - sx0) * 3;
   // 4-byte coalesced loads from the enclosing aligned span; `mis` is the offset of the first wanted byte in it
   const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
@@ -61,7 +62,7 @@ __global__ void resample_h_kernel(const uint8_t* __restrict__ src, int64_t row_s
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) s4[i] = __ldg(row4 + i);
   __syncthreads();
   const uint8_t* s = srow + mis;
-  uint8_t* orow = tmp + static_cast<int64_t>(blockIdx.x) * cols * 3;
+  uint8_t* orow = tmp + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * cols * 3;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) {
     const int xx = x0 + i;
     const int first = bounds[2 * xx], cnt = bounds[2 * xx + 1];
@@ -79,8 +80,8 @@ __global__ void resample_h_kernel(const uint8_t* __restrict__ src, int64_t row_s
   }
 }
 
-// Thread per output pixel (x, yy = top + blockIdx.y) of the cropped target.
-__global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int cols, int y0, const int32_t* __restrict__ bounds,
+// Thread per output pixel (x, yy = top + blockIdx.y) of the cropped target of frame blockIdx.z.
+__global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows, int cols, int y0, const int32_t* __restrict__ bounds,
                                        const int32_t* __restrict__ coeffs, int out_size, int top, int th, float m0, float m1,
                                        float m2, float s0, float s1, float s2, float* __restrict__ out_chw,
                                        uint8_t* __restrict__ out_u8) {
@@ -90,7 +91,7 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int cols
   const int yy = top + y;
   const int first = bounds[2 * yy], cnt = bounds[2 * yy + 1];
   int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
-  const uint8_t* p = tmp + (static_cast<int64_t>(first - y0) * cols + x) * 3;
+  const uint8_t* p = tmp + ((static_cast<int64_t>(blockIdx.z) * rows + (first - y0)) * cols + x) * 3;
   const int64_t rs = static_cast<int64_t>(cols) * 3;
   for (int t = 0; t < cnt; ++t, p += rs) {
     const int k = __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy);  // warp-uniform
@@ -100,7 +101,7 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int cols
   }
   const uint8_t u0 = clip8(a0), u1 = clip8(a1), u2 = clip8(a2);
   if (out_u8) {
-    uint8_t* o = out_u8 + (static_cast<int64_t>(y) * cols + x) * 3;
+    uint8_t* o = out_u8 + ((static_cast<int64_t>(blockIdx.z) * th + y) * cols + x) * 3;
     o[0] = u0;
     o[1] = u1;
     o[2] = u2;
@@ -108,7 +109,7 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int cols
   if (out_chw) {
     // torchvision: ToTensor = float(u) / 255, Normalize = (t - mean) / std; each step rounded to fp32
     const int64_t plane = static_cast<int64_t>(th) * cols;
-    const int64_t o = static_cast<int64_t>(y) * cols + x;
+    const int64_t o = 3 * plane * blockIdx.z + static_cast<int64_t>(y) * cols + x;
     out_chw[o] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u0), 255.0f), m0), s0);
     out_chw[plane + o] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u1), 255.0f), m1), s1);
     out_chw[2 * plane + o] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(u2), 255.0f), m2), s2);
@@ -207,11 +208,12 @@ extern "C" int ma_resample_coeffs(int in_size, int out_size, int filter, int* ks
   return MA_OK;
 }
 
-extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int y0, int rows, int sx0, int sx1,
-                                   const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols, uint8_t* tmp,
-                                   void* stream) {
-  MA_REQUIRE(src && bounds && coeffs && tmp && rows > 0 && cols > 0 && sx1 > sx0 && x0 >= 0 && x0 + cols <= out_size,
-             "ma_resample_h_u8rgb: bad arguments (rows=%d cols=%d)", rows, cols);
+extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int64_t src_frame_stride, int n, int y0, int rows,
+                                   int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols,
+                                   uint8_t* tmp, void* stream) {
+  MA_REQUIRE(src && bounds && coeffs && tmp && n > 0 && n <= 65535 && rows > 0 && cols > 0 && sx1 > sx0 && x0 >= 0 &&
+                 x0 + cols <= out_size,
+             "ma_resample_h_u8rgb: bad arguments (n=%d rows=%d cols=%d)", n, rows, cols);
   const size_t smem = static_cast<size_t>(sx1 - sx0) * 3 + 8;
   MA_REQUIRE(smem <= 200 * 1024, "ma_resample_h_u8rgb: source rows of %d pixels do not fit shared memory", sx1 - sx0);
   if (smem > 48 * 1024) {
@@ -221,23 +223,24 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
       configured = 200 * 1024;
     }
   }
-  resample_h_kernel<<<rows, 256, smem, static_cast<cudaStream_t>(stream)>>>(src, src_row_stride, y0, sx0, sx1, bounds, coeffs,
-                                                                           out_size, x0, cols, tmp);
+  resample_h_kernel<<<dim3(rows, n), 256, smem, static_cast<cudaStream_t>(stream)>>>(src, src_row_stride, src_frame_stride, y0, sx0,
+                                                                                     sx1, bounds, coeffs, out_size, x0, cols, tmp);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
 
-extern "C" int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int cols, int y0, const int32_t* bounds, const int32_t* coeffs,
-                                        int out_size, int top, int th, const float* mean_host, const float* std_host,
-                                        float* out_chw, uint8_t* out_u8, void* stream) {
-  MA_REQUIRE(tmp && bounds && coeffs && cols > 0 && th > 0 && top >= 0 && top + th <= out_size && (out_chw || out_u8),
-             "ma_resample_v_norm_u8rgb: bad arguments (cols=%d th=%d)", cols, th);
+extern "C" int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int n, int rows, int cols, int y0, const int32_t* bounds,
+                                        const int32_t* coeffs, int out_size, int top, int th, const float* mean_host,
+                                        const float* std_host, float* out_chw, uint8_t* out_u8, void* stream) {
+  MA_REQUIRE(tmp && bounds && coeffs && n > 0 && n <= 65535 && rows > 0 && cols > 0 && th > 0 && top >= 0 && top + th <= out_size &&
+                 (out_chw || out_u8),
+             "ma_resample_v_norm_u8rgb: bad arguments (n=%d cols=%d th=%d)", n, cols, th);
   MA_REQUIRE(!out_chw || (mean_host && std_host), "ma_resample_v_norm_u8rgb: mean / std missing");
   const float m0 = mean_host ? mean_host[0] : 0.f, m1 = mean_host ? mean_host[1] : 0.f, m2 = mean_host ? mean_host[2] : 0.f;
   const float s0 = std_host ? std_host[0] : 1.f, s1 = std_host ? std_host[1] : 1.f, s2 = std_host ? std_host[2] : 1.f;
-  dim3 grid((cols + 127) / 128, th);
-  resample_v_norm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(tmp, cols, y0, bounds, coeffs, out_size, top, th, m0,
-                                                                             m1, m2, s0, s1, s2, out_chw, out_u8);
+  dim3 grid((cols + 127) / 128, th, n);
+  resample_v_norm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th,
+                                                                             m0, m1, m2, s0, s1, s2, out_chw, out_u8);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

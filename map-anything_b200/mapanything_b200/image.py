@@ -96,13 +96,17 @@ def resize_plan(W1: int, H1: int, target: Tuple[int, int]) -> Tuple[int, int, in
 
 def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_type: Optional[str] = "dinov2",
                           return_u8: bool = False, crop_offset: Optional[Tuple[int, int]] = None):
-    """img_u8: CUDA uint8 (H, W, 3), rows contiguous -> fp32 (1, 3, th, tw) normalised image (and / or the uint8
-    (th, tw, 3) image when return_u8), bit-exact with PIL resize + crop + torchvision ToTensor/Normalize.
+    """img_u8: CUDA uint8 (H, W, 3) or a batch (n, H, W, 3) of same-size frames, packed RGB -> fp32 (n, 3, th, tw)
+    normalised images (n = 1 for a single frame) and / or the uint8 (n, th, tw, 3) images when return_u8, bit-exact with
+    PIL resize + crop + torchvision ToTensor/Normalize.  One launch of each of the two kernels for the whole batch.
     crop_offset = (left, top) in the resized image; default: the centred crop of the image-only path."""
-    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.shape[2] != 3 or img_u8.stride(2) != 1 \
-            or img_u8.stride(1) != 3:
-        raise ValueError("resize_crop_normalize expects a CUDA uint8 (H, W, 3) tensor with packed RGB pixels")
-    H1, W1, _ = img_u8.shape
+    single = img_u8.dim() == 3
+    if single:
+        img_u8 = img_u8[None]
+    if not img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[3] != 3 or img_u8.stride(3) != 1 \
+            or img_u8.stride(2) != 3:
+        raise ValueError("resize_crop_normalize expects CUDA uint8 (H, W, 3) / (n, H, W, 3) tensors with packed RGB pixels")
+    n, H1, W1, _ = img_u8.shape
     tw, th = int(target[0]), int(target[1])
     rw, rh, filt, left, top = resize_plan(W1, H1, (tw, th))
     if crop_offset is not None:
@@ -117,9 +121,10 @@ def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_ty
     sx1 = int(th_.bounds[left + tw - 1, 0] + th_.bounds[left + tw - 1, 1])
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
-    tmp = torch.empty(y1 - y0, tw, 3, device=dev, dtype=torch.uint8)
-    check(lib.ma_resample_h_u8rgb(img_u8.data_ptr(), img_u8.stride(0), y0, y1 - y0, sx0, sx1, th_.d_bounds.data_ptr(),
-                                  th_.d_coeffs.data_ptr(), rw, left, tw, tmp.data_ptr(), stream), "ma_resample_h_u8rgb")
+    tmp = torch.empty(n, y1 - y0, tw, 3, device=dev, dtype=torch.uint8)
+    check(lib.ma_resample_h_u8rgb(img_u8.data_ptr(), img_u8.stride(1), img_u8.stride(0), n, y0, y1 - y0, sx0, sx1,
+                                  th_.d_bounds.data_ptr(), th_.d_coeffs.data_ptr(), rw, left, tw, tmp.data_ptr(), stream),
+          "ma_resample_h_u8rgb")
     out = out8 = None
     m3 = s3 = None
     if norm_type is not None:
@@ -129,13 +134,15 @@ def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_ty
             )
         mean, std = IMAGE_NORMALIZATION_DICT[norm_type]
         m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
-        out = torch.empty(1, 3, th, tw, device=dev, dtype=torch.float32)
+        out = torch.empty(n, 3, th, tw, device=dev, dtype=torch.float32)
     if return_u8 or out is None:
-        out8 = torch.empty(th, tw, 3, device=dev, dtype=torch.uint8)
-    check(lib.ma_resample_v_norm_u8rgb(tmp.data_ptr(), tw, y0, tv_.d_bounds.data_ptr(), tv_.d_coeffs.data_ptr(), rh, top, th,
-                                       m3, s3, None if out is None else out.data_ptr(),
+        out8 = torch.empty(n, th, tw, 3, device=dev, dtype=torch.uint8)
+    check(lib.ma_resample_v_norm_u8rgb(tmp.data_ptr(), n, y1 - y0, tw, y0, tv_.d_bounds.data_ptr(), tv_.d_coeffs.data_ptr(), rh,
+                                       top, th, m3, s3, None if out is None else out.data_ptr(),
                                        None if out8 is None else out8.data_ptr(), stream), "ma_resample_v_norm_u8rgb")
     ops._count(2)
+    if single and out8 is not None:
+        out8 = out8[0]
     if out is None:
         return out8
     return (out, out8) if return_u8 else out
@@ -150,7 +157,8 @@ class _Uploader:
         self.events: List[Optional[torch.cuda.Event]] = [None, None]
         self.i = 0
 
-    def upload(self, arr: np.ndarray) -> torch.Tensor:
+    def upload(self, arr: np.ndarray, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Copies `arr` into `dst` (a contiguous CUDA uint8 tensor of the same size) or into a new device tensor."""
         arr = np.ascontiguousarray(arr)
         n = arr.size
         j = self.i
@@ -160,7 +168,8 @@ class _Uploader:
         if self.bufs[j] is None or self.bufs[j].numel() < n:
             self.bufs[j] = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
         self.bufs[j][:n].numpy()[...] = arr.reshape(-1)
-        dst = torch.empty(arr.shape, dtype=torch.uint8, device=self.device)
+        if dst is None:
+            dst = torch.empty(arr.shape, dtype=torch.uint8, device=self.device)
         dst.view(-1).copy_(self.bufs[j][:n], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -241,6 +250,8 @@ def load_images(
     # first pass: decode on the host (Pillow, like the reference), start the uploads, collect aspect ratios
     up = _Uploader(dev)
     loaded, aspect_ratios = [], []
+    slabs: Dict[Tuple[int, int], List[list]] = {}   # (W, H) -> [[device tensor (cap, H, W, 3), frames used], ...]
+    slab_bytes = 256 << 20                          # frames per slab = what fits 256 MB (at least 1, at most 64)
     with torch.cuda.device(dev):
         for i, path in enumerate(folder_content):
             if i % stride != 0 or not path.lower().endswith(exts):
@@ -255,7 +266,16 @@ def load_images(
                 else:
                     img = exif_transpose(PIL.Image.open(os.path.join(root, path))).convert("RGB")
                 W1, H1 = img.size
-                loaded.append((path, up.upload(np.asarray(img)), W1, H1))
+                arr = np.asarray(img)
+                # frames of one size are uploaded side by side, so the resize runs as one batched launch per slab
+                lst = slabs.setdefault((W1, H1), [])
+                if not lst or lst[-1][1] == lst[-1][0].shape[0]:
+                    cap = max(1, min(64, slab_bytes // (H1 * W1 * 3)))
+                    lst.append([torch.empty(cap, H1, W1, 3, dtype=torch.uint8, device=dev), 0])
+                slab = lst[-1]
+                up.upload(arr, slab[0][slab[1]])
+                loaded.append((path, (W1, H1), len(lst) - 1, slab[1], W1, H1))
+                slab[1] += 1
                 aspect_ratios.append(W1 / H1)
             except Exception as e:  # noqa: BLE001  (the reference skips unreadable files the same way)
                 if verbose:
@@ -266,10 +286,12 @@ def load_images(
         target_size = _target_size(aspect_ratios, resize_mode, size, patch_size, resolution_set, verbose)
         if verbose:
             print(f"Using target resolution {target_size[0]}x{target_size[1]} (W x H) for all images")
-        # second pass: resize + crop + normalise on the device
+        # second pass: resize + crop + normalise on the device, ONE pair of launches per slab of same-size frames
+        resized = {key: [resize_crop_normalize(t[:used], target_size, norm_type) for t, used in lst] for key, lst in slabs.items()}
+        tensors = [resized[key][si][fi:fi + 1] for _, key, si, fi, _, _ in loaded]
+        del slabs
         imgs = []
-        for path, d_img, W1, H1 in loaded:
-            t = resize_crop_normalize(d_img, target_size, norm_type)
+        for (path, _, _, _, W1, H1), t in zip(loaded, tensors):
             H2, W2 = t.shape[2], t.shape[3]
             if verbose:
                 print(f" - Adding {path} with resolution {W1}x{H1} --> {W2}x{H2}")
