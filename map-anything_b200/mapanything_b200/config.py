@@ -67,6 +67,31 @@ def mapanything_config(**overrides) -> dict:
     return cfg
 
 
+# module_args of the alternating-attention variants under the reference's configs/model/info_sharing/
+INFO_SHARING_VARIANTS = {
+    "aat_ifr_24_layers": {"name": "aat_24_layers_ifr", "indices": [11, 17], "size": "24_layers", "depth": 24,
+                          "distinguish_ref_and_non_ref_views": True},
+    "aat_ifr_24_layers_no_ref_view": {"name": "aat_24_layers_ifr_no_ref_view", "indices": [11, 17], "size": "24_layers",
+                                      "depth": 24, "distinguish_ref_and_non_ref_views": False},
+    "aat_ifr_48_layers": {"name": "aat_48_layers_ifr", "indices": [11, 23, 35], "size": "48_layers", "depth": 48, "dim": 1024,
+                          "num_heads": 16, "distinguish_ref_and_non_ref_views": True},
+    "aat_ifr_48_layers_no_ref_view": {"name": "aat_48_layers_ifr_no_ref_view", "indices": [11, 23, 35], "size": "48_layers",
+                                      "depth": 48, "dim": 1024, "num_heads": 16, "distinguish_ref_and_non_ref_views": False},
+}
+
+
+def mapanything_variant_config(info_sharing: str = "aat_ifr_24_layers", **overrides) -> dict:
+    """mapanything_config() with another info-sharing YAML of the reference (`model/info_sharing=<name>` on its Hydra
+    command line): the 48-layer / width-1024 transformer with three taps, and the variants without reference-view embedding."""
+    if info_sharing not in INFO_SHARING_VARIANTS:
+        raise ValueError(f"info_sharing must be one of {sorted(INFO_SHARING_VARIANTS)} (this build has alternating attention "
+                         f"with intermediate features only), got {info_sharing!r}")
+    cfg = mapanything_config(**overrides)
+    cfg["info_sharing_config"]["module_args"] = {"norm_intermediate": True, "gradient_checkpointing": False,
+                                                 **copy.deepcopy(INFO_SHARING_VARIANTS[info_sharing])}
+    return cfg
+
+
 def tiny_config(img_size: int = 70, enc_dim: int = 128, enc_depth: int = 2, enc_heads: int = 2, info_dim: int = 128,
                 info_heads: int = 2, info_depth: int = 4, indices=(1, 2)) -> dict:
     """Same wiring at toy width/depth, for fast CPU tests of the host logic and of oracle-vs-CUDA parity."""

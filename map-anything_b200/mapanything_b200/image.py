@@ -123,7 +123,8 @@ def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_ty
     stream = torch.cuda.current_stream().cuda_stream
     tmp = torch.empty(n, y1 - y0, tw, 3, device=dev, dtype=torch.uint8)
     check(lib.ma_resample_h_u8rgb(img_u8.data_ptr(), img_u8.stride(1), img_u8.stride(0), n, y0, y1 - y0, sx0, sx1,
-                                  th_.d_bounds.data_ptr(), th_.d_coeffs.data_ptr(), rw, left, tw, tmp.data_ptr(), stream),
+                                  th_.d_bounds.data_ptr(), th_.d_coeffs.data_ptr(), th_.d_coeffs.shape[0], rw, left, tw,
+                                  tmp.data_ptr(), stream),
           "ma_resample_h_u8rgb")
     out = out8 = None
     m3 = s3 = None

@@ -121,19 +121,24 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                 f"model_return_type='intermediate_features' (got {self.info_sharing_type!r}, {self.info_sharing_return_type!r})"
             )
         self.info_sharing = P.AlternatingAttentionIFR(**cfg["module_args"])
+        # reference model.py:304-313: 2 taps -> the DPT also takes the (fused) encoder features; 3 taps -> it does not
         if len(self.info_sharing.indices) == 2:
             self.use_encoder_features_for_dpt = True
+        elif len(self.info_sharing.indices) == 3:
+            self.use_encoder_features_for_dpt = False
         else:
             raise ValueError(
-                "Invalid number of indices provided for info sharing feature returner. This build supports 2 indices "
-                "(encoder features + 2 intermediate + final for the DPT head)."
+                "Invalid number of indices provided for info sharing feature returner. Please provide 2 or 3 indices."
             )
 
     def _initialize_prediction_heads(self, cfg):
         if self.pred_head_type != "dpt+pose":
             raise ValueError(f"Invalid pred_head_type: {self.pred_head_type}. This build supports 'dpt+pose'.")
         cfg["feature_head"]["patch_size"] = self.encoder.patch_size
-        cfg["feature_head"]["input_feature_dims"] = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+        if self.use_encoder_features_for_dpt:
+            cfg["feature_head"]["input_feature_dims"] = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+        else:
+            cfg["feature_head"]["input_feature_dims"] = [self.info_sharing.dim] * 4
         cfg["regressor_head"]["input_feature_dim"] = cfg["feature_head"]["feature_dim"]
         cfg["pose_head"]["patch_size"] = self.encoder.patch_size
         cfg["pose_head"]["input_feature_dim"] = self.info_sharing.dim
@@ -324,8 +329,8 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                     self._fuse_geometric_inputs(eng, feat, views, b, N, plan, comm)
                 fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
                 taps, final, final32 = eng.info_sharing(fused, num_views, N, plan=plan, comm=comm)
-                raw, pose_raw = eng.dpt_and_pose([fused, taps[0], taps[1], final], num_views, hp, wp, height, width,
-                                                 final32=final32[:num_views * N])
+                dpt_in = [fused, taps[0], taps[1], final] if self.use_encoder_features_for_dpt else [*taps, final]
+                raw, pose_raw = eng.dpt_and_pose(dpt_in, num_views, hp, wp, height, width, final32=final32[:num_views * N])
                 if plan is None:
                     scale_raw = eng.scale_head(final32[num_views * N:])
                 else:  # the scale token lives on rank 0: one float travels to the other ranks

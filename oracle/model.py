@@ -81,13 +81,13 @@ class MapAnythingOracle(nn.Module):
         info_sharing_config["module_args"]["input_embed_dim"] = c
         info_sharing_config["module_args"]["custom_positional_encoding"] = None
         self.info_sharing = U.MultiViewAlternatingAttentionTransformerIFR(**info_sharing_config["module_args"])
-        assert len(self.info_sharing.indices) == 2
-        self.use_encoder_features_for_dpt = True
+        assert len(self.info_sharing.indices) in (2, 3)  # reference model.py:304-313
+        self.use_encoder_features_for_dpt = len(self.info_sharing.indices) == 2
 
         d = self.info_sharing.dim
         ph = pred_head_config
         ph["feature_head"]["patch_size"] = self.encoder.patch_size
-        ph["feature_head"]["input_feature_dims"] = [c] + [d] * 3
+        ph["feature_head"]["input_feature_dims"] = [c] + [d] * 3 if self.use_encoder_features_for_dpt else [d] * 4
         ph["regressor_head"]["input_feature_dim"] = ph["feature_head"]["feature_dim"]
         ph["pose_head"]["patch_size"] = self.encoder.patch_size
         ph["pose_head"]["input_feature_dim"] = d
@@ -232,7 +232,10 @@ class MapAnythingOracle(nn.Module):
         final_feats = [f.float() for f in final_feats]
         final_extra = final_extra.float()
         inter = [([f.float() for f in fs], ex) for fs, ex in inter]
-        dpt_in = [torch.cat(fused, 0), torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(final_feats, 0)]
+        if self.use_encoder_features_for_dpt:  # reference model.py:1549-1572
+            dpt_in = [torch.cat(fused, 0), torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(final_feats, 0)]
+        else:
+            dpt_in = [torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(inter[2][0], 0), torch.cat(final_feats, 0)]
 
         n = dpt_in[0].shape[0]
         chunk = 2 if memory_efficient_inference else n

@@ -70,3 +70,26 @@ def test_no_cpu_fallback():
     views = [{"img": torch.randn(1, 3, 70, 70), "data_norm_type": ["dinov2"]} for _ in range(2)]
     with pytest.raises(RuntimeError, match="no CPU path"):
         model(views)
+
+
+def test_info_sharing_variants_construct_with_reference_key_layout():
+    """3 tap indices (aat_ifr_48_layers*.yaml wiring, reference model.py:304-313) and no_ref_view: the parameter container
+    builds on the CPU with the oracle's state-dict keys; unsupported variants raise the reference's ValueError."""
+    import pytest
+
+    from mapanything_b200 import MapAnything, tiny_config
+    from mapanything_b200.config import mapanything_variant_config
+    from oracle.config import tiny_config as oracle_tiny
+    from oracle.model import MapAnythingOracle
+
+    kw = dict(info_depth=6, indices=(1, 3, 4))
+    m, o = MapAnything(**tiny_config(**kw)), MapAnythingOracle(**oracle_tiny(**kw))
+    assert not m.use_encoder_features_for_dpt and set(m.state_dict()) == set(o.state_dict())
+    with pytest.raises(ValueError, match="Please provide 2 or 3 indices"):
+        MapAnything(**tiny_config(info_depth=6, indices=(1, 2, 3, 4)))
+    cfg = mapanything_variant_config("aat_ifr_48_layers_no_ref_view")
+    ma = cfg["info_sharing_config"]["module_args"]
+    assert (ma["depth"], ma["dim"], ma["num_heads"], ma["indices"]) == (48, 1024, 16, [11, 23, 35])
+    assert ma["distinguish_ref_and_non_ref_views"] is False
+    with pytest.raises(ValueError, match="info_sharing must be one of"):
+        mapanything_variant_config("gat_ifr_24_layers")

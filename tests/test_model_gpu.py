@@ -157,6 +157,34 @@ def test_forward_tiny_reference_style_init_stated_tolerance():
     _assert_within(_metrics(got, ref), "tiny, reference-style init, V=4")
 
 
+@pytest.mark.parametrize("variant", ["three_taps", "no_ref_view", "three_taps_wide"])
+def test_forward_tiny_info_sharing_variants(variant):
+    """Other released info-sharing wirings (reference configs/model/info_sharing/aat_ifr_48_layers*.yaml, *_no_ref_view.yaml):
+    3 tap indices -> the DPT takes three intermediate taps + the final features and NOT the encoder features
+    (model.py:304-313, :1549-1600); distinguish_ref_and_non_ref_views=False -> no reference-view embedding; info-sharing
+    width different from the encoder width with 4 heads of 64."""
+    from oracle.config import tiny_config
+
+    def cfg():
+        if variant == "three_taps":
+            c = tiny_config(info_depth=6, indices=(1, 3, 4))
+        elif variant == "three_taps_wide":
+            c = tiny_config(info_depth=4, indices=(0, 1, 2), info_dim=256, info_heads=4)
+        else:
+            c = tiny_config()
+            c["info_sharing_config"]["module_args"]["distinguish_ref_and_non_ref_views"] = False
+        return c
+
+    oracle, model = _build(cfg, seed=2, init="reference")
+    assert model.use_encoder_features_for_dpt == (variant == "no_ref_view")
+    assert set(model.state_dict().keys()) == set(oracle.state_dict().keys())
+    views = _views(3, 70, seed=13)
+    with torch.no_grad():
+        ref = oracle([dict(v) for v in views])
+    got = model([{**v, "img": v["img"].cuda()} for v in views])
+    _assert_within(_metrics(got, ref), f"tiny, {variant}, V=3")
+
+
 HARD_KEYS = ("depth_rel_median", "depth_rel_p99", "pts_rel_p99", "rot_deg", "scale_rel", "trans_rel", "logit_abs")
 
 
