@@ -81,54 +81,53 @@ __global__ void resample_h_kernel(const uint8_t* __restrict__ src, int64_t row_s
   }
 }
 
-// Strip form of the horizontal pass (the default): a block stages `rpb` consecutive source rows of frame blockIdx.y in
-// shared memory; a thread owns output COLUMNS (xx = x0 + threadIdx.x, + blockDim.x, ...) and keeps that column's window
-// coefficients in registers while it walks down the strip, so the inner loop is nothing but byte loads from shared memory
-// and integer multiply-adds (KMAX taps fully unrolled, absent taps carry a zero coefficient; the staged rows are padded so
-// that their reads stay inside the block's shared memory).  The one-row kernel above re-read every coefficient from
-// global memory for every row and was bound by instruction issue at 12 % of the HBM roofline.
+// Word-load form of the horizontal pass (the default).  Same block <-> source row mapping as resample_h_kernel, but a
+// thread fetches its whole window (3 * KMAX bytes at an arbitrary byte offset of the staged row) with 32-bit shared-memory
+// loads, realigns it with funnel shifts and picks the bytes with PRMT: 3*KMAX/4 + 1 shared-memory instructions per output
+// pixel instead of 3 * taps byte loads.  The byte loads were the bound of the first kernel: neighbouring lanes read
+// windows ~11 bytes apart, every LDS.U8 is a 3-way bank conflict, and the shared-memory pipe -- not HBM, not the integer
+// pipe -- set the time (14.8 us per 1920x1080 frame, 12 % of the HBM roofline).  A "strip" variant that kept the window
+// coefficients in registers over 8 staged rows was measured SLOWER (23.9 us: same byte loads, half the occupancy).
+// Absent taps (t >= cnt) carry a zero coefficient; the staged row is padded so their bytes are inside the block's smem.
 template <int KMAX>
 __global__ void __launch_bounds__(256)
-resample_h_strip_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int y0, int rows, int rpb,
-                        int sx0, int sx1, const int32_t* __restrict__ bounds, const int32_t* __restrict__ coeffs, int out_size,
-                        int x0, int cols, uint8_t* __restrict__ tmp, int pitch) {
+resample_h_vec_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int y0, int sx0, int sx1,
+                      const int32_t* __restrict__ bounds, const int32_t* __restrict__ coeffs, int out_size, int x0, int cols,
+                      uint8_t* __restrict__ tmp) {
+  constexpr int NW = (3 * KMAX + 3) / 4;  // words holding the realigned window
   extern __shared__ __align__(16) uint8_t srow[];
+  const uint8_t* row = src + blockIdx.y * frame_stride + (y0 + static_cast<int64_t>(blockIdx.x)) * row_stride +
+                       static_cast<int64_t>(sx0) * 3;
   const int nbytes = (sx1 - sx0) * 3;
-  const int r0 = blockIdx.x * rpb;
-  const int nr = min(rpb, rows - r0);
-  const uint8_t* base = src + blockIdx.y * frame_stride + (y0 + static_cast<int64_t>(r0)) * row_stride + static_cast<int64_t>(sx0) * 3;
-  for (int r = 0; r < nr; ++r) {
-    const uint8_t* row = base + r * row_stride;
-    const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
-    const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row - mis);
-    const int nwords = (mis + nbytes + 3) >> 2;
-    uint32_t* s4 = reinterpret_cast<uint32_t*>(srow + r * pitch);
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) s4[i] = __ldg(row4 + i);
-  }
+  const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
+  const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row - mis);
+  const int nwords = (mis + nbytes + 3) >> 2;
+  uint32_t* s4 = reinterpret_cast<uint32_t*>(srow);
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) s4[i] = __ldg(row4 + i);
   __syncthreads();
-  const int mis0 = static_cast<int>(reinterpret_cast<uintptr_t>(base) & 3);
-  const int dmis = static_cast<int>(row_stride & 3);  // misalignment advances by this much per row (mod 4)
+  uint8_t* orow = tmp + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * cols * 3;
   for (int i = threadIdx.x; i < cols; i += blockDim.x) {
     const int xx = x0 + i;
     const int first = bounds[2 * xx], cnt = bounds[2 * xx + 1];
-    int k[KMAX];
+    const int off = mis + (first - sx0) * 3;
+    const uint32_t* w4 = s4 + (off >> 2);
+    const int sh = (off & 3) * 8;
+    uint32_t w[NW + 1];
 #pragma unroll
-    for (int t = 0; t < KMAX; ++t) k[t] = t < cnt ? __ldg(coeffs + static_cast<int64_t>(t) * out_size + xx) : 0;
-    const int off = (first - sx0) * 3;
-    uint8_t* o = tmp + ((static_cast<int64_t>(blockIdx.y) * rows + r0) * cols + i) * 3;
-    for (int r = 0; r < nr; ++r, o += static_cast<int64_t>(cols) * 3) {
-      const uint8_t* p = srow + r * pitch + ((mis0 + r * dmis) & 3) + off;
-      int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+    for (int j = 0; j <= NW; ++j) w[j] = w4[j];
 #pragma unroll
-      for (int t = 0; t < KMAX; ++t) {
-        a0 += p[3 * t] * k[t];
-        a1 += p[3 * t + 1] * k[t];
-        a2 += p[3 * t + 2] * k[t];
-      }
-      o[0] = clip8(a0);
-      o[1] = clip8(a1);
-      o[2] = clip8(a2);
+    for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh);  // window byte b is now byte (b & 3) of w[b >> 2]
+    int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+      const int k = t < cnt ? __ldg(coeffs + static_cast<int64_t>(t) * out_size + xx) : 0;
+      a0 += static_cast<int>(__byte_perm(w[(3 * t) >> 2], 0, 0x4440 | ((3 * t) & 3))) * k;
+      a1 += static_cast<int>(__byte_perm(w[(3 * t + 1) >> 2], 0, 0x4440 | ((3 * t + 1) & 3))) * k;
+      a2 += static_cast<int>(__byte_perm(w[(3 * t + 2) >> 2], 0, 0x4440 | ((3 * t + 2) & 3))) * k;
     }
+    orow[3 * i] = clip8(a0);
+    orow[3 * i + 1] = clip8(a1);
+    orow[3 * i + 2] = clip8(a2);
   }
 }
 
@@ -261,22 +260,18 @@ extern "C" int ma_resample_coeffs(int in_size, int out_size, int filter, int* ks
 }
 
 template <int KMAX>
-static int launch_h_strip(const uint8_t* src, int64_t row_stride, int64_t frame_stride, int n, int y0, int rows, int sx0, int sx1,
-                          const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols, uint8_t* tmp,
-                          cudaStream_t stream) {
-  const int pitch = ((sx1 - sx0) * 3 + 3 + KMAX * 3 + 3 + 15) & ~15;
-  int rpb = (96 * 1024) / pitch;  // rows per block: coefficient loads amortised, >= 2 blocks per SM
-  rpb = rpb > 8 ? 8 : rpb;
-  if (rpb < 1) return MA_ERR_INVALID;
-  const size_t smem = static_cast<size_t>(rpb) * pitch;
+static int launch_h_vec(const uint8_t* src, int64_t row_stride, int64_t frame_stride, int n, int y0, int rows, int sx0, int sx1,
+                        const int32_t* bounds, const int32_t* coeffs, int out_size, int x0, int cols, uint8_t* tmp,
+                        cudaStream_t stream) {
+  // staged row + misalignment + the zero-coefficient taps' bytes + the funnel shift's extra word
+  const size_t smem = (static_cast<size_t>(sx1 - sx0) * 3 + 3 + 3 * KMAX + 8 + 15) & ~static_cast<size_t>(15);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_strip_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = 100 * 1024;
+    MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_vec_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
   }
-  dim3 grid((rows + rpb - 1) / rpb, n);
-  resample_h_strip_kernel<KMAX><<<grid, 256, smem, stream>>>(src, row_stride, frame_stride, y0, rows, rpb, sx0, sx1, bounds, coeffs,
-                                                             out_size, x0, cols, tmp, pitch);
+  resample_h_vec_kernel<KMAX><<<dim3(rows, n), 256, smem, stream>>>(src, row_stride, frame_stride, y0, sx0, sx1, bounds, coeffs,
+                                                                    out_size, x0, cols, tmp);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
@@ -288,19 +283,19 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
                  x0 + cols <= out_size && ksize > 0,
              "ma_resample_h_u8rgb: bad arguments (n=%d rows=%d cols=%d ksize=%d)", n, rows, cols, ksize);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const bool one_row = [] {  // MA_RESAMPLE_ONE_ROW=1: the first (one block per row) kernel, kept for A/B runs
-    const char* e = getenv("MA_RESAMPLE_ONE_ROW");
+  static const bool byte_loads = [] {  // MA_RESAMPLE_BYTE_LOADS=1: the first kernel (byte loads, any window length), for A/B runs
+    const char* e = getenv("MA_RESAMPLE_BYTE_LOADS");
     return e && e[0] == '1';
   }();
   const int64_t row_bytes = static_cast<int64_t>(sx1 - sx0) * 3;
-  if (!one_row && ksize <= 64 && row_bytes + 256 <= 96 * 1024) {
-#define MA_H_STRIP(K) \
-  return launch_h_strip<K>(src, src_row_stride, src_frame_stride, n, y0, rows, sx0, sx1, bounds, coeffs, out_size, x0, cols, tmp, st)
-    if (ksize <= 8) MA_H_STRIP(8);
-    if (ksize <= 16) MA_H_STRIP(16);
-    if (ksize <= 32) MA_H_STRIP(32);
-    MA_H_STRIP(64);
-#undef MA_H_STRIP
+  if (!byte_loads && ksize <= 64 && row_bytes + 512 <= 200 * 1024) {
+#define MA_H_VEC(K) \
+  return launch_h_vec<K>(src, src_row_stride, src_frame_stride, n, y0, rows, sx0, sx1, bounds, coeffs, out_size, x0, cols, tmp, st)
+    if (ksize <= 8) MA_H_VEC(8);
+    if (ksize <= 16) MA_H_VEC(16);
+    if (ksize <= 32) MA_H_VEC(32);
+    MA_H_VEC(64);
+#undef MA_H_VEC
   }
   const size_t smem = static_cast<size_t>(row_bytes) + 8;
   MA_REQUIRE(smem <= 200 * 1024, "ma_resample_h_u8rgb: source rows of %d pixels do not fit shared memory", sx1 - sx0);
