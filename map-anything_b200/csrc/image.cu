@@ -290,11 +290,13 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
   const int64_t row_bytes = static_cast<int64_t>(sx1 - sx0) * 3;
   if (!byte_loads && ksize <= 64 && row_bytes + 512 <= 200 * 1024) {
 #define MA_H_VEC(K) \
-  return launch_h_vec<K>(src, src_row_stride, src_frame_stride, n, y0, rows, sx0, sx1, bounds, coeffs, out_size, x0, cols, tmp, st)
-    if (ksize <= 8) MA_H_VEC(8);
-    if (ksize <= 16) MA_H_VEC(16);
-    if (ksize <= 32) MA_H_VEC(32);
-    MA_H_VEC(64);
+  case K / 4:       \
+    return launch_h_vec<K>(src, src_row_stride, src_frame_stride, n, y0, rows, sx0, sx1, bounds, coeffs, out_size, x0, cols, tmp, st)
+    switch ((ksize + 3) / 4) {  // unrolled tap count = the window length rounded up to a multiple of 4
+      MA_H_VEC(4); MA_H_VEC(8); MA_H_VEC(12); MA_H_VEC(16); MA_H_VEC(20); MA_H_VEC(24); MA_H_VEC(28); MA_H_VEC(32);
+      MA_H_VEC(36); MA_H_VEC(40); MA_H_VEC(44); MA_H_VEC(48); MA_H_VEC(52); MA_H_VEC(56); MA_H_VEC(60); MA_H_VEC(64);
+      default: break;
+    }
 #undef MA_H_VEC
   }
   const size_t smem = static_cast<size_t>(row_bytes) + 8;
