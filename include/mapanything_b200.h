@@ -268,11 +268,16 @@ int ma_resample_coeffs(int in_size, int out_size, int filter, int* ksize_out, in
 
 /* Horizontal pass over n frames of the same size.  src: device u8 RGB, interleaved; row / frame strides in bytes;
  * source rows [y0, y0+rows) and source columns [sx0, sx1) are read (sx0/sx1 = the window span of output columns
- * [x0, x0+cols)); bounds / coeffs: device copies of the tables for the horizontal axis (ksize taps, out_size columns).
+ * [x0, x0+cols)); bounds / coeffs: device copies of the tables for the horizontal axis (ksize taps, out_size columns); packed: optional, see ma_resample_pack_coeffs.
  * tmp: device u8 [n][rows][cols][3]. */
 int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int64_t src_frame_stride, int n, int y0, int rows,
-                        int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, int ksize, int out_size, int x0,
-                        int cols, uint8_t* tmp, void* stream);
+                        int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, const uint32_t* packed, int ksize,
+                        int out_size, int x0, int cols, uint8_t* tmp, void* stream);
+
+/* HOST function: the coefficients of ma_resample_coeffs split into bytes for the dp4a form of the horizontal pass.
+ * packed: uint32 [3][ceil(ksize/4)][out_size]; plane 0 / 1 = bits 0-7 / 8-15 (unsigned), plane 2 = bits 16-23 (signed);
+ * each word holds 4 consecutive taps.  Pass its device copy as `packed` above (NULL: plain 32-bit coefficients). */
+int ma_resample_pack_coeffs(const int32_t* coeffs, int ksize, int out_size, uint32_t* packed);
 
 /* Vertical pass + crop + normalise.  tmp: [n][rows][cols][3] u8 whose row 0 is source row y0; output rows
  * [top, top+th) of the resampled image (out_size rows).  out_chw: fp32 (n, 3, th, cols) = ((u/255) - mean) / std in

@@ -131,6 +131,80 @@ resample_h_vec_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64
   }
 }
 
+// dp4a form of the horizontal pass (used when the caller supplies byte-packed coefficients, ma_resample_pack_coeffs).
+// While a row is staged, R, G and B are separated into three byte planes (12 bytes = 4 pixels per thread step: 4 aligned
+// word loads, funnel shift, 6 PRMT, 3 word stores), so 4 consecutive taps of ONE channel sit in one 32-bit word.  The 22-bit
+// signed coefficient k = k0 + 2^8 k1 + 2^16 k2 (k0, k1 unsigned bytes, k2 a signed byte) is applied as three dp4a per word:
+// 3 integer instructions per 4 taps instead of 4 byte extractions + 4 multiply-adds; the three partial sums recombine
+// exactly (two's-complement adds; the true accumulator fits 32 bits as it does in Pillow).
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {  // a: 4 unsigned bytes, b: 4 SIGNED bytes
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int NW4>  // 32-bit words per channel window = ceil(window length / 4)
+__global__ void __launch_bounds__(256)
+resample_h_dp4a_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int64_t frame_stride, int y0, int sx0, int sx1,
+                       const int32_t* __restrict__ bounds, const uint32_t* __restrict__ packed, int out_size, int x0, int cols,
+                       uint8_t* __restrict__ tmp, int plane_words) {
+  extern __shared__ __align__(16) uint8_t srow[];
+  uint32_t* plane = reinterpret_cast<uint32_t*>(srow);  // [3][plane_words]
+  const uint8_t* row = src + blockIdx.y * frame_stride + (y0 + static_cast<int64_t>(blockIdx.x)) * row_stride +
+                       static_cast<int64_t>(sx0) * 3;
+  const int npx = sx1 - sx0;
+  const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(row) & 3);
+  const uint32_t* row4 = reinterpret_cast<const uint32_t*>(row - mis);
+  const int last_word = (mis + npx * 3 - 1) >> 2;  // last word holding a wanted byte: nothing beyond it is read
+  const int sh0 = mis * 8;
+  for (int g = threadIdx.x; g * 4 < npx; g += blockDim.x) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = __ldg(row4 + min(3 * g + j, last_word));
+    const uint32_t b0 = __funnelshift_r(w[0], w[1], sh0);  // R0 G0 B0 R1
+    const uint32_t b1 = __funnelshift_r(w[1], w[2], sh0);  // G1 B1 R2 G2
+    const uint32_t b2 = __funnelshift_r(w[2], w[3], sh0);  // B2 R3 G3 B3
+    plane[g] = __byte_perm(__byte_perm(b0, b1, 0x0630), b2, 0x5210);
+    plane[plane_words + g] = __byte_perm(__byte_perm(b0, b1, 0x0741), b2, 0x6210);
+    plane[2 * plane_words + g] = __byte_perm(__byte_perm(b0, b1, 0x0052), b2, 0x7410);
+  }
+  __syncthreads();
+  uint8_t* orow = tmp + (static_cast<int64_t>(blockIdx.y) * gridDim.x + blockIdx.x) * cols * 3;
+  const int64_t pstride = static_cast<int64_t>(NW4) * out_size;  // words per coefficient byte plane
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) {
+    const int xx = x0 + i;
+    const int po = bounds[2 * xx] - sx0;  // first window pixel, relative to the staged span
+    const uint32_t* wp = plane + (po >> 2);
+    const int sh = (po & 3) * 8;
+    uint32_t k0[NW4], k1[NW4], k2[NW4];
+#pragma unroll
+    for (int j = 0; j < NW4; ++j) {
+      k0[j] = __ldg(packed + static_cast<int64_t>(j) * out_size + xx);
+      k1[j] = __ldg(packed + pstride + static_cast<int64_t>(j) * out_size + xx);
+      k2[j] = __ldg(packed + 2 * pstride + static_cast<int64_t>(j) * out_size + xx);
+    }
+    int acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uint32_t w[NW4 + 1];
+#pragma unroll
+      for (int j = 0; j <= NW4; ++j) w[j] = wp[c * plane_words + j];
+      int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+      for (int j = 0; j < NW4; ++j) {
+        const uint32_t px = __funnelshift_r(w[j], w[j + 1], sh);
+        s0 = static_cast<int>(__dp4a(px, k0[j], static_cast<uint32_t>(s0)));
+        s1 = static_cast<int>(__dp4a(px, k1[j], static_cast<uint32_t>(s1)));
+        s2 = dp4a_us(px, k2[j], s2);
+      }
+      acc[c] = (1 << (RS_PRECISION_BITS - 1)) + s0 + s1 * 256 + s2 * 65536;
+    }
+    orow[3 * i] = clip8(acc[0]);
+    orow[3 * i + 1] = clip8(acc[1]);
+    orow[3 * i + 2] = clip8(acc[2]);
+  }
+}
+
 // Thread per output pixel (x, yy = top + blockIdx.y) of the cropped target of frame blockIdx.z.
 __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows, int cols, int y0, const int32_t* __restrict__ bounds,
                                        const int32_t* __restrict__ coeffs, int out_size, int top, int th, float m0, float m1,
@@ -276,9 +350,47 @@ static int launch_h_vec(const uint8_t* src, int64_t row_stride, int64_t frame_st
   return MA_OK;
 }
 
+template <int NW4>
+static int launch_h_dp4a(const uint8_t* src, int64_t row_stride, int64_t frame_stride, int n, int y0, int rows, int sx0, int sx1,
+                         const int32_t* bounds, const uint32_t* packed, int out_size, int x0, int cols, uint8_t* tmp,
+                         cudaStream_t stream) {
+  // per plane: the staged pixels + the window overhang of the last output (zero coefficients) + the funnel shift's word
+  const int plane_words = ((sx1 - sx0 + 3) >> 2) + NW4 + 2;
+  const size_t smem = static_cast<size_t>(3) * plane_words * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_dp4a_kernel<NW4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  resample_h_dp4a_kernel<NW4><<<dim3(rows, n), 256, smem, stream>>>(src, row_stride, frame_stride, y0, sx0, sx1, bounds, packed,
+                                                                    out_size, x0, cols, tmp, plane_words);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_resample_pack_coeffs(const int32_t* coeffs, int ksize, int out_size, uint32_t* packed) {
+  MA_REQUIRE(coeffs && packed && ksize > 0 && out_size > 0, "ma_resample_pack_coeffs: bad arguments");
+  const int nw = (ksize + 3) / 4;
+  for (int p = 0; p < 3; ++p)
+    for (int j = 0; j < nw; ++j)
+      for (int xx = 0; xx < out_size; ++xx) {
+        uint32_t word = 0;
+        for (int b = 0; b < 4; ++b) {
+          const int t = 4 * j + b;
+          const int32_t k = t < ksize ? coeffs[static_cast<int64_t>(t) * out_size + xx] : 0;
+          const int32_t hi = k >> 16;  // arithmetic shift: k = (k & 255) + 256 * ((k >> 8) & 255) + 65536 * hi
+          MA_REQUIRE(hi >= -128 && hi <= 127, "ma_resample_pack_coeffs: coefficient %d does not fit 24 signed bits", k);
+          const uint32_t byte = p == 0 ? (k & 255) : p == 1 ? ((k >> 8) & 255) : (static_cast<uint32_t>(hi) & 255u);
+          word |= byte << (8 * b);
+        }
+        packed[(static_cast<int64_t>(p) * nw + j) * out_size + xx] = word;
+      }
+  return MA_OK;
+}
+
 extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int64_t src_frame_stride, int n, int y0, int rows,
-                                   int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, int ksize, int out_size,
-                                   int x0, int cols, uint8_t* tmp, void* stream) {
+                                   int sx0, int sx1, const int32_t* bounds, const int32_t* coeffs, const uint32_t* packed,
+                                   int ksize, int out_size, int x0, int cols, uint8_t* tmp, void* stream) {
   MA_REQUIRE(src && bounds && coeffs && tmp && n > 0 && n <= 65535 && rows > 0 && cols > 0 && sx1 > sx0 && x0 >= 0 &&
                  x0 + cols <= out_size && ksize > 0,
              "ma_resample_h_u8rgb: bad arguments (n=%d rows=%d cols=%d ksize=%d)", n, rows, cols, ksize);
@@ -288,6 +400,21 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
     return e && e[0] == '1';
   }();
   const int64_t row_bytes = static_cast<int64_t>(sx1 - sx0) * 3;
+  static const bool no_dp4a = [] {  // MA_RESAMPLE_DP4A=0: ignore the packed coefficients (A/B runs)
+    const char* e = getenv("MA_RESAMPLE_DP4A");
+    return e && e[0] == '0';
+  }();
+  if (packed && !no_dp4a && !byte_loads && ksize <= 64 && row_bytes + 1024 <= 180 * 1024) {
+#define MA_H_DP4A(W) \
+  case W:            \
+    return launch_h_dp4a<W>(src, src_row_stride, src_frame_stride, n, y0, rows, sx0, sx1, bounds, packed, out_size, x0, cols, tmp, st)
+    switch ((ksize + 3) / 4) {
+      MA_H_DP4A(1); MA_H_DP4A(2); MA_H_DP4A(3); MA_H_DP4A(4); MA_H_DP4A(5); MA_H_DP4A(6); MA_H_DP4A(7); MA_H_DP4A(8);
+      MA_H_DP4A(9); MA_H_DP4A(10); MA_H_DP4A(11); MA_H_DP4A(12); MA_H_DP4A(13); MA_H_DP4A(14); MA_H_DP4A(15); MA_H_DP4A(16);
+      default: break;
+    }
+#undef MA_H_DP4A
+  }
   if (!byte_loads && ksize <= 64 && row_bytes + 512 <= 200 * 1024) {
 #define MA_H_VEC(K) \
   case K / 4:       \

@@ -55,7 +55,7 @@ def find_closest_aspect_ratio(aspect_ratio: float, resolution_set: int) -> Tuple
 class _AxisTables:
     """Pillow's resampling windows of one axis (in_size -> out_size): host bounds for planning, device copies for the kernels."""
 
-    __slots__ = ("bounds", "d_bounds", "d_coeffs", "out_size")
+    __slots__ = ("bounds", "d_bounds", "d_coeffs", "d_packed", "out_size")
 
     def __init__(self, in_size: int, out_size: int, filt: int, device: torch.device):
         lib = _lib.load()
@@ -65,8 +65,11 @@ class _AxisTables:
         coeffs = np.empty((ks.value, out_size), np.int32)
         check(lib.ma_resample_coeffs(in_size, out_size, filt, C.byref(ks), self.bounds.ctypes.data, coeffs.ctypes.data),
               "ma_resample_coeffs")
+        packed = np.empty((3, (ks.value + 3) // 4, out_size), np.uint32)   # byte-split coefficients for the dp4a kernel
+        check(lib.ma_resample_pack_coeffs(coeffs.ctypes.data, ks.value, out_size, packed.ctypes.data), "ma_resample_pack_coeffs")
         self.d_bounds = torch.from_numpy(self.bounds).to(device)
         self.d_coeffs = torch.from_numpy(coeffs).to(device)
+        self.d_packed = torch.from_numpy(packed.view(np.int32)).to(device)
         self.out_size = out_size
 
 
@@ -123,7 +126,8 @@ def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_ty
     stream = torch.cuda.current_stream().cuda_stream
     tmp = torch.empty(n, y1 - y0, tw, 3, device=dev, dtype=torch.uint8)
     check(lib.ma_resample_h_u8rgb(img_u8.data_ptr(), img_u8.stride(1), img_u8.stride(0), n, y0, y1 - y0, sx0, sx1,
-                                  th_.d_bounds.data_ptr(), th_.d_coeffs.data_ptr(), th_.d_coeffs.shape[0], rw, left, tw,
+                                  th_.d_bounds.data_ptr(), th_.d_coeffs.data_ptr(), th_.d_packed.data_ptr(),
+                                  th_.d_coeffs.shape[0], rw, left, tw,
                                   tmp.data_ptr(), stream),
           "ma_resample_h_u8rgb")
     out = out8 = None

@@ -194,3 +194,23 @@ def test_preprocess_inputs_validation_errors_need_no_gpu():
         preprocess_inputs([{"img": np.zeros((4, 4), np.uint8)}])
     with pytest.raises(ValueError, match="Unsupported image type"):
         preprocess_inputs([{"img": "file.png"}])
+
+
+@pytest.mark.parametrize("i,o,filt", [(1920, 522, 1), (4032, 522, 1), (97, 140, 3), (64, 64, 1)])
+def test_cabi_pack_coeffs_host(i, o, filt):
+    """ma_resample_pack_coeffs (host): the byte planes recombine to the 22-bit coefficients; 4 taps per word, zero padded."""
+    lib = _lib()
+    ks = C.c_int(0)
+    assert lib.ma_resample_coeffs(i, o, filt, C.byref(ks), None, None) == 0
+    bounds = np.zeros((o, 2), np.int32)
+    coeffs = np.zeros((ks.value, o), np.int32)
+    assert lib.ma_resample_coeffs(i, o, filt, C.byref(ks), bounds.ctypes.data, coeffs.ctypes.data) == 0
+    nw = (ks.value + 3) // 4
+    packed = np.zeros((3, nw, o), np.uint32)
+    assert lib.ma_resample_pack_coeffs(coeffs.ctypes.data, ks.value, o, packed.ctypes.data) == 0
+    b = packed.view(np.uint8).reshape(3, nw, o, 4)                      # little endian: byte b of a word = tap 4j + b
+    taps = b.transpose(0, 1, 3, 2).reshape(3, nw * 4, o).astype(np.int64)
+    k = taps[0] + 256 * taps[1] + 65536 * taps[2].astype(np.uint8).view(np.int8).astype(np.int64).reshape(taps[2].shape)
+    assert np.array_equal(k[:ks.value], coeffs) and not k[ks.value:].any()
+    big = np.full((1, 1), 1 << 24, np.int32)
+    assert lib.ma_resample_pack_coeffs(big.ctypes.data, 1, 1, packed.ctypes.data) != 0
