@@ -280,10 +280,10 @@ int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, int64_t src_
 int ma_resample_pack_coeffs(const int32_t* coeffs, int ksize, int out_size, uint32_t* packed);
 
 /* Vertical pass + crop + normalise.  tmp: [n][rows][cols][3] u8 whose row 0 is source row y0; output rows
- * [top, top+th) of the resampled image (out_size rows).  out_chw: fp32 (n, 3, th, cols) = ((u/255) - mean) / std in
+ * [top, top+th) of the resampled image (out_size rows; bounds / coeffs: the vertical axis' tables, ksize taps).  out_chw: fp32 (n, 3, th, cols) = ((u/255) - mean) / std in
  * torchvision's rounding order (mean / std: 3 HOST floats), may be NULL; out_u8: u8 [n][th][cols][3], may be NULL. */
 int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int n, int rows, int cols, int y0, const int32_t* bounds,
-                             const int32_t* coeffs, int out_size, int top, int th, const float* mean_host,
+                             const int32_t* coeffs, int ksize, int out_size, int top, int th, const float* mean_host,
                              const float* std_host, float* out_chw, uint8_t* out_u8, void* stream);
 
 /* preprocess_inputs() (image.py:335-675) resizes depth maps with cv2.resize(INTER_NEAREST) and slices the crop

@@ -206,6 +206,10 @@ resample_h_dp4a_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int6
 }
 
 // Thread per output pixel (x, yy = top + blockIdx.y) of the cropped target of frame blockIdx.z.
+// KMAX > 0: the tap loop is fully unrolled to KMAX taps (window length rounded up to 4; absent taps re-read the last valid
+// row with a zero coefficient), so all 3 * KMAX byte loads of a pixel are in flight together -- the rolled loop (KMAX = 0,
+// any window length) was bound by the latency of its dependent global loads (ncu: 17 long-scoreboard stalls per issue).
+template <int KMAX>
 __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows, int cols, int y0, const int32_t* __restrict__ bounds,
                                        const int32_t* __restrict__ coeffs, int out_size, int top, int th, float m0, float m1,
                                        float m2, float s0, float s1, float s2, float* __restrict__ out_chw,
@@ -218,11 +222,22 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows
   int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
   const uint8_t* p = tmp + ((static_cast<int64_t>(blockIdx.z) * rows + (first - y0)) * cols + x) * 3;
   const int64_t rs = static_cast<int64_t>(cols) * 3;
-  for (int t = 0; t < cnt; ++t, p += rs) {
-    const int k = __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy);  // warp-uniform
-    a0 += p[0] * k;
-    a1 += p[1] * k;
-    a2 += p[2] * k;
+  if constexpr (KMAX == 0) {
+    for (int t = 0; t < cnt; ++t, p += rs) {
+      const int k = __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy);  // warp-uniform
+      a0 += p[0] * k;
+      a1 += p[1] * k;
+      a2 += p[2] * k;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < KMAX; ++t) {
+      const int k = t < cnt ? __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy) : 0;
+      const uint8_t* q = p + (t < cnt ? t : cnt - 1) * rs;
+      a0 += q[0] * k;
+      a1 += q[1] * k;
+      a2 += q[2] * k;
+    }
   }
   const uint8_t u0 = clip8(a0), u1 = clip8(a1), u2 = clip8(a2);
   if (out_u8) {
@@ -442,17 +457,33 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
 }
 
 extern "C" int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int n, int rows, int cols, int y0, const int32_t* bounds,
-                                        const int32_t* coeffs, int out_size, int top, int th, const float* mean_host,
+                                        const int32_t* coeffs, int ksize, int out_size, int top, int th, const float* mean_host,
                                         const float* std_host, float* out_chw, uint8_t* out_u8, void* stream) {
-  MA_REQUIRE(tmp && bounds && coeffs && n > 0 && n <= 65535 && rows > 0 && cols > 0 && th > 0 && top >= 0 && top + th <= out_size &&
-                 (out_chw || out_u8),
+  MA_REQUIRE(tmp && bounds && coeffs && ksize > 0 && n > 0 && n <= 65535 && rows > 0 && cols > 0 && th > 0 && top >= 0 &&
+                 top + th <= out_size && (out_chw || out_u8),
              "ma_resample_v_norm_u8rgb: bad arguments (n=%d cols=%d th=%d)", n, cols, th);
   MA_REQUIRE(!out_chw || (mean_host && std_host), "ma_resample_v_norm_u8rgb: mean / std missing");
   const float m0 = mean_host ? mean_host[0] : 0.f, m1 = mean_host ? mean_host[1] : 0.f, m2 = mean_host ? mean_host[2] : 0.f;
   const float s0 = std_host ? std_host[0] : 1.f, s1 = std_host ? std_host[1] : 1.f, s2 = std_host ? std_host[2] : 1.f;
   dim3 grid((cols + 127) / 128, th, n);
-  resample_v_norm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th,
-                                                                             m0, m1, m2, s0, s1, s2, out_chw, out_u8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static const bool rolled = [] {  // MA_RESAMPLE_V_ROLLED=1: the rolled tap loop for every window length (A/B runs)
+    const char* e = getenv("MA_RESAMPLE_V_ROLLED");
+    return e && e[0] == '1';
+  }();
+#define MA_V(K)                                                                                                            \
+  case K / 4:                                                                                                              \
+    resample_v_norm_kernel<K><<<grid, 128, 0, st>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th, m0, m1, m2, s0, s1, \
+                                                    s2, out_chw, out_u8);                                                  \
+    break
+  switch (rolled || ksize > 64 ? 0 : (ksize + 3) / 4) {
+    MA_V(4); MA_V(8); MA_V(12); MA_V(16); MA_V(20); MA_V(24); MA_V(28); MA_V(32);
+    MA_V(36); MA_V(40); MA_V(44); MA_V(48); MA_V(52); MA_V(56); MA_V(60); MA_V(64);
+    default:
+      resample_v_norm_kernel<0><<<grid, 128, 0, st>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th, m0, m1, m2, s0, s1, s2,
+                                                      out_chw, out_u8);
+  }
+#undef MA_V
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

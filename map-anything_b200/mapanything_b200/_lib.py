@@ -108,7 +108,7 @@ SIGNATURES = {
     "ma_resample_pack_coeffs": (_i, [_p, _i, _i, _p]),
     "ma_gather_rows_cols_f32": (_i, [_p, _i64, _p, _p, _i, _i, _p, _p]),
     "ma_f32_to_u8": (_i, [_p, _i64, _f, _p, _p]),
-    "ma_resample_v_norm_u8rgb": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "ma_resample_v_norm_u8rgb": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

@@ -244,7 +244,9 @@ class Engine:
         # tail-wave splitting of long attention: implemented and tested, but A/B runs on B200 (8 views, same box, same
         # call) show no gain (26.8 / 27.0 ms without vs 27.1 / 27.3 ms with it) -> off unless MA_ATTN_KV_SPLIT=1
         self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "0") == "1"
-        self.dpt_chunk = 4  # views per DPT pass (bounds the im2col scratch: ~0.62 GB per view at 518 px)
+        # views per DPT pass (bounds the activation scratch: ~0.6 GB per view at 518 px); MA_DPT_CHUNK overrides for A/B runs
+        self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "4")))
+        self.dpt_chunk = self.dpt_chunk_default
 
     # ------------------------------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.bfloat16):

@@ -142,8 +142,8 @@ def resize_crop_normalize(img_u8: torch.Tensor, target: Tuple[int, int], norm_ty
         out = torch.empty(n, 3, th, tw, device=dev, dtype=torch.float32)
     if return_u8 or out is None:
         out8 = torch.empty(n, th, tw, 3, device=dev, dtype=torch.uint8)
-    check(lib.ma_resample_v_norm_u8rgb(tmp.data_ptr(), n, y1 - y0, tw, y0, tv_.d_bounds.data_ptr(), tv_.d_coeffs.data_ptr(), rh,
-                                       top, th, m3, s3, None if out is None else out.data_ptr(),
+    check(lib.ma_resample_v_norm_u8rgb(tmp.data_ptr(), n, y1 - y0, tw, y0, tv_.d_bounds.data_ptr(), tv_.d_coeffs.data_ptr(),
+                                       tv_.d_coeffs.shape[0], rh, top, th, m3, s3, None if out is None else out.data_ptr(),
                                        None if out8 is None else out8.data_ptr(), stream), "ma_resample_v_norm_u8rgb")
     ops._count(2)
     if single and out8 is not None:

@@ -309,7 +309,7 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             raise AssertionError(f"Input image size ({height}, {width}) must be a multiple of the patch size {p}")
         geo_active = self._geometric_inputs_active(views)
         eng = self.engine()
-        eng.dpt_chunk = 2 if memory_efficient_inference else 4
+        eng.dpt_chunk = min(2, eng.dpt_chunk_default) if memory_efficient_inference else eng.dpt_chunk_default
         hp, wp = height // p, width // p
         N = hp * wp
         plan, comm = None, self._shard_comm
