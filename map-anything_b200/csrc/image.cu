@@ -206,10 +206,8 @@ resample_h_dp4a_kernel(const uint8_t* __restrict__ src, int64_t row_stride, int6
 }
 
 // Thread per output pixel (x, yy = top + blockIdx.y) of the cropped target of frame blockIdx.z.
-// KMAX > 0: the tap loop is fully unrolled to KMAX taps (window length rounded up to 4; absent taps re-read the last valid
-// row with a zero coefficient), so all 3 * KMAX byte loads of a pixel are in flight together -- the rolled loop (KMAX = 0,
-// any window length) was bound by the latency of its dependent global loads (ncu: 17 long-scoreboard stalls per issue).
-template <int KMAX>
+// (A fully unrolled tap loop -- all byte loads of a pixel in flight at once -- was measured slower: 11.7 vs 10.1 us per
+// 1920x1080 frame for both passes together.)
 __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows, int cols, int y0, const int32_t* __restrict__ bounds,
                                        const int32_t* __restrict__ coeffs, int out_size, int top, int th, float m0, float m1,
                                        float m2, float s0, float s1, float s2, float* __restrict__ out_chw,
@@ -222,22 +220,11 @@ __global__ void resample_v_norm_kernel(const uint8_t* __restrict__ tmp, int rows
   int a0 = 1 << (RS_PRECISION_BITS - 1), a1 = a0, a2 = a0;
   const uint8_t* p = tmp + ((static_cast<int64_t>(blockIdx.z) * rows + (first - y0)) * cols + x) * 3;
   const int64_t rs = static_cast<int64_t>(cols) * 3;
-  if constexpr (KMAX == 0) {
-    for (int t = 0; t < cnt; ++t, p += rs) {
-      const int k = __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy);  // warp-uniform
-      a0 += p[0] * k;
-      a1 += p[1] * k;
-      a2 += p[2] * k;
-    }
-  } else {
-#pragma unroll
-    for (int t = 0; t < KMAX; ++t) {
-      const int k = t < cnt ? __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy) : 0;
-      const uint8_t* q = p + (t < cnt ? t : cnt - 1) * rs;
-      a0 += q[0] * k;
-      a1 += q[1] * k;
-      a2 += q[2] * k;
-    }
+  for (int t = 0; t < cnt; ++t, p += rs) {
+    const int k = __ldg(coeffs + static_cast<int64_t>(t) * out_size + yy);  // warp-uniform
+    a0 += p[0] * k;
+    a1 += p[1] * k;
+    a2 += p[2] * k;
   }
   const uint8_t u0 = clip8(a0), u1 = clip8(a1), u2 = clip8(a2);
   if (out_u8) {
@@ -466,24 +453,8 @@ extern "C" int ma_resample_v_norm_u8rgb(const uint8_t* tmp, int n, int rows, int
   const float m0 = mean_host ? mean_host[0] : 0.f, m1 = mean_host ? mean_host[1] : 0.f, m2 = mean_host ? mean_host[2] : 0.f;
   const float s0 = std_host ? std_host[0] : 1.f, s1 = std_host ? std_host[1] : 1.f, s2 = std_host ? std_host[2] : 1.f;
   dim3 grid((cols + 127) / 128, th, n);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static const bool rolled = [] {  // MA_RESAMPLE_V_ROLLED=1: the rolled tap loop for every window length (A/B runs)
-    const char* e = getenv("MA_RESAMPLE_V_ROLLED");
-    return e && e[0] == '1';
-  }();
-#define MA_V(K)                                                                                                            \
-  case K / 4:                                                                                                              \
-    resample_v_norm_kernel<K><<<grid, 128, 0, st>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th, m0, m1, m2, s0, s1, \
-                                                    s2, out_chw, out_u8);                                                  \
-    break
-  switch (rolled || ksize > 64 ? 0 : (ksize + 3) / 4) {
-    MA_V(4); MA_V(8); MA_V(12); MA_V(16); MA_V(20); MA_V(24); MA_V(28); MA_V(32);
-    MA_V(36); MA_V(40); MA_V(44); MA_V(48); MA_V(52); MA_V(56); MA_V(60); MA_V(64);
-    default:
-      resample_v_norm_kernel<0><<<grid, 128, 0, st>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th, m0, m1, m2, s0, s1, s2,
-                                                      out_chw, out_u8);
-  }
-#undef MA_V
+  resample_v_norm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(tmp, rows, cols, y0, bounds, coeffs, out_size, top, th,
+                                                                             m0, m1, m2, s0, s1, s2, out_chw, out_u8);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }
