@@ -7,13 +7,18 @@
 // separable filter is evaluated in double precision, normalised, rounded to 22-bit fixed point; each pass accumulates
 // int32 products from 1 << 21, shifts right by 22 and clamps to a byte; the horizontal pass runs first and its 8-bit
 // result feeds the vertical pass.  Restated here so that the GPU path is BIT-EXACT with the reference's images:
-//   * ma_resample_coeffs   (host, libm double precision like Pillow): window bounds + fixed-point coefficients
-//   * resample_h_kernel    one block per source row: the row is staged in shared memory with 4-byte coalesced loads,
-//                          every thread produces output pixels (3 channels) of that row
+//   * ma_resample_coeffs / ma_resample_pack_coeffs (host, libm double precision like Pillow): window bounds, fixed-point
+//                          coefficients and their byte planes
+//   * resample_h_dp4a_kernel  one block per source row: the row is staged in shared memory with 4-byte coalesced loads and
+//                          split into R / G / B byte planes; every thread produces output pixels of that row with dp4a on
+//                          byte-split coefficients.  resample_h_vec_kernel (32-bit loads + PRMT) and resample_h_kernel
+//                          (byte loads, any window length) are the earlier forms, kept as fallbacks / for A/B runs
 //   * resample_v_norm_kernel  thread per output pixel of the CROPPED target: vertical pass over the 8-bit
 //                          intermediate (taps are row-contiguous across a warp), byte clamp, (u/255 - mean)/std in the
 //                          rounding order of torchvision, planar fp32 (3,H,W) output = the model's `img` layout
-// Both kernels are HBM-bound byte work (a 1920x1080 frame: 6.2 MB in, 1.7 MB intermediate, 3.2 MB out).
+//   * gather_rows_cols_f32_kernel / f32_to_u8_kernel  nearest-neighbour depth resize + crop, float image -> bytes
+// By bytes this is HBM work (a 1920x1080 frame: 6.2 MB in, 1.7 MB intermediate, 1.8 MB out); in practice the integer
+// pipes bound it (25-tap LANCZOS windows at this reduction), see DESIGN.md section 5 for the measured forms.
 #include <math.h>
 #include <stdlib.h>
 
