@@ -214,3 +214,35 @@ def test_cabi_pack_coeffs_host(i, o, filt):
     assert np.array_equal(k[:ks.value], coeffs) and not k[ks.value:].any()
     big = np.full((1, 1), 1 << 24, np.int32)
     assert lib.ma_resample_pack_coeffs(big.ctypes.data, 1, 1, packed.ctypes.data) != 0
+
+
+def test_host_planning_matches_oracle_on_random_sizes():
+    """Host-side planning of the drop-in (target size, resize plan, crop box, nearest-neighbour offsets, intrinsics update)
+    against the oracle restatement of the reference over many random shapes -- no GPU involved."""
+    from mapanything_b200 import image as PI
+
+    rng = np.random.default_rng(42)
+    for _ in range(400):
+        W1, H1 = int(rng.integers(16, 5000)), int(rng.integers(16, 4000))
+        mode = ["fixed_mapping", "square", "longest_side", "fixed_size"][int(rng.integers(0, 4))]
+        size = None if mode == "fixed_mapping" else (int(rng.integers(28, 800)) if mode != "fixed_size"
+                                                    else (int(rng.integers(28, 800)), int(rng.integers(28, 800))))
+        ratios = [W1 / H1, float(rng.uniform(0.4, 2.5))]
+        rset = int(rng.choice([518, 512]))
+        target = PI._target_size(ratios, mode, size, 14, rset, False)
+        assert tuple(target) == tuple(OI.target_size_for(ratios, mode, size, 14, rset))
+        if min(target) < 14:
+            continue
+        assert PI.resize_plan(W1, H1, target) == OI.resize_plan(W1, H1, target)
+        rw, rh, _, _, _ = PI.resize_plan(W1, H1, target)
+        assert np.array_equal(PI._nearest_indices(W1, rw), OI.nearest_indices(W1, rw))
+        for dtype in (np.float32, np.float64):
+            K = np.array([[rng.uniform(0.5, 2) * W1, 0, W1 / 2 + rng.uniform(-20, 20)],
+                          [0, rng.uniform(0.5, 2) * W1, H1 / 2 + rng.uniform(-20, 20)], [0, 0, 1]], dtype)
+            scale = max(np.array(target) / np.array((W1, H1))) + 1e-8
+            a = PI._camera_matrix_of_crop(K, np.array((W1, H1)), np.array((rw, rh)), scaling=scale)
+            b = OI.camera_matrix_of_crop(K, np.array((W1, H1)), np.array((rw, rh)), scaling=scale)
+            assert a.dtype == b.dtype == dtype and np.array_equal(a, b)
+            a2 = PI._camera_matrix_of_crop(a, (rw, rh), target, offset_factor=0.5)
+            b2 = OI.camera_matrix_of_crop(b, (rw, rh), target, offset_factor=0.5)
+            assert np.array_equal(a2, b2)
