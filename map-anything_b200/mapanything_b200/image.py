@@ -182,6 +182,25 @@ class _Uploader:
         return dst
 
 
+_RESIZE_MODES = ["fixed_mapping", "longest_side", "square", "fixed_size"]
+
+
+def _check_resize_args(resize_mode, size) -> None:
+    """Argument checks shared by load_images and preprocess_inputs; messages as in the reference (image.py:165-188, :371-394)."""
+    if resize_mode not in _RESIZE_MODES:
+        raise ValueError(f"Resize_mode must be one of {_RESIZE_MODES}, got '{resize_mode}'")
+    needs_int, needs_pair = resize_mode in ("longest_side", "square"), resize_mode == "fixed_size"
+    if (needs_int or needs_pair) and size is None:
+        raise ValueError(f"Size parameter is required for resize_mode='{resize_mode}'")
+    if needs_int and not isinstance(size, int):
+        raise ValueError(f"Size must be an int for resize_mode='{resize_mode}', got {type(size)}")
+    if needs_pair:
+        if not isinstance(size, (tuple, list)) or len(size) != 2:
+            raise ValueError(f"Size must be a tuple/list of (width, height) for resize_mode='fixed_size', got {size}")
+        if not all(isinstance(x, int) for x in size):
+            raise ValueError(f"Size values must be integers for resize_mode='fixed_size', got {size}")
+
+
 def _target_size(aspect_ratios: Sequence[float], resize_mode: str, size, patch_size: int, resolution_set: int, verbose: bool):
     """One (W, H) for all images from their average aspect ratio (image.py:240-289)."""
     average_aspect_ratio = sum(aspect_ratios) / len(aspect_ratios)
@@ -214,19 +233,7 @@ def load_images(
     """Same contract as the reference `load_images` (image.py:134-332): a list of view dicts with `img` (1, 3, H, W) fp32,
     `true_shape`, `idx`, `instance`, `data_norm_type`; every image is brought to ONE target size chosen from the average
     aspect ratio.  `img` lives on `device` (default: the current CUDA device)."""
-    valid_resize_modes = ["fixed_mapping", "longest_side", "square", "fixed_size"]
-    if resize_mode not in valid_resize_modes:
-        raise ValueError(f"Resize_mode must be one of {valid_resize_modes}, got '{resize_mode}'")
-    if resize_mode in ["longest_side", "square", "fixed_size"] and size is None:
-        raise ValueError(f"Size parameter is required for resize_mode='{resize_mode}'")
-    if resize_mode in ["longest_side", "square"]:
-        if not isinstance(size, int):
-            raise ValueError(f"Size must be an int for resize_mode='{resize_mode}', got {type(size)}")
-    elif resize_mode == "fixed_size":
-        if not isinstance(size, (tuple, list)) or len(size) != 2:
-            raise ValueError(f"Size must be a tuple/list of (width, height) for resize_mode='fixed_size', got {size}")
-        if not all(isinstance(x, int) for x in size):
-            raise ValueError(f"Size values must be integers for resize_mode='fixed_size', got {size}")
+    _check_resize_args(resize_mode, size)
 
     if isinstance(folder_or_list, str):
         if verbose:
@@ -419,19 +426,7 @@ def preprocess_inputs(
     multi-modal inputs of every view (intrinsics or ray directions, depth_z, camera poses) to one target resolution.
     Images are resampled like load_images; depth with nearest neighbour; intrinsics follow the scale and a
     principal-point preserving crop (cropping.py:278-318, :362-381).  `img` and `depth_z` are returned on `device`."""
-    valid_resize_modes = ["fixed_mapping", "longest_side", "square", "fixed_size"]
-    if resize_mode not in valid_resize_modes:
-        raise ValueError(f"Resize_mode must be one of {valid_resize_modes}, got '{resize_mode}'")
-    if resize_mode in ["longest_side", "square", "fixed_size"] and size is None:
-        raise ValueError(f"Size parameter is required for resize_mode='{resize_mode}'")
-    if resize_mode in ["longest_side", "square"]:
-        if not isinstance(size, int):
-            raise ValueError(f"Size must be an int for resize_mode='{resize_mode}', got {type(size)}")
-    elif resize_mode == "fixed_size":
-        if not isinstance(size, (tuple, list)) or len(size) != 2:
-            raise ValueError(f"Size must be a tuple/list of (width, height) for resize_mode='fixed_size', got {size}")
-        if not all(isinstance(x, int) for x in size):
-            raise ValueError(f"Size values must be integers for resize_mode='fixed_size', got {size}")
+    _check_resize_args(resize_mode, size)
     if not input_views:
         raise ValueError("input_views cannot be empty")
 

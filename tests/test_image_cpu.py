@@ -246,3 +246,25 @@ def test_host_planning_matches_oracle_on_random_sizes():
             a2 = PI._camera_matrix_of_crop(a, (rw, rh), target, offset_factor=0.5)
             b2 = OI.camera_matrix_of_crop(b, (rw, rh), target, offset_factor=0.5)
             assert np.array_equal(a2, b2)
+
+
+@pytest.mark.parametrize("i,o,filt", [(1920, 522, 1), (4032, 522, 1), (8000, 130, 1), (97, 140, 3), (300, 518, 3)])
+def test_dp4a_decomposition_is_exact_in_int32(i, o, filt):
+    """The dp4a kernel accumulates three byte-plane partial sums in int32 and recombines them as s0 + 256 s1 + 65536 s2.
+    Emulated here with numpy int32 (wrap-around) arithmetic for worst-case (all 255) and random pixels: identical to the
+    direct 64-bit sum, which itself stays inside int32 (as it must for Pillow's own int accumulator)."""
+    b, k = OI.resample_coeffs(i, o, filt)          # [out][ksize]
+    k = k.astype(np.int64)
+    k0, k1, k2 = k & 255, (k >> 8) & 255, k >> 16
+    assert np.array_equal(k0 + 256 * k1 + 65536 * k2, k) and k2.min() >= -128 and k2.max() <= 127
+    rng = np.random.default_rng(i + o)
+    for px in (np.full(k.shape, 255, np.int64), rng.integers(0, 256, k.shape).astype(np.int64),
+               np.where(k > 0, 255, 0).astype(np.int64), np.where(k < 0, 255, 0).astype(np.int64)):
+        direct = (px * k).sum(1) + (1 << 21)
+        assert direct.max() < 2 ** 31 and direct.min() >= -2 ** 31
+        with np.errstate(over="ignore"):
+            s0 = (px * k0).sum(1).astype(np.int32)
+            s1 = (px * k1).sum(1).astype(np.int32)
+            s2 = (px * k2).sum(1).astype(np.int32)
+            acc = np.int32(1 << 21) + s0 + s1 * np.int32(256) + s2 * np.int32(65536)
+        assert np.array_equal(acc.astype(np.int64), direct)
