@@ -17,7 +17,6 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT / "map-anything_b200"))
-sys.path.insert(0, str(ROOT))
 from mapanything_b200.image import _Uploader, find_closest_aspect_ratio, resize_crop_normalize, resize_plan  # noqa: E402
 
 
@@ -51,7 +50,11 @@ def main():
     # reference host pipeline on one frame
     import PIL.Image
 
-    from oracle.image import normalize_u8
+    mean = torch.tensor((0.485, 0.456, 0.406)).view(3, 1, 1)
+    std = torch.tensor((0.229, 0.224, 0.225)).view(3, 1, 1)
+
+    def normalize_u8(a, _norm):  # torchvision ToTensor + Normalize, as the reference applies them (image.py:291-296)
+        return torch.from_numpy(a.copy()).permute(2, 0, 1).contiguous().float().div(255).sub_(mean).div_(std)[None]
 
     t0 = time.perf_counter()
     reps = 5
