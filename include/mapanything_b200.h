@@ -128,10 +128,9 @@ int ma_attention_fwd(const void* q, int64_t ldq, int64_t q_rows, int q_col0, con
 #define MA_ATTN_MAX_SEGMENTS 16
 #define MA_ATTN_STATE_IN 1
 #define MA_ATTN_STATE_OUT 2
-#define MA_ATTN_PINGPONG 4 /* experimental: two query tiles per CTA, softmax warpgroups alternate their exponential phases */
 typedef struct ma_attn_ext {
   int32_t n_segments; /* 0 = single range [0, kv_len) */
-  int32_t flags;      /* MA_ATTN_STATE_* | MA_ATTN_PINGPONG */
+  int32_t flags;      /* MA_ATTN_STATE_* */
   int32_t seg_row0[MA_ATTN_MAX_SEGMENTS];
   int32_t seg_len[MA_ATTN_MAX_SEGMENTS];
   float* state_o;

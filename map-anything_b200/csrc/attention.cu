@@ -547,7 +547,6 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
       const float sl2 = p.scale_log2;
 
-      const bool pingpong = NQT == 2 && n_qt == 2 && (p.flags & MA_ATTN_PINGPONG) != 0;
       float m_run = -INFINITY, l_run = 0.f;
       if (state_in) {
         const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D;
@@ -628,14 +627,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           l_run *= alpha;
         }
         m_run = m_new;
-        float msc = m_run * sl2;
-        // Ping-pong (two-tile kernel, MA_ATTN_PINGPONG): the exponential phases of the two softmax warpgroups of the SM
-        // are forced to ALTERNATE through two named barriers.  Left free-running, the two groups settle in phase -- both
-        // read S and take maxima together, then share the MUFU pipe at half rate each -- and the pipe idles while both
-        // are outside their exponential phase (69 % busy).  Alternating, one group owns the MUFU pipe
-        // at full rate for ~1024 clk while the other does its tensor-memory reads, maximum, pack and stores.  The
-        // barrier carries `msc` so that no exponential can be scheduled above it.
-        if (pingpong && (t == 1 || j > 0)) asm volatile("bar.sync %1, 256;" : "+f"(msc) : "r"(1 + t) : "memory");
+        const float msc = m_run * sl2;
 
         // exponentials -> bf16 pairs (two per 32-bit P column) in registers; the wait for the previous tile's P.V
         // (which still reads the single P buffer in tensor memory) is only needed before the stores
@@ -657,10 +649,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           pb[i] = pack_bf16x2(e4, e5);
           pb[16 + i] = pack_bf16x2(e6, e7);
         }
-        float lsum = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        // hand the MUFU pipe to the other warpgroup (the sum depends on every exponential of this tile)
-        if (pingpong && (t == 0 || j + 1 < n_kv_tiles)) asm volatile("bar.arrive %1, 256;" : "+f"(lsum) : "r"(2 - t) : "memory");
-        l_run += lsum;
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
         tc_fence_after();
         tmem_st_32x32b_x32(tmem_p, pa);
@@ -896,12 +885,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       const char* e = getenv("MA_ATTN_NQT");
       return e ? atoi(e) : 0;
     }();
-    static const bool pingpong_env = [] {  // MA_ATTN_PINGPONG=1: every launch uses the two-tile kernel with alternating phases
-      const char* e = getenv("MA_ATTN_PINGPONG");
-      return e && e[0] == '1';
-    }();
-    if (pingpong_env) p.flags |= MA_ATTN_PINGPONG;
-    const int nqt = (p.kv_split > 1 || (p.flags & MA_ATTN_PINGPONG)) ? 2 : (nqt_env == 1 || nqt_env == 2) ? nqt_env : 1;
+    const int nqt = p.kv_split > 1 ? 2 : (nqt_env == 1 || nqt_env == 2) ? nqt_env : 1;
     if (nqt == 2) {
       MA_CHECK_CUDA(launch_kernel(attention_fwd_v2_kernel<2>, dim3(grid_ctas), dim3(A2Cfg<2>::THREADS), A2Cfg<2>::SMEM_BYTES,
                                   static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));

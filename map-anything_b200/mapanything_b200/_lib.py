@@ -43,7 +43,7 @@ class GemmEpilogue(C.Structure):
     ]
 
 
-MA_ATTN_MAX_SEGMENTS, MA_ATTN_STATE_IN, MA_ATTN_STATE_OUT, MA_ATTN_PINGPONG = 16, 1, 2, 4
+MA_ATTN_MAX_SEGMENTS, MA_ATTN_STATE_IN, MA_ATTN_STATE_OUT = 16, 1, 2
 
 
 class AttnExt(C.Structure):

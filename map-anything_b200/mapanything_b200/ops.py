@@ -198,10 +198,8 @@ def attention(
     state_out: bool = False,
     kv_split: int = 1,
     kv_split_from: int = 0,
-    pingpong: bool = False,
 ) -> torch.Tensor:
-    """softmax(q k^T * scale) v per (sequence, head), head_dim 64.  pingpong: experimental two-tile kernel whose softmax
-    warpgroups alternate their exponential phases (MA_ATTN_PINGPONG).
+    """softmax(q k^T * scale) v per (sequence, head), head_dim 64.
 
     q/k/v/out are 2-D token-major bf16 views whose rows may be strided column slices of a wider matrix
     (e.g. qkv[:, :D], qkv[:, D:2D], qkv[:, 2D:]); no head permutation is materialised. See ma_attention_fwd.
@@ -229,9 +227,8 @@ def attention(
     if kv_split > 1 and state is None:
         raise ValueError("kv_split > 1 writes partial states: pass state=...")
     ext = None
-    if kv_segments is not None or state_in or state_out or kv_split > 1 or pingpong:
+    if kv_segments is not None or state_in or state_out or kv_split > 1:
         ext = AttnExt()
-        ext.kv_split = 1
         if kv_segments is not None:
             if len(kv_segments) > MA_ATTN_MAX_SEGMENTS:
                 raise ValueError(f"at most {MA_ATTN_MAX_SEGMENTS} kv segments")
@@ -250,8 +247,6 @@ def attention(
             ext.state_o, ext.ld_state_o, ext.state_m = so.data_ptr(), so.stride(1), sm.data_ptr()
             ext.kv_split, ext.split_stride_o, ext.split_stride_m = kv_split, so.stride(0), sm.stride(0)
             ext.kv_split_from = kv_split_from
-    if pingpong:
-        ext.flags |= _lib.MA_ATTN_PINGPONG
     with launch("attention", 4.0 * num_seqs * num_heads * q_len * kv_len * 64, tag=f"{num_seqs}x{num_heads}x{q_len}x{kv_len}"):
         check(
             lib.ma_attention_fwd_ex(
