@@ -181,3 +181,42 @@ def test_depthmap_to_world_frame_matches_reference():
     assert np.array_equal(pc.numpy(), gold["pts_cam"]) and np.array_equal(valid.numpy(), gold["valid"])
     pw, _ = G.depthmap_to_world_frame(depth, K, pose)
     assert np.abs(pw.numpy() - gold["pts_world"]).max() < 1e-6
+
+
+def test_small_vit_matches_huggingface_dinov2():
+    """Independent cross-check of stage 1: the oracle ViT against `transformers.Dinov2Model` -- a second
+    implementation of DINOv2 that shares no code with the reference's vendored copy -- on the same synthetic weights."""
+    transformers = pytest.importorskip("transformers")
+    from oracle.vit import OracleDinoV2
+    from oracle.weights import synth_state_dict
+
+    dim, depth, heads = 128, 2, 2
+    m = OracleDinoV2(img_size=70, embed_dim=dim, depth=depth, num_heads=heads).eval()
+    sd = synth_state_dict(m, seed=5)
+    m.load_state_dict(sd)
+    cfg = transformers.Dinov2Config(hidden_size=dim, num_hidden_layers=depth, num_attention_heads=heads, image_size=70,
+                                    patch_size=14, mlp_ratio=4, qkv_bias=True, hidden_act="gelu", layer_norm_eps=1e-6,
+                                    layerscale_value=1.0, attn_implementation="eager")
+    hf = transformers.Dinov2Model(cfg).eval()
+    new = {"embeddings.cls_token": sd["cls_token"], "embeddings.mask_token": sd["mask_token"],
+           "embeddings.position_embeddings": sd["pos_embed"],
+           "embeddings.patch_embeddings.projection.weight": sd["patch_embed.proj.weight"],
+           "embeddings.patch_embeddings.projection.bias": sd["patch_embed.proj.bias"],
+           "layernorm.weight": sd["norm.weight"], "layernorm.bias": sd["norm.bias"]}
+    for i in range(depth):
+        s, d = f"blocks.{i}.", f"encoder.layer.{i}."
+        qw, kw, vw = sd[s + "attn.qkv.weight"].chunk(3, 0)
+        qb, kb, vb = sd[s + "attn.qkv.bias"].chunk(3, 0)
+        for n, w, b in (("query", qw, qb), ("key", kw, kb), ("value", vw, vb)):
+            new[d + f"attention.attention.{n}.weight"], new[d + f"attention.attention.{n}.bias"] = w, b
+        new[d + "attention.output.dense.weight"], new[d + "attention.output.dense.bias"] = sd[s + "attn.proj.weight"], sd[s + "attn.proj.bias"]
+        new[d + "layer_scale1.lambda1"], new[d + "layer_scale2.lambda1"] = sd[s + "ls1.gamma"], sd[s + "ls2.gamma"]
+        for n in ("norm1", "norm2", "mlp.fc1", "mlp.fc2"):
+            new[d + n + ".weight"], new[d + n + ".bias"] = sd[s + n + ".weight"], sd[s + n + ".bias"]
+    missing, unexpected = hf.load_state_dict(new, strict=False)
+    assert not unexpected and not [k for k in missing if "mask_token" not in k], (missing, unexpected)
+    img = torch.randn(2, 3, 70, 70, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ours = m.forward_patch_tokens(img)
+        theirs = hf(pixel_values=img).last_hidden_state[:, 1:]
+    assert torch.allclose(ours, theirs, atol=2e-5), (ours - theirs).abs().max()
