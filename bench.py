@@ -330,7 +330,7 @@ def run_ours(args):
     h2d = (sum(im.numel() * 4 for im in host_imgs)
            + sum(x.numel() * x.element_size() for e in host_extra for x in e.values())) * world
     if rank == 0:
-        cpu = cpu_baseline(V)
+        cpu = cpu_baseline(V) if world == 1 else None  # the host baseline is reported at N = 1 only
         line = {
             "metric": METRIC, "value": vps, "unit": "views/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
