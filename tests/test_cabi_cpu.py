@@ -93,3 +93,27 @@ def test_info_sharing_variants_construct_with_reference_key_layout():
     assert ma["distinguish_ref_and_non_ref_views"] is False
     with pytest.raises(ValueError, match="info_sharing must be one of"):
         mapanything_variant_config("gat_ifr_24_layers")
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and a gcc-built client (tests/cabi_host_check.c) links against the
+    shared library and runs its host entry points."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+
+        pytest.skip("no gcc")
+    lib_dir = root / "map-anything_b200" / "mapanything_b200"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    str(root / "include" / "mapanything_b200.h")], check=True)
+    exe = tmp_path / "cabi_host_check"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", str(root / "include"), str(root / "tests" / "cabi_host_check.c"), "-o", str(exe),
+                    "-L", str(lib_dir), "-l:libmapanything_b200.so", f"-Wl,-rpath,{lib_dir}"], check=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stdout, res.stderr)
+    assert "cabi host check ok: ksize 25" in res.stdout
