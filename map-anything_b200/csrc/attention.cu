@@ -373,8 +373,79 @@ struct A2Cfg {
   static constexpr int BMQ = NQT * ATT_BM;     // query rows per CTA
 };
 constexpr float A2_RESCALE_LOG2 = 8.0f;
+constexpr int A2_DEFAULT_POLY = 7;  // of 16 score pairs: measured best split between the MUFU and the FMA pipe
 
-template <int NQT>
+// Exponentials of one 32-column chunk of a score row (16 register pairs) -> 16 packed bf16x2 probabilities + row-sum
+// contribution.  NPOLY of every 16 pairs are evaluated on the FMA pipe (exp2_poly_pair), the rest on the MUFU; all
+// arithmetic that can be is issued as packed fp32x2 (half the issue slots).  mref is an integer-valued reference maximum
+// in log2 units: p = 2^(s * sl2 - mref).
+__host__ __device__ constexpr bool a2_poly_slot(int i, int npoly) { return ((i * npoly) & 15) < npoly; }
+
+template <int NPOLY>
+__device__ __forceinline__ void a2_exp_chunk(const uint32_t (&v)[32], uint32_t* dst, uint64_t sl2_2, uint64_t nm2, uint64_t k2,
+                                             float smin, uint64_t (&acc)[4]) {
+  // Written stage by stage over all pairs of the chunk (not pair by pair): every stage is NPOLY (or 16 - NPOLY)
+  // independent instructions, so the dependent chain clamp -> r -> u -> g -> cubic -> exponent insert never waits on
+  // the fixed FMA-pipe latency even with only two softmax warps per scheduler.
+  constexpr int NP = NPOLY > 0 ? NPOLY : 1;
+  uint64_t s2[16], r2[NP], g2[NP];
+  int pi = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (a2_poly_slot(i, NPOLY)) {
+      s2[i] = pack2(fmaxf(__uint_as_float(v[2 * i]), smin), fmaxf(__uint_as_float(v[2 * i + 1]), smin));
+    } else {
+      s2[i] = ffma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, nm2);
+    }
+  }
+  if (NPOLY > 0) {
+    const uint64_t c3 = pack2(0.055205505f, 0.055205505f), c2 = pack2(0.24261397f, 0.24261397f);
+    const uint64_t c1 = pack2(0.69325477f, 0.69325477f), c0 = pack2(0.9999277f, 0.9999277f);
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) r2[pi++] = ffma2(s2[i], sl2_2, k2);
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) { g2[pi] = fsub2(k2, r2[pi]); ++pi; }
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) { g2[pi] = ffma2(s2[i], sl2_2, g2[pi]); ++pi; }
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) { s2[i] = ffma2(g2[pi], c3, c2); ++pi; }
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) { s2[i] = ffma2(s2[i], g2[pi], c1); ++pi; }
+    pi = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (a2_poly_slot(i, NPOLY)) { s2[i] = ffma2(s2[i], g2[pi], c0); ++pi; }
+  }
+  pi = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float ea, eb;
+    unpack2(s2[i], ea, eb);
+    if (a2_poly_slot(i, NPOLY)) {
+      float ra, rb;
+      unpack2(r2[pi++], ra, rb);
+      ea = __uint_as_float(__float_as_uint(ea) + (__float_as_uint(ra) << 23));
+      eb = __uint_as_float(__float_as_uint(eb) + (__float_as_uint(rb) << 23));
+    } else {
+      ea = fast_exp2(ea);
+      eb = fast_exp2(eb);
+    }
+    acc[i & 3] = fadd2(acc[i & 3], pack2(ea, eb));
+    dst[i] = pack_bf16x2(ea, eb);
+  }
+}
+
+template <int NQT, int NPOLY>
 __global__ void __launch_bounds__(A2Cfg<NQT>::THREADS, NQT == 2 ? 1 : 2)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -547,8 +618,15 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
       const float sl2 = p.scale_log2;
 
-      float m_run = -INFINITY, l_run = 0.f;
+      // mref: reference maximum of the row in log2 units (score * scale * log2 e), kept INTEGER valued so that the
+      // polynomial exp2 path needs no per-row fraction; any reference works (it cancels in O / l), so the true running
+      // maximum is only tracked to within the lazy-rescale slack
+      float mref = 0.f, l_run = 0.f;
       if (state_in) {
+        // carried state = (normalised O, m' in raw score units, l = 1): re-express it against the integer reference
+        const float m_in = q_ok ? p.state_m[q_grow * p.num_heads + head] : 0.f;
+        mref = rintf(m_in * sl2);
+        const float c_in = q_ok ? fast_exp2(fmaf(m_in, sl2, -mref)) : 0.f;  // in [2^-0.5, 2^0.5]
         const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D;
 #pragma unroll 1
         for (int c = 0; c < ATT_D; c += 8) {
@@ -557,16 +635,18 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           for (int i = 0; i < 8; ++i) o[i] = 0u;
           if (q_ok) {
             const float4 x = *reinterpret_cast<const float4*>(so + c), y = *reinterpret_cast<const float4*>(so + c + 4);
-            o[0] = __float_as_uint(x.x); o[1] = __float_as_uint(x.y); o[2] = __float_as_uint(x.z); o[3] = __float_as_uint(x.w);
-            o[4] = __float_as_uint(y.x); o[5] = __float_as_uint(y.y); o[6] = __float_as_uint(y.z); o[7] = __float_as_uint(y.w);
+            o[0] = __float_as_uint(x.x * c_in); o[1] = __float_as_uint(x.y * c_in); o[2] = __float_as_uint(x.z * c_in);
+            o[3] = __float_as_uint(x.w * c_in); o[4] = __float_as_uint(y.x * c_in); o[5] = __float_as_uint(y.y * c_in);
+            o[6] = __float_as_uint(y.z * c_in); o[7] = __float_as_uint(y.w * c_in);
           }
           tmem_st_32x32b_x8(tmem_o + c, o);
         }
-        m_run = q_ok ? p.state_m[q_grow * p.num_heads + head] : 0.f;
-        l_run = q_ok ? 1.f : 0.f;
+        l_run = c_in;
         tmem_st_wait();
         tc_fence_before();
       }
+      const uint64_t sl2_2 = pack2(sl2, sl2);
+      const float inv_sl2 = 1.0f / sl2;
 
       KvCursor cur;
       cur.skip(p, kv_tile0);
@@ -604,15 +684,16 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
         // lazy rescale: adopt the new maximum only when it grew by more than 2^8
-        float m_new = m_run;
+        const float mt2 = m_tile * sl2;
+        float m_new = mref;
         bool need = false;
-        if (j == 0 && !state_in) m_new = m_tile;
-        else if ((m_tile - m_run) * sl2 > A2_RESCALE_LOG2) { need = true; m_new = m_tile; }
+        if (j == 0 && !state_in) m_new = rintf(mt2);
+        else if (mt2 - mref > A2_RESCALE_LOG2) { need = true; m_new = rintf(mt2); }
         bool waited = false;
         if (__any_sync(0xffffffffu, need)) {
           if (j > 0) { mbar_wait(&p_empty[t], (j - 1) & 1); waited = true; }  // PV of tile j-1 has completed
           tc_fence_after();
-          const float alpha = need ? fast_exp2((m_run - m_new) * sl2) : 1.f;
+          const float alpha = need ? fast_exp2(mref - m_new) : 1.f;  // an exact power of two
 #pragma unroll 1
           for (int c = 0; c < ATT_D; c += 8) {  // rare path
             uint32_t o[8];
@@ -626,34 +707,45 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tc_fence_before();
           l_run *= alpha;
         }
-        m_run = m_new;
-        const float msc = m_run * sl2;
+        mref = m_new;
 
-        // exponentials -> bf16 pairs (two per 32-bit P column) in registers; the wait for the previous tile's P.V
-        // (which still reads the single P buffer in tensor memory) is only needed before the stores
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        uint32_t pa[32], pb[32];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), sl2, -msc));
-          const float e1 = fast_exp2(fmaf(__uint_as_float(v0[2 * i + 1]), sl2, -msc));
-          const float e2 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), sl2, -msc));
-          const float e3 = fast_exp2(fmaf(__uint_as_float(v1[2 * i + 1]), sl2, -msc));
-          const float e4 = fast_exp2(fmaf(__uint_as_float(v2[2 * i]), sl2, -msc));
-          const float e5 = fast_exp2(fmaf(__uint_as_float(v2[2 * i + 1]), sl2, -msc));
-          const float e6 = fast_exp2(fmaf(__uint_as_float(v3[2 * i]), sl2, -msc));
-          const float e7 = fast_exp2(fmaf(__uint_as_float(v3[2 * i + 1]), sl2, -msc));
-          l4[0] += e0 + e1; l4[1] += e2 + e3; l4[2] += e4 + e5; l4[3] += e6 + e7;
-          pa[i] = pack_bf16x2(e0, e1);
-          pa[16 + i] = pack_bf16x2(e2, e3);
-          pb[i] = pack_bf16x2(e4, e5);
-          pb[16 + i] = pack_bf16x2(e6, e7);
-        }
-        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);  // PV of tile j-1 no longer reads P
+        // exponentials -> bf16 pairs (two per 32-bit P column), stored to tensor memory chunk by chunk (16 columns = 32
+        // scores at a time, so the packed probabilities never occupy more than 16 registers).  P.V of the previous tile
+        // still reads the single P buffer: it was issued a whole tile ago, so this wait is normally already satisfied
+        if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);
         tc_fence_after();
-        tmem_st_32x32b_x32(tmem_p, pa);
-        tmem_st_32x32b_x32(tmem_p + 32, pb);
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+        const uint64_t nm2 = pack2(-mref, -mref);
+        if (NPOLY == 0 || kv_valid < ATT_BN) {  // masked columns are -inf: MUFU only (ex2(-inf) = 0 exactly)
+          uint32_t pk[16];
+          a2_exp_chunk<0>(v0, pk, sl2_2, nm2, 0ull, 0.f, acc);
+          tmem_st_32x32b_x16(tmem_p, pk);
+          a2_exp_chunk<0>(v1, pk, sl2_2, nm2, 0ull, 0.f, acc);
+          tmem_st_32x32b_x16(tmem_p + 16, pk);
+          a2_exp_chunk<0>(v2, pk, sl2_2, nm2, 0ull, 0.f, acc);
+          tmem_st_32x32b_x16(tmem_p + 32, pk);
+          a2_exp_chunk<0>(v3, pk, sl2_2, nm2, 0ull, 0.f, acc);
+          tmem_st_32x32b_x16(tmem_p + 48, pk);
+        } else {
+          const float kk = 12582912.0f - mref;           // 1.5 * 2^23 - mref, exact for |mref| < 2^22
+          const uint64_t k2 = pack2(kk, kk);
+          const float smin = (mref - 120.0f) * inv_sl2;  // keeps the exponent field of 2^n in range
+          uint32_t pk[16];
+          a2_exp_chunk<NPOLY>(v0, pk, sl2_2, nm2, k2, smin, acc);
+          tmem_st_32x32b_x16(tmem_p, pk);
+          a2_exp_chunk<NPOLY>(v1, pk, sl2_2, nm2, k2, smin, acc);
+          tmem_st_32x32b_x16(tmem_p + 16, pk);
+          a2_exp_chunk<NPOLY>(v2, pk, sl2_2, nm2, k2, smin, acc);
+          tmem_st_32x32b_x16(tmem_p + 32, pk);
+          a2_exp_chunk<NPOLY>(v3, pk, sl2_2, nm2, k2, smin, acc);
+          tmem_st_32x32b_x16(tmem_p + 48, pk);
+        }
+        {
+          float a0, a1, a2, a3;
+          unpack2(fadd2(acc[0], acc[1]), a0, a1);
+          unpack2(fadd2(acc[2], acc[3]), a2, a3);
+          l_run += (a0 + a1) + (a2 + a3);
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -687,7 +779,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (q_ok && write_state)
-        p.state_m[part * p.split_stride_m + q_grow * p.num_heads + head] = m_run + __log2f(l_run) / sl2;
+        p.state_m[part * p.split_stride_m + q_grow * p.num_heads + head] = (mref + __log2f(l_run)) * inv_sl2;
     }
   }
 
@@ -696,6 +788,342 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, A2_TMEM_COLS);
+  }
+}
+
+
+// ================================================================================================================
+// v3: three CTAs per SM.
+//   * one 128-row query tile per CTA as in v2<1>, but key / value steps of 64 rows: a softmax thread holds 64 scores
+//     (112 registers instead of 168) and a CTA needs 64 (S) + 64 (O) + 32 (P) = 160 tensor-memory columns, taken as TWO
+//     allocations (128 + 32; a single allocation must be a power of two), so THREE CTAs fit an SM (480 of 512 columns,
+//     3 x 64 KB shared memory, 3 x 192 x 112 registers).  Every scheduler then holds three softmax warps from three
+//     independent CTAs.  The v2 layout (two per scheduler) leaves the MUFU pipe -- the bound at head_dim 64: 128 x 128
+//     exponentials = 1024 clk per tile against 512 clk of MMA -- 29 % idle, because two warps cannot cover each other's
+//     tensor-memory reads, maxima and barrier round trips (profiles/r2_attn_v2_poly0_ncu.csv: MUFU 71 %, tensor 35 %);
+//   * the intra-CTA pipeline of v2 is kept: S is released as soon as it is in registers, so Q K_{j+1}^T runs under the
+//     exponentials of step j; P has its own columns; O accumulates in tensor memory with lazy rescaling.  (A first form
+//     without that pipeline -- P written in place over S, 128 columns, the chain S_j -> softmax -> P_j V_j -> S_{j+1}
+//     strictly serial per CTA -- measured 494 TFLOP/s on the 8-view global shape against 766 for v2: three CTAs do not
+//     hide ~2000 clk of barrier / MMA latency per step.)
+//   * same exponentials as v2 (a2_exp_chunk): packed fp32x2 arithmetic, integer reference maximum, NPOLY of 16 pairs on
+//     the FMA pipe.
+// Same interface / masking / segment / carried-state semantics; kv_split stays with the v2 two-tile kernel.
+// ================================================================================================================
+constexpr int A3_BN = 64;
+constexpr int A3_STAGES = 3;
+constexpr int A3_KV_BYTES = A3_BN * ATT_D * 2;  // 8 KB per K or V stage
+constexpr int A3_SMEM_BYTES = ATT_TILE_BYTES + 2 * A3_STAGES * A3_KV_BYTES + 256;
+constexpr int A3_THREADS = 6 * 32;  // warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: softmax
+constexpr int A3_TMEM_COLS = 128;   // first allocation: S [0, 64), O [64, 128)
+constexpr int A3_TMEM_P_COLS = 32;  // second allocation: P (64 probabilities as bf16 pairs)
+
+struct Kv64Cursor {
+  int seg = 0, jj = 0;
+  __device__ __forceinline__ int row0(const AttnParams& p) const { return p.seg_row0[seg] + jj * A3_BN; }
+  __device__ __forceinline__ int valid(const AttnParams& p) const { return p.seg_len[seg] - jj * A3_BN; }
+  __device__ __forceinline__ void next(const AttnParams& p) {
+    if ((jj + 1) * A3_BN < p.seg_len[seg]) ++jj;
+    else { ++seg; jj = 0; }
+  }
+};
+
+// Registers: a scheduler (SM sub-partition) owns 16 K registers and the warps of the resident CTAs are spread over the four
+// schedulers: 3 CTAs x 6 warps = 18 warps -> one scheduler holds 5 of them -> at most 16384 / (5 x 32) = 102 registers per
+// thread, i.e. 96.  (At 104-112 registers only TWO CTAs were resident: launch__occupancy_limit_registers = 2.)
+template <int NPOLY>
+__global__ void __maxnreg__(96)
+attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATT_TILE_BYTES;
+  uint8_t* sV = sK + A3_STAGES * A3_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + A3_STAGES * A3_KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + A3_STAGES;
+  uint64_t* v_full = k_empty + A3_STAGES;
+  uint64_t* v_empty = v_full + A3_STAGES;
+  uint64_t* s_full = v_empty + A3_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* p_empty = p_full + 1;  // "P_j V_j has completed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 1);  // [2]
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  // full 128-row query tiles of every (head, sequence) first, the ragged last tiles at the end (they fill the tail wave)
+  const int n_full = p.q_len / ATT_BM;
+  const int hs_count = p.num_heads * p.num_seqs;
+  const int bid = blockIdx.x;
+  int qb, hs;
+  if (bid < n_full * hs_count) {
+    qb = bid % n_full;
+    hs = bid / n_full;
+  } else {
+    qb = n_full;
+    hs = bid - n_full * hs_count;
+  }
+  const int q0 = qb * ATT_BM;
+  const int head = hs % p.num_heads;
+  const int seq = hs / p.num_heads;
+  int n_kv_tiles = 0;
+  for (int sgm = 0; sgm < p.n_segs; ++sgm) n_kv_tiles += (p.seg_len[sgm] + A3_BN - 1) / A3_BN;
+  const bool write_state = (p.flags & MA_ATTN_STATE_OUT) != 0;
+  const bool state_in = (p.flags & MA_ATTN_STATE_IN) != 0;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[ma] attention v3: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int st = 0; st < A3_STAGES; ++st) {
+      mbar_init(&k_full[st], 1);
+      mbar_init(&k_empty[st], 1);
+      mbar_init(&v_full[st], 1);
+      mbar_init(&v_empty[st], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    __syncwarp();
+    // the 128-column block first: three of them tile [0, 384) and the 32-column blocks land behind them, so a CTA that
+    // starts while two others are resident always finds its 128 aligned columns free
+    tmem_alloc(tmem_slot, A3_TMEM_COLS);
+    tmem_alloc(tmem_slot + 1, A3_TMEM_P_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot[0];
+  const uint32_t tmem_pbase = tmem_slot[1];
+  pdl_sync();  // no global memory access before this point
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int q_row = static_cast<int>(seq * p.q_seq_stride) + q0;
+      const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
+      Kv64Cursor cur;
+      for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
+        const int st = j % A3_STAGES;
+        const uint32_t ph = (j / A3_STAGES) & 1;
+        const int row = kv_row0 + cur.row0(p);
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], A3_KV_BYTES);
+        tma_load_2d(sK + st * A3_KV_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, row);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], A3_KV_BYTES);
+        tma_load_2d(sV + st * A3_KV_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, A3_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t tmem_s = tmem_base;
+      const uint32_t tmem_o = tmem_base + 64;
+      auto issue_qk = [&](int j) {
+        const int st = j % A3_STAGES;
+        mbar_wait(&k_full[st], (j / A3_STAGES) & 1);
+        mbar_wait(s_empty, (j & 1) ^ 1);  // the softmax warps hold S of step j-1 in registers
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * A3_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                       idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv_tiles; ++j) {
+        if (j + 1 < n_kv_tiles) issue_qk(j + 1);
+        const int st = j % A3_STAGES;
+        mbar_wait(&v_full[st], (j / A3_STAGES) & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + st * A3_KV_BYTES);
+        const uint32_t acc0 = (j > 0 || state_in) ? 1u : 0u;
+#pragma unroll
+        for (int k = 0; k < A3_BN / 16; ++k)
+          umma_bf16_ts(tmem_o, tmem_pbase + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv, k != 0 ? 1u : acc0);
+        umma_commit(p_empty);
+        umma_commit(&v_empty[st]);
+      }
+    }
+  } else if (warp >= 2) {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base;
+    const uint32_t tmem_o = tmem_base + lane_base + 64;
+    const uint32_t tmem_p = tmem_pbase + lane_base;
+    const int q_idx = q0 + row;
+    const bool q_ok = q_idx < p.q_len;
+    const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
+    const float sl2 = p.scale_log2;
+    float mref = 0.f, l_run = 0.f;
+    if (state_in) {
+      const float m_in = q_ok ? p.state_m[q_grow * p.num_heads + head] : 0.f;
+      mref = rintf(m_in * sl2);
+      const float c_in = q_ok ? fast_exp2(fmaf(m_in, sl2, -mref)) : 0.f;
+      const float* so = p.state_o + q_grow * p.ld_state_o + head * ATT_D;
+#pragma unroll 1
+      for (int c = 0; c < ATT_D; c += 8) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0u;
+        if (q_ok) {
+          const float4 x = *reinterpret_cast<const float4*>(so + c), y = *reinterpret_cast<const float4*>(so + c + 4);
+          o[0] = __float_as_uint(x.x * c_in); o[1] = __float_as_uint(x.y * c_in); o[2] = __float_as_uint(x.z * c_in);
+          o[3] = __float_as_uint(x.w * c_in); o[4] = __float_as_uint(y.x * c_in); o[5] = __float_as_uint(y.y * c_in);
+          o[6] = __float_as_uint(y.z * c_in); o[7] = __float_as_uint(y.w * c_in);
+        }
+        tmem_st_32x32b_x8(tmem_o + c, o);
+      }
+      l_run = c_in;
+      tmem_st_wait();
+      tc_fence_before();
+    }
+    const uint64_t sl2_2 = pack2(sl2, sl2);
+    const float inv_sl2 = 1.0f / sl2;
+
+    Kv64Cursor cur;
+    for (int j = 0; j < n_kv_tiles; ++j, cur.next(p)) {
+      const int kv_valid = cur.valid(p);
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32b_x32(tmem_s, v0);
+      tmem_ld_32x32b_x32(tmem_s + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the tensor core may overwrite it
+      if (kv_valid < A3_BN) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) v0[i] = __float_as_uint(-INFINITY);
+          if (32 + i >= kv_valid) v1[i] = __float_as_uint(-INFINITY);
+        }
+      }
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        mx4[0] = fmaxf(mx4[0], __uint_as_float(v0[i]));
+        mx4[1] = fmaxf(mx4[1], __uint_as_float(v0[16 + i]));
+        mx4[2] = fmaxf(mx4[2], __uint_as_float(v1[i]));
+        mx4[3] = fmaxf(mx4[3], __uint_as_float(v1[16 + i]));
+      }
+      const float mt2 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+      float m_new = mref;
+      bool need = false;
+      if (j == 0 && !state_in) m_new = rintf(mt2);
+      else if (mt2 - mref > A2_RESCALE_LOG2) { need = true; m_new = rintf(mt2); }
+      bool waited = false;
+      if (__any_sync(0xffffffffu, need)) {  // rare
+        if (j > 0) { mbar_wait(p_empty, (j - 1) & 1); waited = true; }  // P_{j-1} V_{j-1} has completed: O is quiescent
+        tc_fence_after();
+        const float alpha = need ? fast_exp2(mref - m_new) : 1.f;
+#pragma unroll 1
+        for (int c = 0; c < ATT_D; c += 8) {
+          uint32_t o[8];
+          tmem_ld_32x32b_x8(tmem_o + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x8(tmem_o + c, o);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        l_run *= alpha;
+      }
+      mref = m_new;
+
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+      const uint64_t nm2 = pack2(-mref, -mref);
+      uint32_t pk[16];
+      // the single P buffer is still read by P_{j-1} V_{j-1}: wait for it only once the first 32 exponentials are done
+      if (NPOLY == 0 || kv_valid < A3_BN) {
+        a2_exp_chunk<0>(v0, pk, sl2_2, nm2, 0ull, 0.f, acc);
+        if (!waited && j > 0) mbar_wait(p_empty, (j - 1) & 1);
+        tc_fence_after();
+        tmem_st_32x32b_x16(tmem_p, pk);
+        a2_exp_chunk<0>(v1, pk, sl2_2, nm2, 0ull, 0.f, acc);
+        tmem_st_32x32b_x16(tmem_p + 16, pk);
+      } else {
+        const float kk = 12582912.0f - mref;
+        const uint64_t k2 = pack2(kk, kk);
+        const float smin = (mref - 120.0f) * inv_sl2;
+        a2_exp_chunk<NPOLY>(v0, pk, sl2_2, nm2, k2, smin, acc);
+        if (!waited && j > 0) mbar_wait(p_empty, (j - 1) & 1);
+        tc_fence_after();
+        tmem_st_32x32b_x16(tmem_p, pk);
+        a2_exp_chunk<NPOLY>(v1, pk, sl2_2, nm2, k2, smin, acc);
+        tmem_st_32x32b_x16(tmem_p + 16, pk);
+      }
+      {
+        float a0, a1, a2, a3;
+        unpack2(fadd2(acc[0], acc[1]), a0, a1);
+        unpack2(fadd2(acc[2], acc[3]), a2, a3);
+        l_run += (a0 + a1) + (a2 + a3);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    mbar_wait(p_empty, (n_kv_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    uint32_t o[32];
+#pragma unroll 1
+    for (int c = 0; c < ATT_D; c += 32) {
+      tmem_ld_32x32b_x32(tmem_o + c, o);
+      tmem_ld_wait();
+      if (q_ok && write_state) {
+        float4* so = reinterpret_cast<float4*>(p.state_o + q_grow * p.ld_state_o + head * ATT_D + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          so[i] = make_float4(__uint_as_float(o[4 * i]) * inv_l, __uint_as_float(o[4 * i + 1]) * inv_l,
+                              __uint_as_float(o[4 * i + 2]) * inv_l, __uint_as_float(o[4 * i + 3]) * inv_l);
+      } else if (q_ok) {
+        __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D + c;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<uint4*>(optr)[q] =
+              make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l),
+                         pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
+      }
+    }
+    if (q_ok && write_state) p.state_m[q_grow * p.num_heads + head] = (mref + __log2f(l_run)) * inv_sl2;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_pbase, A3_TMEM_P_COLS);
+    tmem_dealloc(tmem_base, A3_TMEM_COLS);
   }
 }
 
@@ -847,12 +1275,6 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     int rc = make_tmap_bf16(&tv, v, 2, dims, str, box);
     if (rc != MA_OK) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
-    MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       ATT_SMEM_BYTES));
-    configured = true;
-  }
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.q_len = q_len;
@@ -863,21 +1285,24 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.v_col0 = v_col0;
   p.o_col0 = o_col0;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  int dev = 0;
+  MA_CHECK_CUDA(cudaGetDevice(&dev));
+  MA_REQUIRE(dev >= 0 && dev < 64, "ma_attention_fwd: device ordinal %d out of range", dev);
   static const bool use_v1 = [] {
     const char* e = getenv("MA_ATTN_V1");
     return e != nullptr && e[0] == '1';
   }();
   if (use_v1) {
+    static bool configured[64] = {};  // the large-shared-memory opt-in is per device
+    if (!configured[dev]) {
+      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATT_SMEM_BYTES));
+      configured[dev] = true;
+    }
     MA_REQUIRE(p.kv_split == 1, "ma_attention_fwd: kv_split is not supported by the v1 kernel");
     dim3 grid((q_len + ATT_BM - 1) / ATT_BM, num_heads, num_seqs);
     attention_fwd_tcgen05_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
   } else {
-    static bool configured2 = false;
-    if (!configured2) {
-      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Cfg<2>::SMEM_BYTES));
-      MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2Cfg<1>::SMEM_BYTES));
-      configured2 = true;
-    }
     // one query tile per CTA, two CTAs per SM: measured faster than two tiles per CTA on every shape of the path (B200,
     // same-box A/B: encoder 521-571 vs 446-462, frame 535-540 vs 482, 8-view global 765 vs 709 TFLOP/s); the two-tile
     // form is kept for the kv-split mode and for A/B runs (MA_ATTN_NQT=2)
@@ -885,15 +1310,47 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       const char* e = getenv("MA_ATTN_NQT");
       return e ? atoi(e) : 0;
     }();
-    const int nqt = p.kv_split > 1 ? 2 : (nqt_env == 1 || nqt_env == 2) ? nqt_env : 1;
-    if (nqt == 2) {
-      MA_CHECK_CUDA(launch_kernel(attention_fwd_v2_kernel<2>, dim3(grid_ctas), dim3(A2Cfg<2>::THREADS), A2Cfg<2>::SMEM_BYTES,
-                                  static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));
-    } else {
-      const int ctas = ((q_len + ATT_BM - 1) / ATT_BM) * num_heads * num_seqs;
-      MA_CHECK_CUDA(launch_kernel(attention_fwd_v2_kernel<1>, dim3(ctas), dim3(A2Cfg<1>::THREADS), A2Cfg<1>::SMEM_BYTES,
-                                  static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));
+    // pairs of every 16 whose exponential runs on the FMA pipe (a2_exp_chunk); MA_ATTN_POLY selects a variant for A/B runs
+    static const int poly_env = [] {
+      const char* e = getenv("MA_ATTN_POLY");
+      return e ? atoi(e) : -1;
+    }();
+    using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+    struct Variant { int nqt, npoly; KernelFn fn; };  // nqt 3 = the v3 kernel (three CTAs per SM, 64-row kv steps)
+    static const Variant variants[] = {
+        {3, 0, attention_fwd_v3_kernel<0>}, {3, 4, attention_fwd_v3_kernel<4>}, {3, 6, attention_fwd_v3_kernel<6>},
+        {3, 7, attention_fwd_v3_kernel<7>}, {3, 8, attention_fwd_v3_kernel<8>}, {3, 10, attention_fwd_v3_kernel<10>},
+        {1, 0, attention_fwd_v2_kernel<1, 0>}, {1, 7, attention_fwd_v2_kernel<1, 7>},
+        {2, 0, attention_fwd_v2_kernel<2, 0>},
+    };
+    const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : 3;
+    const int want_poly = poly_env >= 0 ? poly_env : A2_DEFAULT_POLY;
+    const Variant* pick = nullptr;
+    for (const Variant& v : variants)
+      if (v.nqt == nqt && (pick == nullptr || abs(v.npoly - want_poly) < abs(pick->npoly - want_poly))) pick = &v;
+    const int smem_bytes = nqt == 3 ? A3_SMEM_BYTES : nqt == 2 ? A2Cfg<2>::SMEM_BYTES : A2Cfg<1>::SMEM_BYTES;
+    const int threads = nqt == 3 ? A3_THREADS : nqt == 2 ? A2Cfg<2>::THREADS : A2Cfg<1>::THREADS;
+    static bool configured2[64][sizeof(variants) / sizeof(variants[0])] = {};
+    const int vi = static_cast<int>(pick - variants);
+    if (!configured2[dev][vi]) {
+      MA_CHECK_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+      MA_CHECK_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured2[dev][vi] = true;
     }
+    const int ctas = nqt == 2 ? grid_ctas : ((q_len + ATT_BM - 1) / ATT_BM) * num_heads * num_seqs;
+    if (nqt == 3) {  // key / value boxes of 64 rows
+      const uint32_t box64[2] = {ATT_D, A3_BN};
+      uint64_t dims[2] = {(uint64_t)ldk, (uint64_t)kv_rows};
+      uint64_t str[1] = {(uint64_t)ldk * 2};
+      int rc = make_tmap_bf16(&tk, k, 2, dims, str, box64);
+      if (rc != MA_OK) return rc;
+      dims[0] = (uint64_t)ldv;
+      str[0] = (uint64_t)ldv * 2;
+      rc = make_tmap_bf16(&tv, v, 2, dims, str, box64);
+      if (rc != MA_OK) return rc;
+    }
+    MA_CHECK_CUDA(launch_kernel(pick->fn, dim3(ctas), dim3(threads), smem_bytes, static_cast<cudaStream_t>(stream), pdl_enabled(),
+                                tq, tk, tv, p));
   }
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;

@@ -34,6 +34,17 @@ __device__ __forceinline__ void pdl_sync() {
   pdl_launch_dependents();
 }
 
+// Register re-balancing between the warpgroups (4 consecutive warps) of a CTA: producer / issuer warps give registers back,
+// the math warpgroup takes them.  The kernel is launched with the (small) per-thread count of its launch bound.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(
@@ -72,6 +83,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (mbarrier.try_wait may suspend the thread for a hardware-defined time; a polling state machine wants this)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -235,6 +260,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -388,6 +421,54 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// ----------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 -- one issue slot for two lanes of work; the FMA-pipe math rate is
+// unchanged, tools/ubench.cu) on a 64-bit register pair {lo, hi}
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// 2^x for a pair of scores on the FMA pipe instead of the MUFU (16 ex2 / clk / SM is the attention bottleneck at head_dim
+// 64): x = s * sl2 - m with m an INTEGER, so with K = 1.5 * 2^23 - m the sum r = fl(s * sl2 + K) carries n = round(x) in
+// its low mantissa bits (r = 1.5 * 2^23 + n), g = s * sl2 - (r - K) in [-0.5, 0.5] is exact, 2^g is a cubic (minimax,
+// relative error 7.6e-5 -- the result is rounded to bf16, 2^-9) and 2^n goes into the exponent field with one shift-add.
+// The caller clamps s so that n >= -126.
+__device__ __forceinline__ void exp2_poly_pair(uint64_t s2, uint64_t sl2_2, uint64_t k2, float& ea, float& eb) {
+  const uint64_t c3 = pack2(0.055205505f, 0.055205505f), c2 = pack2(0.24261397f, 0.24261397f);
+  const uint64_t c1 = pack2(0.69325477f, 0.69325477f), c0 = pack2(0.9999277f, 0.9999277f);
+  const uint64_t r2 = ffma2(s2, sl2_2, k2);
+  const uint64_t g2 = ffma2(s2, sl2_2, fsub2(k2, r2));
+  uint64_t p2 = ffma2(g2, c3, c2);
+  p2 = ffma2(p2, g2, c1);
+  p2 = ffma2(p2, g2, c0);
+  float ra, rb, pa, pb;
+  unpack2(r2, ra, rb);
+  unpack2(p2, pa, pb);
+  ea = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23));
+  eb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23));
 }
 
 // erf with |abs err| < 1.5e-7 (Abramowitz & Stegun 7.1.26) -- far below bf16 output resolution.
