@@ -373,7 +373,7 @@ struct A2Cfg {
   static constexpr int BMQ = NQT * ATT_BM;     // query rows per CTA
 };
 constexpr float A2_RESCALE_LOG2 = 8.0f;
-constexpr int A2_DEFAULT_POLY = 7;  // of 16 score pairs: measured best split between the MUFU and the FMA pipe
+constexpr int A2_DEFAULT_POLY = 0;  // of 16 score pairs on the FMA pipe: 0 measured fastest
 
 // Exponentials of one 32-column chunk of a score row (16 register pairs) -> 16 packed bf16x2 probabilities + row-sum
 // contribution.  NPOLY of every 16 pairs are evaluated on the FMA pipe (exp2_poly_pair), the rest on the MUFU; all
@@ -1318,12 +1318,15 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     using KernelFn = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
     struct Variant { int nqt, npoly; KernelFn fn; };  // nqt 3 = the v3 kernel (three CTAs per SM, 64-row kv steps)
     static const Variant variants[] = {
-        {3, 0, attention_fwd_v3_kernel<0>}, {3, 4, attention_fwd_v3_kernel<4>}, {3, 6, attention_fwd_v3_kernel<6>},
-        {3, 7, attention_fwd_v3_kernel<7>}, {3, 8, attention_fwd_v3_kernel<8>}, {3, 10, attention_fwd_v3_kernel<10>},
+        {3, 0, attention_fwd_v3_kernel<0>}, {3, 7, attention_fwd_v3_kernel<7>},
         {1, 0, attention_fwd_v2_kernel<1, 0>}, {1, 7, attention_fwd_v2_kernel<1, 7>},
         {2, 0, attention_fwd_v2_kernel<2, 0>},
     };
-    const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : 3;
+    // Default (same-box A/B on B200, tools/bench_kernels.py, TFLOP/s v3 / v2<1>): 1370-key sequences (encoder, frame
+    // attention) 586 / 572 and 552 / 535 at 8 views, 658 / 622 and 634 / 604 at 24 views -> v3; one long sequence (global
+    // attention) 740 / 766 at 8 views, 786 / 799 at 24 views -> v2<1>.  Every exponential on the MUFU (NPOLY = 0): moving a
+    // share of them to the FMA pipe was slower in both kernels (v2<1>: 766 -> 646 at 7 of 16; v3: 740 -> 720).
+    const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : (kv_len <= 4096 ? 3 : 1);
     const int want_poly = poly_env >= 0 ? poly_env : A2_DEFAULT_POLY;
     const Variant* pick = nullptr;
     for (const Variant& v : variants)

@@ -87,8 +87,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int tm = t % tiles_m;
-        const int n0 = (t / tiles_m) * BN;
+        int tm, tn;
+        raster_tile(t, tiles_n, static_cast<int>(gridDim.x), tm, tn);
+        const int n0 = tn * BN;
         if (cg.mode) {
           const int img = tm / tiles_per_img;
           const int r = tm - img * tiles_per_img;
@@ -153,8 +154,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = t % tiles_m;
-      const int n0 = (t / tiles_m) * BN;
+      int tm, tn;
+      raster_tile(t, tiles_n, static_cast<int>(gridDim.x), tm, tn);
+      const int n0 = tn * BN;
       // output row of this thread's accumulator lane: tile row r = quarter*32 + lane
       int m;
       bool row_ok;

@@ -91,8 +91,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const int tm = (t % tiles_m) * 2 + static_cast<int>(cta);  // this CTA's 128-row tile
-        const int n0 = (t / tiles_m) * BN + static_cast<int>(cta) * (BN / 2);
+        int tm2, tn;
+        raster_tile(t, tiles_n, num_clusters, tm2, tn);
+        const int tm = tm2 * 2 + static_cast<int>(cta);  // this CTA's 128-row tile
+        const int n0 = tn * BN + static_cast<int>(cta) * (BN / 2);
         if (cg.mode) {
           // a row tile past the end (odd tile count) reads image index n: fully out of bounds -> zero fill
           const int img = tm / tiles_per_img;
@@ -159,8 +161,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int tm = (t % tiles_m) * 2 + static_cast<int>(cta);
-      const int n0 = (t / tiles_m) * BN;
+      int tm2, tn;
+      raster_tile(t, tiles_n, num_clusters, tm2, tn);
+      const int tm = tm2 * 2 + static_cast<int>(cta);
+      const int n0 = tn * BN;
       int m;
       bool row_ok;
       if (cg.mode) {

@@ -12,6 +12,22 @@ constexpr int GEMM_BK = 64;
 // tile (bh x bw output pixels of one image) and of tap (ky,kx) is the input window shifted by (ky-1, kx-1): ONE 4-D TMA
 // box {64 channels, bw, bh, 1} whose out-of-bounds pixels (the zero padding) and channels are zero-filled by the TMA
 // unit -- no im2col matrix is ever written.  K runs over 9 taps x ceil(C/64) channel blocks.
+// Tile raster of the persistent GEMMs: tile t of tiles_m x tiles_n -> (row tile, column tile).  Concurrently running
+// workers (CTAs / CTA pairs) take consecutive t.  M-fastest order made every worker of a wave stream a DIFFERENT X row
+// tile against the same W panel, so X was re-read once per column panel -- from DRAM when X + residual exceed the L2 (ncu,
+// 10960 x 1024 x 4096: 260 MB read for 143 MB algorithmic).  Banded order: `band` row tiles x all column tiles are in flight
+// together, column-fastest, so the tiles_n workers sharing an X row tile run at the same time (one DRAM read, L2 hits for
+// the rest) while the W panels (a few MB) stay L2 resident.
+__device__ __forceinline__ void raster_tile(int t, int tiles_n, int workers, int& tm, int& tn) {
+  int band = workers / tiles_n;
+  band = band < 1 ? 1 : band;
+  const int per_band = band * tiles_n;
+  const int b = t / per_band;
+  const int r = t - b * per_band;  // the last band is shorter, but every earlier one is full: no special case
+  tm = b * band + r / tiles_n;
+  tn = r - (r / tiles_n) * tiles_n;
+}
+
 struct ConvGeom {
   int mode;  // 0 = plain GEMM
   int H, W, C;
