@@ -45,6 +45,10 @@ int ma_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * setting.  Initial value: environment variable MA_PDL, else the build default.  The reference has no counterpart (it
  * relies on the PyTorch stream order, model.py:1477-1909). */
 int ma_set_pdl(int enabled);
+/* Which kernel the last ma_gemm_bf16 / ma_conv3x3_bf16 call of THIS thread launched, as a block_n code (64 / 128 / 256 = the
+ * one-CTA kernel gemm_bf16_tcgen05_kernel<block_n>, 2128 / 2256 = the CTA-pair kernel gemm_bf16_2cta_kernel<block_n - 2000>);
+ * 0 before the first call.  Measurement aid (bench.py names the dominant kernel from it); no reference counterpart. */
+int ma_last_gemm_block(void);
 
 /* ---- GEMM: Y = epilogue(X . W^T) ------------------------------------------------------------
  * Replaces every nn.Linear / 1x1 conv / im2col'ed conv on the path (cuBLASLt / cuDNN calls in the

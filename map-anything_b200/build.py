@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objs = [OBJ / (s.stem + ".o") for s in srcs]
     if jobs or not OUT.exists():
         cmd = [_nvcc(), "-shared", "-o", str(OUT), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a",
-               "-cudart", "static"]
+               "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)

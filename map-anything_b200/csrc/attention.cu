@@ -1285,15 +1285,13 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.v_col0 = v_col0;
   p.o_col0 = o_col0;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  int dev = 0;
-  MA_CHECK_CUDA(cudaGetDevice(&dev));
-  MA_REQUIRE(dev >= 0 && dev < 64, "ma_attention_fwd: device ordinal %d out of range", dev);
+  const int dev = current_device();
   static const bool use_v1 = [] {
     const char* e = getenv("MA_ATTN_V1");
     return e != nullptr && e[0] == '1';
   }();
   if (use_v1) {
-    static bool configured[64] = {};  // the large-shared-memory opt-in is per device
+    static bool configured[MA_MAX_DEVICES] = {};  // the large-shared-memory opt-in is per device
     if (!configured[dev]) {
       MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          ATT_SMEM_BYTES));
@@ -1333,7 +1331,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
       if (v.nqt == nqt && (pick == nullptr || abs(v.npoly - want_poly) < abs(pick->npoly - want_poly))) pick = &v;
     const int smem_bytes = nqt == 3 ? A3_SMEM_BYTES : nqt == 2 ? A2Cfg<2>::SMEM_BYTES : A2Cfg<1>::SMEM_BYTES;
     const int threads = nqt == 3 ? A3_THREADS : nqt == 2 ? A2Cfg<2>::THREADS : A2Cfg<1>::THREADS;
-    static bool configured2[64][sizeof(variants) / sizeof(variants[0])] = {};
+    static bool configured2[MA_MAX_DEVICES][sizeof(variants) / sizeof(variants[0])] = {};
     const int vi = static_cast<int>(pick - variants);
     if (!configured2[dev][vi]) {
       MA_CHECK_CUDA(cudaFuncSetAttribute(pick->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

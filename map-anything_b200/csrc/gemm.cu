@@ -205,7 +205,8 @@ template <int BN>
 static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
                        const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg = ConvGeom{}) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
+  static bool configured_dev[MA_MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     MA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
@@ -260,6 +261,8 @@ static int pick_block_n(int M, int N, int tiles_m_override = 0) {
   }
   return best;
 }
+
+thread_local int g_last_block = 0;
 
 static bool valid_block_code(int bn) {
   return bn == 64 || bn == 128 || bn == 256 || bn == MA_GEMM_2CTA + 128 || bn == MA_GEMM_2CTA + 256;
@@ -319,6 +322,7 @@ extern "C" int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const 
   const int tiles_m = n * cg.tiles_x * cg.tiles_y;
   int bn = block_n ? block_n : pick_block_n(M, Cout, tiles_m);
   MA_REQUIRE(valid_block_code(bn), "ma_conv3x3_bf16: bad block_n %d", block_n);
+  g_last_block = bn;
   const bool pair = bn > MA_GEMM_2CTA;
   if (pair) bn -= MA_GEMM_2CTA;
 
@@ -347,6 +351,8 @@ extern "C" int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const 
   }
 }
 
+extern "C" int ma_last_gemm_block(void) { return ma::g_last_block; }
+
 extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, int M, int N, int K,
                             const ma_gemm_epilogue* epi, int block_n, void* stream) {
   using namespace ma;
@@ -361,6 +367,7 @@ extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t l
   }
   int bn = block_n ? block_n : pick_block_n(M, N);
   MA_REQUIRE(valid_block_code(bn), "ma_gemm_bf16: bad block_n %d", block_n);
+  g_last_block = bn;
   const bool pair = bn > MA_GEMM_2CTA;
   if (pair) bn -= MA_GEMM_2CTA;
 

@@ -212,7 +212,8 @@ template <int BN>
 static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& tout, int epi_mode,
                         const ma_gemm_epilogue& ep, int M, int N, int K, cudaStream_t stream, const ConvGeom& cg) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool configured = false;
+  static bool configured_dev[MA_MAX_DEVICES] = {};
+  bool& configured = configured_dev[current_device()];
   if (!configured) {
     MA_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;

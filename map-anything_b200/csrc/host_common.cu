@@ -94,14 +94,21 @@ bool pdl_enabled() {
   return mode != 0;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MA_MAX_DEVICES) return 0;
+  return dev;
+}
+
 int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static int sms[MA_MAX_DEVICES] = {};  // per device ordinal: a process may drive several GPUs
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 }  // namespace ma

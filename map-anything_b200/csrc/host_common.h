@@ -40,6 +40,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int swizzle_bytes);
 
+// Per-device state (SM count, the large-dynamic-shared-memory opt-in of each kernel) is cached per device ordinal: the
+// same process may run the model on several GPUs (model.to("cuda:1")).
+constexpr int MA_MAX_DEVICES = 64;
+int current_device();
 int device_sm_count();
 
 // Programmatic dependent launch of the chained hot-path kernels (GEMM, attention, LayerNorm): MA_PDL=0/1, see ptx.cuh.

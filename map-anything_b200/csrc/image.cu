@@ -346,7 +346,8 @@ static int launch_h_vec(const uint8_t* src, int64_t row_stride, int64_t frame_st
                         cudaStream_t stream) {
   // staged row + misalignment + the zero-coefficient taps' bytes + the funnel shift's extra word
   const size_t smem = (static_cast<size_t>(sx1 - sx0) * 3 + 3 + 3 * KMAX + 8 + 15) & ~static_cast<size_t>(15);
-  static size_t configured = 0;
+  static size_t configured_dev[MA_MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device()];
   if (smem > 48 * 1024 && smem > configured) {
     MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_vec_kernel<KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
@@ -364,7 +365,8 @@ static int launch_h_dp4a(const uint8_t* src, int64_t row_stride, int64_t frame_s
   // per plane: the staged pixels + the window overhang of the last output (zero coefficients) + the funnel shift's word
   const int plane_words = ((sx1 - sx0 + 3) >> 2) + NW4 + 2;
   const size_t smem = static_cast<size_t>(3) * plane_words * 4;
-  static size_t configured = 0;
+  static size_t configured_dev[MA_MAX_DEVICES] = {};
+  size_t& configured = configured_dev[current_device()];
   if (smem > 48 * 1024 && smem > configured) {
     MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_dp4a_kernel<NW4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = 200 * 1024;
@@ -436,7 +438,8 @@ extern "C" int ma_resample_h_u8rgb(const uint8_t* src, int64_t src_row_stride, i
   const size_t smem = static_cast<size_t>(row_bytes) + 8;
   MA_REQUIRE(smem <= 200 * 1024, "ma_resample_h_u8rgb: source rows of %d pixels do not fit shared memory", sx1 - sx0);
   if (smem > 48 * 1024) {
-    static size_t configured = 0;
+    static size_t configured_dev[MA_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device()];
     if (smem > configured) {
       MA_CHECK_CUDA(cudaFuncSetAttribute(resample_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = 200 * 1024;

@@ -32,13 +32,15 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 class Lin:
     """Packed y = x W^T + b."""
 
-    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], kpad: int = 0):
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], kpad: int = 0, algo_nk=None):
         w2 = w.detach().reshape(w.shape[0], -1)
+        k0 = w2.shape[1]
         if kpad and kpad > w2.shape[1]:
             w2 = torch.cat([w2, w2.new_zeros(w2.shape[0], kpad - w2.shape[1])], dim=1)
         self.w = _bf16(w2)
         self.b = _f32(b) if b is not None else None
         self.n, self.k = self.w.shape
+        ops.register_algorithmic_shape(self.w, *(algo_nk or (self.n, k0)))   # zero padding is not algorithmic work
 
 
 class Lin3:
@@ -46,7 +48,7 @@ class Lin3:
     [w_hi | w_hi | w_lo] per `group` input channels, matching activations split as [a_hi | a_lo | a_hi].
     group = K for a Linear / 1x1 conv; group = Cin for the (tap-major) im2col layout of a 3x3 conv."""
 
-    def __init__(self, w2d: torch.Tensor, b: Optional[torch.Tensor], group: Optional[int] = None):
+    def __init__(self, w2d: torch.Tensor, b: Optional[torch.Tensor], group: Optional[int] = None, algo_nk=None):
         w2d = w2d.detach().float().reshape(w2d.shape[0], -1)
         n, k = w2d.shape
         group = group or k
@@ -56,6 +58,7 @@ class Lin3:
         self.w = torch.cat([hi, hi, lo], dim=2).reshape(n, 3 * k).contiguous()
         self.b = _f32(b) if b is not None else None
         self.n, self.k = n, 3 * k
+        ops.register_algorithmic_shape(self.w, *(algo_nk or (n, k)))   # the 3x of the split is not algorithmic work
 
 
 def _conv3x3(conv: nn.Conv2d) -> Lin:
@@ -88,8 +91,8 @@ def _conv3x3_padded(conv: nn.Conv2d, cin_pad: int, cout_pad: int, split: bool = 
     bp = b.new_zeros(cout_pad)
     bp[:cout] = b
     if split:
-        return Lin3(wp.reshape(cout_pad, 9 * cin_pad), bp, group=cin_pad)
-    return Lin(wp.reshape(cout_pad, 9 * cin_pad), bp)
+        return Lin3(wp.reshape(cout_pad, 9 * cin_pad), bp, group=cin_pad, algo_nk=(cout, 9 * cin))
+    return Lin(wp.reshape(cout_pad, 9 * cin_pad), bp, algo_nk=(cout, 9 * cin))
 
 
 def _linear_padded(w: torch.Tensor, b: Optional[torch.Tensor], kpad: int, npad: int) -> Lin:
@@ -99,7 +102,7 @@ def _linear_padded(w: torch.Tensor, b: Optional[torch.Tensor], kpad: int, npad: 
     bp = w.new_zeros(npad)
     if b is not None:
         bp[:w.shape[0]] = b.detach().float()
-    return Lin(wp, bp)
+    return Lin(wp, bp, algo_nk=(w.shape[0], w.shape[1]))
 
 
 class DenseEncW:
@@ -248,6 +251,9 @@ class Engine:
         # views 311.1 vs 301.6 views/s (fewer, larger launches); MA_DPT_CHUNK overrides for A/B runs
         self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "8")))
         self.dpt_chunk = self.dpt_chunk_default
+        # measurement aid (bench.py `strong` record): when a list, every sharded global block appends the CUDA events that
+        # bracket its wait for the K/V all-gather on the compute stream
+        self.ag_wait_events = None
 
     # ------------------------------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.bfloat16):
@@ -379,7 +385,14 @@ class Engine:
             sm.fill_(float("-inf"))                          # unused partial slots are skipped by the merge
             ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=(so[:s_l], sm[:s_l]),
                           state_out=True, kv_split=s_l, kv_split_from=f_l, **common)
+            if self.ag_wait_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record()
             work.wait()                                      # current stream waits for the gathered slots
+            if self.ag_wait_events is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                self.ag_wait_events.append((e0, e1))
             ops.attention(q, K, Vv, None, kv_len=kv_r, kv_segments=remote, state=(so[s_l:s_l + s_r], sm[s_l:s_l + s_r]),
                           state_out=True, kv_split=s_r, kv_split_from=f_r, **common)
             ops.attention_merge((so[:s_l + s_r], sm[:s_l + s_r]), a, num_heads=heads)

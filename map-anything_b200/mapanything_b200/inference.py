@@ -30,7 +30,9 @@ IMAGE_NORMALIZATION_DICT = {
 }
 
 
-def validate_input_views_for_inference(views: List[Dict[str, Any]]) -> List[Dict[str, Any]]:
+def validate_input_views_for_inference(views: List[Dict[str, Any]], first_view_is_reference: bool = True) -> List[Dict[str, Any]]:
+    """reference utils/inference.py:128-199.  first_view_is_reference=False (ranks > 0 of a view-sharded scene, whose first
+    local view is not the scene's view 0) skips the reference-view pose rule, which is then checked scene-wide."""
     if not views:
         raise ValueError("At least one view must be provided")
     views_with_poses = []
@@ -59,7 +61,7 @@ def validate_input_views_for_inference(views: List[Dict[str, Any]]) -> List[Dict
             )
         if "camera_poses" in provided_keys:
             views_with_poses.append(view_idx)
-    if views_with_poses and 0 not in views_with_poses:
+    if first_view_is_reference and views_with_poses and 0 not in views_with_poses:
         raise ValueError(
             f"Camera pose constraint violation: Views {views_with_poses} have camera_poses, "
             f"but view 0 (reference view) does not. When using camera_poses, the first view "
@@ -169,6 +171,16 @@ def postprocess_model_outputs_for_inference(
     confidence_percentile: float = 10,
 ) -> List[Dict[str, torch.Tensor]]:
     """Same outputs as the reference function, computed per view on the device (no D2H, no numpy loop)."""
+    dev = next((t.device for r in raw_outputs for t in r.values() if torch.is_tensor(t) and t.is_cuda), None)
+    if dev is None:
+        raise RuntimeError("postprocess_model_outputs_for_inference: mapanything_b200 has no CPU path (outputs must be CUDA tensors)")
+    with torch.cuda.device(dev):
+        return _postprocess(raw_outputs, input_views, apply_mask, mask_edges, edge_normal_threshold, edge_depth_threshold,
+                            apply_confidence_mask, confidence_percentile)
+
+
+def _postprocess(raw_outputs, input_views, apply_mask, mask_edges, edge_normal_threshold, edge_depth_threshold,
+                 apply_confidence_mask, confidence_percentile):
     processed = []
     for raw, view in zip(raw_outputs, input_views):
         out = dict(raw)

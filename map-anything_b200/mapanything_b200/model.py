@@ -14,7 +14,6 @@ for unknown types.
 """
 from __future__ import annotations
 
-import warnings
 from functools import partial
 from typing import Any, Callable, Dict, List, Type, Union
 
@@ -158,8 +157,28 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         ok = (a.get("ray_directions_mode", "linear") == "linear" and a.get("ray_directions_normalize_to_unit_sphere", True)
               and a.get("depth_mode", "exp") == "exp" and a.get("confidence_type", "exp") == "exp"
               and float(a.get("confidence_vmin", 1)) == 1.0 and float(a.get("depth_vmin", 0)) == 0.0)
+        inf = float("inf")
+        ok = (ok and a.get("ray_directions_vmin", -inf) == -inf and a.get("ray_directions_vmax", inf) == inf
+              and not a.get("ray_directions_normalize_to_unit_image_plane", False)
+              and not a.get("ray_directions_clamp_min_of_z_dir", False)
+              and a.get("depth_vmax", inf) == inf and a.get("confidence_vmax", inf) == inf)
         if not ok:
             raise ValueError("the fused decode kernel implements the released dense adaptor parameters only")
+        # the same kernel hard-codes the pose adaptor (linear translation, linear + normalised quaternion) and the scale
+        # adaptor (exp, clamped below at 1e-8): reject anything else instead of silently decoding it differently
+        pa = cfg.get("pose_adaptor", {})
+        ok = (pa.get("cam_trans_mode", "linear") == "linear" and pa.get("quaternions_mode", "linear") == "linear"
+              and pa.get("quaternions_normalize", True) and pa.get("cam_trans_vmin", -inf) == -inf
+              and pa.get("cam_trans_vmax", inf) == inf and pa.get("quaternions_vmin", -inf) == -inf
+              and pa.get("quaternions_vmax", inf) == inf)
+        if not ok:
+            raise ValueError("the fused decode kernel implements the released pose adaptor parameters only "
+                             "(linear translation, linear normalised quaternion, no clamping)")
+        sa = cfg.get("scale_adaptor", {})
+        ok = (sa.get("mode", "exp") == "exp" and abs(float(sa.get("vmin", 1e-8)) - 1e-8) < 1e-12
+              and sa.get("vmax", inf) == inf)
+        if not ok:
+            raise ValueError("the fused decode kernel implements the released scale adaptor parameters only (exp, vmin 1e-8)")
         self.scene_rep_type = "raydirs+depth+pose+confidence+mask"
 
     def _load_pretrained_weights(self):
@@ -198,7 +217,8 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
     def engine(self) -> Engine:
         """Packs the parameters for the kernels (once per weight/device change)."""
         if self._engine is None or self._engine.device != self.device:
-            self._engine = Engine(self)
+            with torch.cuda.device(self.device):  # weight packing launches kernels: on the module's device, not the current one
+                self._engine = Engine(self)
         return self._engine
 
     # ------------------------------------------------------------------------------------------ multi-GPU
@@ -218,85 +238,140 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         self._shard_counts = None
         return self
 
-    def _geometric_inputs_active(self, views) -> bool:
-        """With p in {0,1} (always the case inside infer) the masks of model.py:1155-1201 are deterministic: a modality is
-        fused iff overall_prob and (1 - dropout_prob) and its own prob are all 1 and a view provides it.  When nothing
-        is active the reference still runs all five encoders on zeros and multiplies by 0; the result is
-        exactly LayerNorm(encoder features), which is what this path computes directly."""
-        g = self.geometric_input_config
-        for name in ("overall_prob", "dropout_prob", "ray_dirs_prob", "depth_prob", "cam_prob"):
-            if g[name] not in (0, 1, 0.0, 1.0):
-                raise ValueError(
-                    f"geometric_input_config[{name!r}]={g[name]}: stochastic input dropout is a training feature; "
-                    "inference needs probabilities in {0, 1}"
-                )
-        if not (g["overall_prob"] == 1 and g["dropout_prob"] == 0):
-            return False
-        keys = []
-        if g["ray_dirs_prob"] == 1:
-            keys.append("ray_directions_cam")
-        if g["depth_prob"] == 1:
-            keys.append("depth_along_ray")
-        if g["cam_prob"] == 1:
-            keys += ["camera_pose_quats"]
-        return any(k in v for v in views for k in keys)
+    def _sample_geometric_gates(self, views, comm=None) -> Dict[str, Any]:
+        """The random input masks of reference model.py:1155-1201 for one batch item, drawn on the host:
+          overall_prob (per batch item), 1 - dropout_prob (per view), ray_dirs_prob / depth_prob / cam_prob (per batch item),
+          sparse_depth_prob (one coin), depth_scale_norm_all_prob / pose_scale_norm_all_prob (per view).
+        With probabilities in {0, 1} -- always the case inside infer() -- nothing is random and a modality is fused iff a
+        view provides it.  When nothing is active the reference still runs all five encoders on zeros and multiplies by 0
+        (SURVEY F8); the result is exactly LayerNorm(encoder features), which is what this path computes directly.
 
-    def _fuse_geometric_inputs(self, eng, feat, views, b, N, plan, comm):
-        """Rows a7-a11 of SURVEY 8a for batch item b: with probabilities in {0,1} the reference's random masks
-        (model.py:1155-1201) reduce to "the view provides the modality".  Encodes ray directions, depth (+ its metric scale)
-        and the camera poses relative to view 0 (+ their metric scale) and adds them to the encoder features in place."""
+        View-sharded (comm with world > 1): the per-batch-item coins are drawn on rank 0 and broadcast (one coin per scene,
+        as in the reference), and "does ANY view of the scene use the modality" is an all-reduce of three flags -- the
+        fusion path contains a collective (the pose all-gather), so every rank must take the same branch even when only
+        some shards carry geometric inputs."""
+        g = self.geometric_input_config
+        V = len(views)
+        sharded = comm is not None and comm.world > 1
+
+        def coin(p: float, u: float) -> bool:
+            return u < float(p)   # p = 1 -> always, p = 0 -> never (u in [0, 1))
+
+        names = ("overall_prob", "ray_dirs_prob", "depth_prob", "cam_prob", "sparse_depth_prob")
+        if all(float(g.get(n, 0.0)) in (0.0, 1.0) for n in names):
+            u = [0.0] * len(names)
+        else:
+            ut = torch.rand(len(names))
+            if sharded:
+                ut = comm.broadcast(ut.to(self.device), src=0).cpu()
+            u = ut.tolist()
+        overall, ray_b, depth_b, cam_b, sparse = (coin(g.get(n, 0.0), x) for n, x in zip(names, u))
+
+        def per_view(p: float) -> List[bool]:
+            p = float(p)
+            if p in (0.0, 1.0):
+                return [p == 1.0] * V
+            return [bool(x) for x in (torch.rand(V) < p).tolist()]
+
+        keep = [overall and k for k in per_view(1.0 - float(g["dropout_prob"]))]
+        gates = {
+            "ray": [keep[i] and ray_b and "ray_directions_cam" in v for i, v in enumerate(views)],
+            "depth": [keep[i] and depth_b and "depth_along_ray" in v for i, v in enumerate(views)],
+            "cam": [keep[i] and cam_b and "camera_pose_quats" in v and "camera_pose_trans" in v for i, v in enumerate(views)],
+            "cam_enabled": overall and cam_b,
+            "sparse_depth": sparse,
+            "depth_norm_all": per_view(g["depth_scale_norm_all_prob"]),
+            "pose_norm_all": per_view(g["pose_scale_norm_all_prob"]),
+        }
+        flags = [any(gates["ray"]), any(gates["depth"]), any(gates["cam"])]
+        if sharded:
+            flags = comm.any_flags(flags, self.device)
+        gates["active"] = any(flags)
+        return gates
+
+    def _fuse_geometric_inputs(self, eng, feat, views, b, N, plan, comm, gates=None):
+        """Rows a7-a11 of SURVEY 8a for batch item b.  `gates` = _sample_geometric_gates(): which view uses which modality
+        (with probabilities in {0,1}: "the view provides it").  Encodes ray directions, depth (+ its metric scale) and the
+        camera poses relative to view 0 (+ their metric scale) and adds them to the encoder features in place."""
         g = self.geometric_input_config
         V = len(views)
         dev = self.device
+        if gates is None:
+            gates = self._sample_geometric_gates(views, comm)
 
         def metric_flag(view):
             return bool(view["is_metric_scale"][b]) if "is_metric_scale" in view else False
 
         ray = depth = pose = None
-        if g["ray_dirs_prob"] == 1:
-            ids = [i for i, v in enumerate(views) if "ray_directions_cam" in v]
-            if ids:
-                ray = (ids, torch.cat([views[i]["ray_directions_cam"][b:b + 1] for i in ids], 0).to(dev, torch.float32))
-        if g["depth_prob"] == 1:
-            ids = [i for i, v in enumerate(views) if "depth_along_ray" in v]
-            if ids:
-                d = torch.cat([views[i]["depth_along_ray"][b:b + 1] for i in ids], 0).to(dev, torch.float32)
-                norm_all = g["depth_scale_norm_all_prob"] == 1
-                depth = (ids, d, [0.0 if norm_all else float(metric_flag(views[i])) for i in ids])
-        if g["cam_prob"] == 1:
-            has = [("camera_pose_quats" in v and "camera_pose_trans" in v) for v in views]
-            sharded = plan is not None and plan.world > 1
-            if any(has) or sharded:
-                q = torch.zeros(V, 4, device=dev)
-                t = torch.zeros(V, 3, device=dev)
-                for i, v in enumerate(views):
-                    if has[i]:
-                        q[i] = v["camera_pose_quats"][b].to(dev, torch.float32)
-                        t[i] = v["camera_pose_trans"][b].to(dev, torch.float32)
-                hp_ = torch.tensor(has, dtype=torch.uint8, device=dev)
-                lo, n_loc = 0, V
-                if sharded:  # the pose of view 0 and the translation norms of all views are needed on every rank
-                    packed = torch.cat([q, t, hp_.float().unsqueeze(1)], dim=1)           # [V_local, 8]
-                    allp = comm.all_gather_rows(packed, plan.counts)                      # [V_total, 8]
-                    q, t, hp_ = allp[:, :4].contiguous(), allp[:, 4:7].contiguous(), allp[:, 7].to(torch.uint8).contiguous()
-                    lo = plan.view_offset
-                    has_any = bool(hp_.any())  # one host sync; only with pose inputs in sharded mode
-                else:
-                    has_any = True
-                if has_any:
-                    if not bool(hp_[0]):
-                        raise ValueError("camera pose inputs need the pose of view 0 (the reference view)")
-                    from . import ops as _ops
-
-                    q8, t8, s8 = _ops.pose_inputs(q, t, hp_)
-                    norm_all = g["pose_scale_norm_all_prob"] == 1
-                    pose = (q8[lo:lo + n_loc].contiguous(), t8[lo:lo + n_loc].contiguous(), s8[lo:lo + n_loc].contiguous(),
-                            [float(x) for x in has], [0.0 if norm_all else float(metric_flag(v)) for v in views])
+        ids = [i for i in range(V) if gates["ray"][i]]
+        if ids:
+            ray = (ids, torch.cat([views[i]["ray_directions_cam"][b:b + 1] for i in ids], 0).to(dev, torch.float32))
+        ids = [i for i in range(V) if gates["depth"][i]]
+        if ids:
+            d = torch.cat([views[i]["depth_along_ray"][b:b + 1] for i in ids], 0).to(dev, torch.float32)
+            if gates["sparse_depth"]:
+                d = self._sparsify_depth(d, float(g.get("sparsification_removal_percent", 0.0)))
+            depth = (ids, d, [0.0 if gates["depth_norm_all"][i] else float(metric_flag(views[i])) for i in ids])
+        sharded = plan is not None and plan.world > 1
+        if any(gates["cam"]) or (sharded and gates["cam_enabled"]):
+            # view 0's pose is the reference frame whenever it is PROVIDED, even if view 0's own pose features are dropped
+            # (reference model.py:689-703 reads views[0]["camera_pose_*"] under the other view's mask)
+            has_data = [("camera_pose_quats" in v and "camera_pose_trans" in v) for v in views]
+            q = torch.zeros(V, 4, device=dev)
+            t = torch.zeros(V, 3, device=dev)
+            for i, v in enumerate(views):
+                if has_data[i]:
+                    q[i] = v["camera_pose_quats"][b].to(dev, torch.float32)
+                    t[i] = v["camera_pose_trans"][b].to(dev, torch.float32)
+            use = list(gates["cam"])
+            first_is_ref = (not sharded) or plan.rank == 0
+            if first_is_ref and has_data[0]:
+                use[0] = True     # relative pose of view 0 to itself = identity, zero translation: inert in the normaliser
+            hp_ = torch.tensor(use, dtype=torch.uint8, device=dev)
+            lo, n_loc = 0, V
+            if sharded:  # the pose of view 0 and the translation norms of all views are needed on every rank
+                packed = torch.cat([q, t, hp_.float().unsqueeze(1)], dim=1)           # [V_local, 8]
+                allp = comm.all_gather_rows(packed, plan.counts)                      # [V_total, 8]
+                q, t, hp_ = allp[:, :4].contiguous(), allp[:, 4:7].contiguous(), allp[:, 7].to(torch.uint8).contiguous()
+                lo = plan.view_offset
+                has_any = bool(hp_.any())  # one host sync; only with pose inputs in sharded mode
+            else:
+                has_any = True
+            if has_any:
+                if not bool(hp_[0]):
+                    raise ValueError("camera pose inputs need the pose of view 0 (the reference view)")
+                q8, t8, s8 = ops.pose_inputs(q, t, hp_)
+                pose = (q8[lo:lo + n_loc].contiguous(), t8[lo:lo + n_loc].contiguous(), s8[lo:lo + n_loc].contiguous(),
+                        [float(x) for x in gates["cam"]],
+                        [0.0 if gates["pose_norm_all"][i] else float(metric_flag(v)) for i, v in enumerate(views)])
         eng.fuse_geometric(feat, V, N, ray=ray, depth=depth, pose=pose)
+
+    @staticmethod
+    def _sparsify_depth(d: torch.Tensor, removal: float) -> torch.Tensor:
+        """Training-time augmentation of reference model.py:902-933: zero a random `removal` share of the valid (> 0)
+        pixels of every depth map.  Host-orchestrated torch indexing: not part of the inference hot path (infer() sets
+        sparse_depth_prob = 0)."""
+        d = d.clone()
+        for i in range(d.shape[0]):
+            valid = (d[i] > 0).nonzero(as_tuple=True)
+            n = valid[0].numel()
+            k = int(n * removal)
+            if k > 0:
+                sel = torch.randperm(n, device=d.device)[:k]
+                d[i][tuple(ix[sel] for ix in valid)] = 0
+        return d
 
     # ------------------------------------------------------------------------------------------ forward
     def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False) -> List[Dict[str, torch.Tensor]]:
-        """Same contract as the reference forward (model.py:1477-1909). Runs under no_grad: this is an inference engine."""
+        """Same contract as the reference forward (model.py:1477-1909). Runs under no_grad: this is an inference engine.
+        Kernels, side streams and scratch allocations follow the MODULE's device (model.to("cuda:1") works whatever the
+        caller's current device is)."""
+        if self.device.type != "cuda":
+            raise RuntimeError("mapanything_b200 has no CPU path: move the module to a CUDA (sm_100a) device first")
+        with torch.cuda.device(self.device):
+            return self._forward(views, memory_efficient_inference)
+
+    def _forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False) -> List[Dict[str, torch.Tensor]]:
         batch_size_per_view, _, height, width = views[0]["img"].shape
         num_views = len(views)
         data_norm_type = views[0]["data_norm_type"][0]
@@ -307,7 +382,6 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         p = self.encoder.patch_size
         if height % p or width % p:
             raise AssertionError(f"Input image size ({height}, {width}) must be a multiple of the patch size {p}")
-        geo_active = self._geometric_inputs_active(views)
         eng = self.engine()
         eng.dpt_chunk = min(2, eng.dpt_chunk_default) if memory_efficient_inference else eng.dpt_chunk_default
         hp, wp = height // p, width // p
@@ -325,8 +399,9 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             for b in range(batch_size_per_view):
                 imgs = torch.cat([v["img"][b:b + 1] for v in views], dim=0).to(self.device, torch.float32)
                 feat = eng.encode(imgs)                       # fp32 [V*N][C]   DINOv2 x_norm_patchtokens
-                if geo_active:
-                    self._fuse_geometric_inputs(eng, feat, views, b, N, plan, comm)
+                gates = self._sample_geometric_gates(views, comm)
+                if gates["active"]:
+                    self._fuse_geometric_inputs(eng, feat, views, b, N, plan, comm, gates)
                 fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
                 taps, final, final32 = eng.info_sharing(fused, num_views, N, plan=plan, comm=comm)
                 dpt_in = [fused, taps[0], taps[1], final] if self.use_encoder_features_for_dpt else [*taps, final]
@@ -392,10 +467,29 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         ignore_pose_scale_inputs: bool = False,
     ) -> List[Dict[str, torch.Tensor]]:
         """Same surface as the reference infer (model.py:1964-2112).  The kernels always compute with bf16 tensor-core
-        operands, fp32 accumulation and fp32 residual streams -- the reference's `use_amp=True, amp_dtype="bf16"` mode."""
-        if not use_amp or amp_dtype not in ("bf16",):
-            warnings.warn("mapanything_b200 always computes in bf16 (fp32 accumulate); use_amp/amp_dtype are ignored")
-        validated = validate_input_views_for_inference(views)
+        operands, fp32 accumulation and fp32 residual streams -- the reference's `use_amp=True, amp_dtype="bf16"` mode;
+        `use_amp=False` / other amp_dtype values raise (there is no fp32 / fp16 path to fall back to)."""
+        if self.device.type != "cuda":
+            raise RuntimeError("mapanything_b200 has no CPU path: move the module to a CUDA (sm_100a) device first")
+        with torch.cuda.device(self.device):
+            return self._infer(views, memory_efficient_inference, use_amp, amp_dtype, apply_mask, mask_edges,
+                               edge_normal_threshold, edge_depth_threshold, apply_confidence_mask, confidence_percentile,
+                               ignore_calibration_inputs, ignore_depth_inputs, ignore_pose_inputs, ignore_depth_scale_inputs,
+                               ignore_pose_scale_inputs)
+
+    def _infer(self, views, memory_efficient_inference, use_amp, amp_dtype, apply_mask, mask_edges, edge_normal_threshold,
+               edge_depth_threshold, apply_confidence_mask, confidence_percentile, ignore_calibration_inputs,
+               ignore_depth_inputs, ignore_pose_inputs, ignore_depth_scale_inputs, ignore_pose_scale_inputs):
+        if not use_amp or amp_dtype != "bf16":
+            raise ValueError(
+                f"mapanything_b200 computes with bf16 tensor-core operands (fp32 accumulate / residual streams) only: "
+                f"use_amp={use_amp!r}, amp_dtype={amp_dtype!r} is not available (reference model.py:2044-2059 would run "
+                f"fp32 / fp16 autocast)")
+        # view-sharded: only rank 0's first view is the scene's reference view; the scene-wide "view 0 has a pose" rule is
+        # enforced on the gathered flags in _fuse_geometric_inputs (identically on every rank)
+        sharded = self._shard_comm is not None and self._shard_comm.world > 1
+        validated = validate_input_views_for_inference(
+            views, first_view_is_reference=(not sharded) or self._shard_comm.rank == 0)
         ignore_keys = {"instance", "idx", "true_shape", "data_norm_type"}
         for view in validated:
             for key in view.keys():

@@ -18,6 +18,19 @@ from ._lib import (MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU, MA_ATTN_MAX_SEGMENTS, 
 
 LAUNCHES = 0
 PROFILE = None
+# weight data_ptr -> (algorithmic N, algorithmic K) for packed weights whose stored shape is larger than the reference layer's:
+# K zero-padded for TMA alignment (patch embed 588 -> 640, conv channels to multiples of 8) or tripled by the split-bf16
+# packing.  The roofline counts 2*M*N*K of the REFERENCE layer, not the executed MMA work.
+ALGO_NK = {}
+
+
+def register_algorithmic_shape(w: torch.Tensor, n: int, k: int) -> None:
+    ALGO_NK[w.data_ptr()] = (int(n), int(k))
+
+
+def _gemm_kernel_name() -> str:
+    code = _lib.load().ma_last_gemm_block()
+    return f"gemm_bf16_2cta_kernel<{code - 2000}>" if code > 2000 else f"gemm_bf16_tcgen05_kernel<{code}>"
 
 
 class launch:
@@ -142,11 +155,14 @@ def gemm(
     ep = _epilogue(out, N, bias, act, colscale, residual, residual_row_mod, out_relu, rows_per_group_in, rows_per_group_out,
                    row_offset_out, act_after_residual, relu_out_before_residual)
     lib = _lib.load()
-    with launch("gemm", 2.0 * M * N * K, tag=f"{M}x{N}x{K}"):
+    n_alg, k_alg = ALGO_NK.get(w.data_ptr(), (N, K))
+    with launch("gemm", 2.0 * M * n_alg * k_alg, tag=f"{M}x{N}x{K}") as rec:
         check(
             lib.ma_gemm_bf16(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), M, N, K, C.byref(ep), block_n, _stream()),
             "ma_gemm_bf16",
         )
+        if PROFILE is not None:
+            rec.tag = f"{M}x{N}x{K}|{_gemm_kernel_name()}"
     return out
 
 
@@ -173,9 +189,12 @@ def conv3x3(
     if w.shape[1] != 9 * C_ or out.shape[-1] != Cout or out.numel() // Cout != n * H * W:
         raise ValueError(f"conv3x3: shape mismatch x {tuple(x.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
     ep = _epilogue(out, Cout, bias, act, None, residual, 0, out_relu, 0, 0, 0, act_after_residual, relu_out_before_residual)
-    with launch("conv3x3", 2.0 * n * H * W * Cout * 9 * C_, tag=f"{n}x{H}x{W}x{C_}->{Cout}"):
+    n_alg, k_alg = ALGO_NK.get(w.data_ptr(), (Cout, 9 * C_))
+    with launch("conv3x3", 2.0 * n * H * W * n_alg * k_alg, tag=f"{n}x{H}x{W}x{C_}->{Cout}") as rec:
         check(_lib.load().ma_conv3x3_bf16(x.data_ptr(), n, H, W, C_, w.data_ptr(), w.stride(0), Cout, C.byref(ep), block_n,
                                           _stream()), "ma_conv3x3_bf16")
+        if PROFILE is not None:
+            rec.tag = f"{n}x{H}x{W}x{C_}->{Cout}|{_gemm_kernel_name()}"
     return out
 
 

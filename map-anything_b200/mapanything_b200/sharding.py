@@ -93,6 +93,14 @@ class ViewShardComm:
         dist.all_gather_into_tensor(t, mine, group=self.group)
         return [int(x) for x in t.tolist()]
 
+    def any_flags(self, flags: Sequence[bool], device) -> List[bool]:
+        """Element-wise OR of per-rank booleans (all-reduce MAX): decisions that select a code path containing collectives
+        -- "does ANY view of the scene provide this modality" -- must be taken on scene-wide facts, or ranks whose shard
+        differs would issue different collectives and hang."""
+        t = torch.tensor([1 if f else 0 for f in flags], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return [bool(x) for x in t.tolist()]
+
     def all_gather_slots(self, buf: torch.Tensor, slot_rows: int):
         """In-place all-gather of `buf` [world*slot_rows, C]: every rank has filled its own slot.  Returns a work handle;
         `.wait()` makes the CURRENT stream wait for the gather (no host block on NCCL)."""

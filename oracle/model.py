@@ -212,13 +212,13 @@ class MapAnythingOracle(nn.Module):
     # ---------------------------------------------------------------------------------- forward
     def forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False, return_internals: bool = False,
                 amp_bf16: bool = False):
-        """amp_bf16=True reproduces the reference's infer(use_amp=True, amp_dtype="bf16") numerics on the CPU: encoder and
+        """amp_bf16=True reproduces the reference's infer(use_amp=True, amp_dtype="bf16") numerics (on the module's device): encoder and
         info sharing under bf16 autocast (model.py:2092-2095), input fusion and every head with autocast disabled
         (model.py:1516, :1599).  It is the yardstick for how far ANY bf16 path sits from the fp32 result."""
         import contextlib
 
         def amp():
-            return torch.autocast("cpu", dtype=torch.bfloat16) if amp_bf16 else contextlib.nullcontext()
+            return torch.autocast(self.device.type, dtype=torch.bfloat16) if amp_bf16 else contextlib.nullcontext()
 
         b, _, h, w = views[0]["img"].shape
         v = len(views)
@@ -298,7 +298,8 @@ class MapAnythingOracle(nn.Module):
               mask_edges=True, edge_normal_threshold=5.0, edge_depth_threshold=0.03, apply_confidence_mask=False,
               confidence_percentile=10, ignore_calibration_inputs=False, ignore_depth_inputs=False,
               ignore_pose_inputs=False, ignore_depth_scale_inputs=False, ignore_pose_scale_inputs=False):
-        """The oracle always computes in fp32 (use_amp / amp_dtype accepted for signature parity)."""
+        """On the CPU the oracle always computes in fp32 (use_amp / amp_dtype accepted for signature parity).  Moved to a CUDA
+        device (bench.py's GPU-eager baseline) it follows the reference: bf16 autocast when use_amp and amp_dtype == "bf16"."""
         views = I.validate_views(views)
         for view in views:
             for k in view:
@@ -309,7 +310,8 @@ class MapAnythingOracle(nn.Module):
                                                not ignore_pose_inputs, not ignore_depth_scale_inputs,
                                                not ignore_pose_scale_inputs)
         try:
-            preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference)
+            preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference,
+                                 amp_bf16=bool(use_amp and amp_dtype == "bf16" and self.device.type == "cuda"))
         finally:
             self._restore_original_geometric_input_config()
         return I.postprocess_outputs(preds, processed, apply_mask, mask_edges, edge_normal_threshold,

@@ -14,7 +14,8 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     cfg_name, V, size = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-    multimodal = len(sys.argv) > 4 and sys.argv[4] == "mm"
+    mode = sys.argv[4] if len(sys.argv) > 4 else "img"
+    multimodal = mode in ("mm", "mm0")  # mm0: only the views of rank 0's shard carry geometric inputs
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -31,7 +32,12 @@ def main():
     if multimodal:  # internal keys of forward(): unit rays, depth along ray, poses (view 0 = identity), metric scale
         from mapanything_b200.preprocess import preprocess_input_views_for_inference
 
+        from mapanything_b200.sharding import partition_views as _pv
+
+        n_geo = _pv(V, world)[0] if mode == "mm0" else V
         for i, v in enumerate(views):
+            if i >= n_geo:
+                continue
             f = 0.8 * size + 0.4 * size * float(torch.rand(1, generator=g))
             v["intrinsics"] = torch.tensor([[[f, 0, size / 2], [0, f, size / 2], [0, 0, 1.0]]], device=dev)
             if i != 2:

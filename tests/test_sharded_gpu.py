@@ -49,6 +49,16 @@ def test_view_sharded_multimodal_scene_matches_single_gpu():
     assert r["worst_rel"] < 1e-2, r
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_view_sharded_geometric_inputs_on_rank0_only():
+    """Only rank 0's shard carries intrinsics / depth / poses: the decision to run the fusion path (which contains the
+    pose all-gather) is taken scene-wide, so rank 1 -- whose own views are image-only -- enters the same collectives
+    instead of hanging (round-1 advisor finding)."""
+    r = _run(2, "tiny_config", 5, 70, mode="mm0")
+    print(r)
+    assert r["worst_rel"] < 1e-2, r
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs 4 GPUs")
 def test_view_sharded_scene_four_ranks_uneven():
     r = _run(4, "tiny_config", 7, 70)

@@ -95,6 +95,8 @@ def _worker(rank, world, port, N, counts, D, out_q):
         err = (state[0] - ref).abs().max().item()
         s = torch.tensor([3.25 if rank == 0 else 0.0])
         comm.broadcast(s, src=0)
+        # scene-wide modality flags: every rank must see the OR of all ranks' flags (selects paths with collectives)
+        assert comm.any_flags([rank == 0, False, rank == 1], torch.device("cpu")) == [True, False, True]
         out_q.put((rank, err, float(s.item())))
     finally:
         dist.destroy_process_group()
