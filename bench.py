@@ -46,6 +46,14 @@ sys.path.insert(0, str(ROOT))
 
 IMG = 518
 METRIC = "views_per_sec_518px"
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the run, on the real stdout (see main())."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 # Algorithmic GFLOP per view (SURVEY.md section 8d / BASELINE.md section 3), D = 768, regressor hidden 128
 F_ENC, F_IS_LIN, F_FRAME, F_GLOBAL_PER_VIEW, F_DPT, F_POSE = 1013.6, 467.3, 69.1, 69.1, 308.9, 35.5
@@ -240,7 +248,7 @@ def run_reference(args):
         "cpu_baseline": {"value": vps, "unit": "views/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": vps, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(v: int, gpus: int, multi: str = "shard", multimodal: bool = False) -> str:
@@ -434,8 +442,7 @@ def run_ours(args):
         sharded_rel = sharded_vs_single(model, dev, rank, world, V)   # leaves view sharding enabled
         if sharded_rel > 1e-2:
             if rank == 0:
-                print(json.dumps({"error": "sharded scene deviates from the single-GPU scene", "sharded_vs_single_rel": sharded_rel}),
-                      flush=True)
+                emit({"error": "sharded scene deviates from the single-GPU scene", "sharded_vs_single_rel": sharded_rel})
             dist.barrier()
             dist.destroy_process_group()
             sys.exit(3)
@@ -478,7 +485,7 @@ def run_ours(args):
         fwd_step()
         torch.cuda.synchronize()
         if rank == 0:
-            print(json.dumps({"profile_mode": True, "views": V, "launches_per_step": ops.LAUNCHES // 2}))
+            emit({"profile_mode": True, "views": V, "launches_per_step": ops.LAUNCHES // 2})
         return
     for _ in range(max(args.warmup, 3)):
         fwd_step()
@@ -571,7 +578,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -603,10 +610,15 @@ def cpu_baseline(v: int, model, multimodal: bool):
 
 def main():
     # rank 0 prints exactly ONE line on stdout
-    if "NCCL_DEBUG" not in os.environ:   # NCCL's init lines (rings, NVLS, transports) go to stderr, not to the JSON line
+    # ... and everything else any library writes to fd 1 (NCCL's banner and INFO lines among them) goes to stderr: the
+    # process-wide stdout is re-pointed at stderr and the JSON line is written to a private duplicate of the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":   # keep NCCL's init lines (transports, NVLS) visible
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -384,11 +384,13 @@ __host__ __device__ constexpr bool a2_poly_slot(int i, int npoly) { return ((i *
 template <int NPOLY>
 __device__ __forceinline__ void a2_exp_chunk(const uint32_t (&v)[32], uint32_t* dst, uint64_t sl2_2, uint64_t nm2, uint64_t k2,
                                              float smin, uint64_t (&acc)[4]) {
-  // Written stage by stage over all pairs of the chunk (not pair by pair): every stage is NPOLY (or 16 - NPOLY)
-  // independent instructions, so the dependent chain clamp -> r -> u -> g -> cubic -> exponent insert never waits on
-  // the fixed FMA-pipe latency even with only two softmax warps per scheduler.
+  // Written stage by stage over all pairs of the chunk (not pair by pair): every stage is a run of independent
+  // instructions.  (ptxas re-schedules the result freely -- the SASS consumes each pair of exponentials two MUFU
+  // instructions after issuing them whatever the source order, volatile asm included.)
   constexpr int NP = NPOLY > 0 ? NPOLY : 1;
+  constexpr int AHEAD = 1;
   uint64_t s2[16], r2[NP], g2[NP];
+  float ea[16], eb[16];
   int pi = 0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -426,22 +428,26 @@ __device__ __forceinline__ void a2_exp_chunk(const uint32_t (&v)[32], uint32_t* 
     for (int i = 0; i < 16; ++i)
       if (a2_poly_slot(i, NPOLY)) { s2[i] = ffma2(s2[i], g2[pi], c0); ++pi; }
   }
-  pi = 0;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float ea, eb;
-    unpack2(s2[i], ea, eb);
+  auto evaluate = [&](int i, int& pidx) {
+    unpack2(s2[i], ea[i], eb[i]);
     if (a2_poly_slot(i, NPOLY)) {
       float ra, rb;
-      unpack2(r2[pi++], ra, rb);
-      ea = __uint_as_float(__float_as_uint(ea) + (__float_as_uint(ra) << 23));
-      eb = __uint_as_float(__float_as_uint(eb) + (__float_as_uint(rb) << 23));
+      unpack2(r2[pidx++], ra, rb);
+      ea[i] = __uint_as_float(__float_as_uint(ea[i]) + (__float_as_uint(ra) << 23));
+      eb[i] = __uint_as_float(__float_as_uint(eb[i]) + (__float_as_uint(rb) << 23));
     } else {
-      ea = fast_exp2(ea);
-      eb = fast_exp2(eb);
+      ea[i] = fast_exp2(ea[i]);
+      eb[i] = fast_exp2(eb[i]);
     }
-    acc[i & 3] = fadd2(acc[i & 3], pack2(ea, eb));
-    dst[i] = pack_bf16x2(ea, eb);
+  };
+  pi = 0;
+#pragma unroll
+  for (int i = 0; i < AHEAD; ++i) evaluate(i, pi);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i + AHEAD < 16) evaluate(i + AHEAD, pi);
+    acc[i & 3] = fadd2(acc[i & 3], pack2(ea[i], eb[i]));
+    dst[i] = pack_bf16x2(ea[i], eb[i]);
   }
 }
 

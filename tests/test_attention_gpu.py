@@ -167,3 +167,78 @@ def test_attention_kv_split_and_merge(split):
     assert torch.isfinite(out2.float()).all()
     err = (out2.float() - ref).abs().max().item()
     assert err < 2.5e-2, err
+
+
+def _ref_rows_fp64(q_rows, k, v, H):
+    """fp64 softmax attention for a few query rows: q_rows [R, H*64] bf16, k / v [L, H*64] bf16 -> [R, H*64] fp64."""
+    R, L = q_rows.shape[0], k.shape[0]
+    qf = q_rows.double().view(R, H, 64).transpose(0, 1)
+    kf = k.double().view(L, H, 64).transpose(0, 1)
+    vf = v.double().view(L, H, 64).transpose(0, 1)
+    return (torch.softmax(qf @ kf.transpose(1, 2) / 8.0, -1) @ vf).transpose(0, 1).reshape(R, H * 64)
+
+
+def test_attention_long_sequence_64_views():
+    """One global-attention sequence of 64 * 1369 + 1 = 87617 tokens (the 8-GPU bench scene; 685 kv tiles): 256 sampled query
+    rows against an fp64 softmax.  Exercises the lazy rescale and the bf16 probabilities over ~10^3 tiles."""
+    from mapanything_b200 import ops
+
+    H, L = 12, 64 * 1369 + 1
+    D = H * 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    qkv = (torch.randn(L, 3 * D, device="cuda", generator=g) * 1.3).bfloat16()
+    # a drifting score level: later keys score higher on average, so the running maximum keeps moving (forces rescales)
+    qkv[:, D:2 * D] += (torch.linspace(0, 1.5, L, device="cuda")[:, None] * torch.sign(qkv[:1, :D].float())).bfloat16()
+    out = torch.full((L, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, num_heads=H, num_seqs=1, q_len=L, kv_len=L)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    rows = torch.randint(0, L, (256,), generator=torch.Generator().manual_seed(3)).cuda()
+    rows[0], rows[1] = 0, L - 1
+    ref = _ref_rows_fp64(qkv[rows, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], H)
+    err = (out[rows].double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"\n[attention, 87617 keys] max abs err {err:.3e} (|out| max {scale:.3f})")
+    assert err < 2e-2 * max(1.0, scale), err
+
+
+def test_attention_sharded_protocol_100_views():
+    """The sequence-parallel global attention of BASELINE config[3] as rank 0 of 8 executes it: 100 views = 136901 key rows
+    in 8 padded slots, 13 * 1369 + 1 local query rows; local keys first (partial state), the 7 remote slots in a second
+    launch (second partial state), ma_attention_merge.  256 sampled rows against an fp64 softmax over all 136901 keys."""
+    from mapanything_b200 import ops
+    from mapanything_b200.sharding import ViewShardPlan, partition_views
+
+    H, N = 12, 1369
+    D = H * 64
+    plan = ViewShardPlan(partition_views(100, 8), 0, N)
+    rows, slot = plan.rows(), plan.slot_rows
+    g = torch.Generator(device="cuda").manual_seed(22)
+    kv = torch.zeros(plan.world * slot, 2 * D, device="cuda", dtype=torch.bfloat16)
+    dense = []
+    for r in range(plan.world):
+        blk = (torch.randn(plan.rows(r), 2 * D, device="cuda", generator=g) * 1.3).bfloat16()
+        kv[r * slot:r * slot + plan.rows(r)] = blk
+        dense.append(blk)
+    q = (torch.randn(rows, D, device="cuda", generator=g) * 1.3).bfloat16()
+    K, V = kv[:, :D], kv[:, D:]
+    so = torch.empty(2, rows, D, device="cuda")
+    sm = torch.full((2, rows, H), float("-inf"), device="cuda")
+    common = dict(num_heads=H, num_seqs=1, q_len=rows, kv_seq_stride=kv.shape[0])
+    remote = plan.remote_segments()
+    ops.attention(q, K, V, None, kv_len=rows, kv_segments=plan.local_segment(), state=(so[:1], sm[:1]), state_out=True, **common)
+    ops.attention(q, K, V, None, kv_len=sum(l for _, l in remote), kv_segments=remote, state=(so[1:], sm[1:]), state_out=True,
+                  **common)
+    out = torch.full((rows, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attention_merge((so, sm), out, num_heads=H)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    # the order of the dense keys must follow the segment order the kernel walked: local slot, then ranks 1..7
+    order = [0] + [(0 + i) % plan.world for i in range(1, plan.world)]
+    alld = torch.cat([dense[r] for r in order], 0)
+    assert alld.shape[0] == plan.total_rows == 100 * N + 1
+    pick = torch.randint(0, rows, (256,), generator=torch.Generator().manual_seed(4)).cuda()
+    ref = _ref_rows_fp64(q[pick], alld[:, :D], alld[:, D:], H)
+    err = (out[pick].double() - ref).abs().max().item()
+    print(f"\n[sharded attention protocol, 136901 keys in 8 slots] max abs err {err:.3e}")
+    assert err < 2e-2, err

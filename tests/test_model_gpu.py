@@ -48,9 +48,12 @@ def _rel(a, b):
 
 
 def _rot_err_deg(q1, q2):
+    """Angle of the relative rotation between unit quaternions, well conditioned near zero: |q1 - q2| = 2 sin(theta / 4) (sign
+    aligned).  (acos of the dot product has a 0.04 degree noise floor from fp32 rounding alone: acos(1 - 6e-8).)"""
     q1, q2 = q1.double().cpu(), q2.double().cpu()
-    d = (q1 * q2).sum(-1).abs().clamp(max=1.0)
-    return (2 * torch.acos(d) * 180 / math.pi).max().item()
+    q1, q2 = q1 / q1.norm(dim=-1, keepdim=True), q2 / q2.norm(dim=-1, keepdim=True)
+    d = torch.minimum((q1 - q2).norm(dim=-1), (q1 + q2).norm(dim=-1))
+    return (4 * torch.asin((d / 2).clamp(max=1.0)) * 180 / math.pi).max().item()
 
 
 def _metrics(got, ref):
