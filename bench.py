@@ -318,6 +318,17 @@ def strong_scaling_record(model, dev, rank, world, timed, peak_tf, scene=100, st
     eng.ag_wait_events = None
     exposed = torch.tensor([sum(waits) / max(len(waits), 1)], device=dev)
     dist.all_reduce(exposed, op=dist.ReduceOp.MAX)
+    # end to end: infer() from pinned host images, every rank reads its views' point maps / masks / poses back
+    host = [im.pin_memory() for im in imgs[lo:lo + counts[rank]]]
+
+    def e2e():
+        preds = model.infer([{"img": im, "data_norm_type": ["dinov2"]} for im in host])
+        outs = [p[k].to("cpu", non_blocking=True) for p in preds for k in ("pts3d", "conf", "mask", "camera_poses", "intrinsics")]
+        torch.cuda.current_stream().synchronize()
+        return outs
+
+    e2e()
+    ms_e2e = timed(e2e, 2) / 2
     # the same scene on ONE GPU of this box (rank 0; the other ranks idle at the barrier)
     model.disable_view_sharding()
     ms_1 = torch.zeros(1, device=dev)
@@ -339,6 +350,7 @@ def strong_scaling_record(model, dev, rank, world, timed, peak_tf, scene=100, st
     return {
         "scene_views": scene, "views_per_rank": counts, "steps": steps,
         "ms_per_step": ms_n, "views_per_s": scene / (ms_n * 1e-3),
+        "e2e_ms_per_step": ms_e2e, "e2e_views_per_s": scene / (ms_e2e * 1e-3),
         "single_gpu_ms_per_step": ms_1.item(), "single_gpu_views_per_s": scene / (ms_1.item() * 1e-3),
         "speedup_vs_single_gpu": ms_1.item() / ms_n, "efficiency": ms_1.item() / ms_n / world,
         "per_gpu_step_frac": tf_scene / world / (ms_n * 1e-3) / peak_tf,

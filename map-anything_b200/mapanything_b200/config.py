@@ -77,6 +77,22 @@ INFO_SHARING_VARIANTS = {
                           "num_heads": 16, "distinguish_ref_and_non_ref_views": True},
     "aat_ifr_48_layers_no_ref_view": {"name": "aat_48_layers_ifr_no_ref_view", "indices": [11, 23, 35], "size": "48_layers",
                                       "depth": 48, "dim": 1024, "num_heads": 16, "distinguish_ref_and_non_ref_views": False},
+    # view-index positional encoding: random table rows for the non-reference views (aat_ifr_24_layers_w_view_pe.yaml)
+    "aat_ifr_24_layers_w_view_pe": {"name": "aat_24_layers_ifr_w_view_pe", "indices": [11, 17], "size": "24_layers", "depth": 24,
+                                    "distinguish_ref_and_non_ref_views": True, "max_num_views_for_pe": 1000,
+                                    "use_rand_idx_pe_for_non_reference_views": True},
+    # entropy scaling of the attention logits (aat_ifr_24_layers_escaling.yaml / aat_ifr_48_layers_escaling.yaml)
+    "aat_ifr_24_layers_escaling": {"name": "aat_24_layers_ifr", "indices": [11, 17], "size": "24_layers", "depth": 24,
+                                   "distinguish_ref_and_non_ref_views": True, "use_entropy_scaling": True},
+    "aat_ifr_48_layers_escaling": {"name": "aat_48_layers_ifr", "indices": [11, 23, 35], "size": "48_layers", "depth": 48,
+                                   "dim": 1024, "num_heads": 16, "distinguish_ref_and_non_ref_views": True,
+                                   "use_entropy_scaling": True},
+    # global attention in every block (model_type "global_attention": gat_ifr_24_layers.yaml, gat_ifr_24_layers_escaling.yaml)
+    "gat_ifr_24_layers": {"name": "gat_24_layers_ifr", "indices": [11, 17], "size": "24_layers", "depth": 24,
+                          "max_num_views": 1000, "use_rand_idx_pe_for_non_reference_views": True},
+    "gat_ifr_24_layers_escaling": {"name": "gat_24_layers_ifr", "indices": [11, 17], "size": "24_layers", "depth": 24,
+                                   "max_num_views": 1000, "use_rand_idx_pe_for_non_reference_views": True,
+                                   "use_entropy_scaling": True},
 }
 
 
@@ -84,11 +100,13 @@ def mapanything_variant_config(info_sharing: str = "aat_ifr_24_layers", **overri
     """mapanything_config() with another info-sharing YAML of the reference (`model/info_sharing=<name>` on its Hydra
     command line): the 48-layer / width-1024 transformer with three taps, and the variants without reference-view embedding."""
     if info_sharing not in INFO_SHARING_VARIANTS:
-        raise ValueError(f"info_sharing must be one of {sorted(INFO_SHARING_VARIANTS)} (this build has alternating attention "
-                         f"with intermediate features only), got {info_sharing!r}")
+        raise ValueError(f"info_sharing must be one of {sorted(INFO_SHARING_VARIANTS)} (intermediate-feature transformers with "
+                         f"alternating or global attention), got {info_sharing!r}")
     cfg = mapanything_config(**overrides)
     cfg["info_sharing_config"]["module_args"] = {"norm_intermediate": True, "gradient_checkpointing": False,
                                                  **copy.deepcopy(INFO_SHARING_VARIANTS[info_sharing])}
+    if info_sharing.startswith("gat_"):
+        cfg["info_sharing_config"]["model_type"] = "global_attention"
     return cfg
 
 

@@ -76,6 +76,14 @@ def _convT(conv: nn.ConvTranspose2d) -> Lin:
     return Lin(w, b)
 
 
+def _sinusoid_table(n_rows: int, dim: int, base: float = 10000.0) -> torch.Tensor:
+    """MAE / CroCo-style fixed table (SURVEY App. A.3): angle[pos, j] = pos / base^(2 (j // 2) / dim), sin on even j, cos on odd."""
+    pos = torch.arange(n_rows, dtype=torch.float64)[:, None]
+    j = torch.arange(dim, dtype=torch.float64)[None, :]
+    angle = pos / torch.pow(torch.tensor(base, dtype=torch.float64), 2 * torch.div(j, 2, rounding_mode="floor") / dim)
+    return torch.where((torch.arange(dim) % 2 == 0)[None, :], torch.sin(angle), torch.cos(angle)).float()
+
+
 def _pad8(n: int) -> int:
     return (n + 7) // 8 * 8
 
@@ -186,6 +194,8 @@ class Engine:
         self._geo = None
 
         isx = model.info_sharing
+        self.isx = isx   # wiring switches: is_global(i), view_pe_rows(V, first), softmax_scale_factor(n_keys)
+        self._view_pe_table = None
         self.D, self.is_heads, self.indices = isx.dim, isx.num_heads, list(isx.indices)
         self.norm_intermediate = isx.norm_intermediate
         if isinstance(isx.proj_embed, nn.Linear):
@@ -225,6 +235,8 @@ class Engine:
         self.reg1, self.reg2, self.reg3 = _conv3x3(reg.conv1), _conv3x3(reg.conv2[0]), _conv1x1(reg.conv2[2])
 
         ph = model.pose_head
+        self.pose_relu_after_skip = bool(getattr(ph, "final_relu_after_skip", True))
+        self.scale_act = MA_ACT_GELU if getattr(model.scale_head, "activation", "relu") == "gelu" else MA_ACT_RELU
         self.pose_blocks = []
         for rb in ph.res_conv:
             if not isinstance(rb.head_skip, nn.Identity):
@@ -332,19 +344,21 @@ class Engine:
         ops.attention(q, k, v, out, state=(so, sm), kv_split=parts, kv_split_from=first, **common)
         return ops.attention_merge((so, sm), out, num_heads=heads, first_slot=first)
 
-    def _block(self, x, bw: BlockW, rows: int, heads: int, num_seqs: int, seq_len: int, seq_stride: int):
+    def _block(self, x, bw: BlockW, rows: int, heads: int, num_seqs: int, seq_len: int, seq_stride: int,
+               scale_factor: float = 1.0):
         """One pre-LN transformer block, in place on the fp32 residual stream x[:rows]."""
         dim = x.shape[1]
+        scale = None if scale_factor == 1.0 else 64 ** -0.5 * scale_factor
         xr = x[:rows]
         h = self._empty(rows, dim)
         ops.layernorm(xr, h, bw.n1w, bw.n1b)
         qkv = self._lin(h, bw.qkv)
         a = self._empty(rows, dim)
-        if num_seqs == 1 and seq_len >= 2048:
+        if num_seqs == 1 and seq_len >= 2048 and scale is None:
             self._attention_one_sequence(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, heads, seq_len, seq_len)
         else:
             ops.attention(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, num_heads=heads, num_seqs=num_seqs,
-                          q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride)
+                          q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride, scale=scale)
         ops.gemm(a, bw.proj.w, xr, bias=bw.proj.b, colscale=bw.ls1, residual=xr)
         ops.layernorm(xr, h, bw.n2w, bw.n2b)
         f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
@@ -368,7 +382,9 @@ class Engine:
         K, Vv = kvbuf[:, :dim], kvbuf[:, dim:]
         a = self._empty(rows, dim)
         remote = plan.remote_segments()
-        common = dict(num_heads=heads, num_seqs=1, q_len=rows, kv_seq_stride=kvbuf.shape[0])
+        sf = self.isx.softmax_scale_factor(plan.total_rows)
+        common = dict(num_heads=heads, num_seqs=1, q_len=rows, kv_seq_stride=kvbuf.shape[0],
+                      scale=None if sf == 1.0 else 64 ** -0.5 * sf)
         if remote:
             # partial softmax states: the local key range (runs while the all-gather is in flight) and the remote ranges
             # (after it landed), each cut into as many parts as fills the SMs; one merge pass joins them all
@@ -395,7 +411,7 @@ class Engine:
                 self.ag_wait_events.append((e0, e1))
             ops.attention(q, K, Vv, None, kv_len=kv_r, kv_segments=remote, state=(so[s_l:s_l + s_r], sm[s_l:s_l + s_r]),
                           state_out=True, kv_split=s_r, kv_split_from=f_r, **common)
-            ops.attention_merge((so[:s_l + s_r], sm[:s_l + s_r]), a, num_heads=heads)
+            ops.attention_merge((so[:s_l + s_r], sm[:s_l + s_r]), a, num_heads=heads, scale=common["scale"])
         else:
             work.wait()
             ops.attention(q, K, Vv, a, kv_len=rows, kv_segments=plan.local_segment(), **common)
@@ -559,12 +575,23 @@ class Engine:
         has_ref = has_tok
         D, T = self.D, V * N + (1 if has_tok else 0)
         y = self._empty(T, D, dtype=torch.float32)
-        if self.use_ref_pe and has_ref:
+        pe_rows = self.isx.view_pe_rows(V, plan.view_offset if sharded else 0)
+        ref_only = pe_rows is not None and pe_rows[0] == 0 and all(r is None for r in pe_rows[1:])
+        if ref_only:   # released config: sinusoid row 0 on the reference view's tokens, folded into the GEMM epilogue
             ops.gemm(fused[:N], self.proj_embed.w, y[:N], bias=self.proj_embed.b, residual=self.pe0, residual_row_mod=1)
             if V > 1:
                 ops.gemm(fused[N:], self.proj_embed.w, y[N:V * N], bias=self.proj_embed.b)
         else:
             ops.gemm(fused, self.proj_embed.w, y[:V * N], bias=self.proj_embed.b)
+            if pe_rows is not None and any(r is not None for r in pe_rows):
+                # per-view rows of the fixed sinusoid table (view-index PE, *_w_view_pe.yaml / gat_ifr_*.yaml): one
+                # broadcast-add launch over all views
+                if self._view_pe_table is None:
+                    self._view_pe_table = _sinusoid_table(self.isx.max_views, D).to(self.device)
+                idx = torch.tensor([r if r is not None else 0 for r in pe_rows], device=self.device)
+                gw = torch.zeros(4, V, device=self.device)
+                gw[0] = torch.tensor([1.0 if r is not None else 0.0 for r in pe_rows], device=self.device)
+                ops.fuse_add(y[:V * N], V, N, globals_=[self._view_pe_table[idx].contiguous(), None, None, None], gw=gw)
         if has_tok:
             ops.set_rows(y, self.scale_tok_proj.reshape(-1), None, groups=1, group_stride=0, row_offset=V * N)
         bufs = None
@@ -581,12 +608,12 @@ class Engine:
             bufs = self._shard_bufs
         taps: List[torch.Tensor] = []
         for i, bw in enumerate(self.is_blocks):
-            if i % 2 == 0 and sharded:
+            if self.isx.is_global(i) and sharded:
                 self._block_global_sharded(y, bw, plan, comm, bufs)
-            elif i % 2 == 0:
-                self._block(y, bw, T, self.is_heads, 1, T, T)  # global: every token of every view + scale token
-            else:
-                self._block(y, bw, V * N, self.is_heads, V, N, N)  # frame: per view, scale token bypasses the block
+            elif self.isx.is_global(i):  # global: every token of every view + scale token
+                self._block(y, bw, T, self.is_heads, 1, T, T, scale_factor=self.isx.softmax_scale_factor(T))
+            else:  # frame: per view, scale token bypasses the block
+                self._block(y, bw, V * N, self.is_heads, V, N, N, scale_factor=self.isx.softmax_scale_factor(N))
             if i in self.indices:
                 tap = self._empty(V * N, D)
                 if self.norm_intermediate:
@@ -643,7 +670,8 @@ class Engine:
             u2 = self._empty(n * N, c2.n, dtype=torch.float32)
             ops.conv3x3(us, c2.w, u2, bias=c2.b, act=MA_ACT_RELU)
             xn = self._empty(n * N, c3.n, dtype=torch.float32)
-            ops.gemm(ops.split3(u2), c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU, act_after_residual=True)
+            ops.gemm(ops.split3(u2), c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU,
+                     act_after_residual=self.pose_relu_after_skip)
             x32 = xn
         pooled = self._empty(n, D, dtype=torch.float32)
         ops.token_mean_f32(x32.view(n, N, D), pooled)
@@ -704,7 +732,7 @@ class Engine:
         x = tok_feat32
         for lin in self.scale_mlp[:-1]:
             xn = self._empty(x.shape[0], lin.n, dtype=torch.float32)
-            ops.gemm(ops.split3(x), lin.w, xn, bias=lin.b, act=MA_ACT_RELU)
+            ops.gemm(ops.split3(x), lin.w, xn, bias=lin.b, act=self.scale_act)
             x = xn
         out = self._empty(1, self.scale_mlp[-1].n, dtype=torch.float32)
         ops.gemm(ops.split3(x), self.scale_mlp[-1].w, out, bias=self.scale_mlp[-1].b)

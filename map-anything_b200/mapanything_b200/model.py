@@ -114,11 +114,15 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         self.custom_positional_encoding = None
         cfg["module_args"]["input_embed_dim"] = self.encoder.enc_embed_dim
         cfg["module_args"]["custom_positional_encoding"] = None
-        if self.info_sharing_return_type != "intermediate_features" or self.info_sharing_type != "alternating_attention":
+        if (self.info_sharing_return_type != "intermediate_features"
+                or self.info_sharing_type not in ("alternating_attention", "global_attention")):
             raise ValueError(
-                f"mapanything_b200 implements info_sharing model_type='alternating_attention' with "
-                f"model_return_type='intermediate_features' (got {self.info_sharing_type!r}, {self.info_sharing_return_type!r})"
+                f"mapanything_b200 implements info_sharing model_type 'alternating_attention' / 'global_attention' with "
+                f"model_return_type='intermediate_features' (got {self.info_sharing_type!r}, {self.info_sharing_return_type!r}); "
+                f"'cross_attention' is the two-view DUSt3R decoder of other model configs"
             )
+        if self.info_sharing_type == "global_attention":   # reference model.py:271-284, gat_ifr_24_layers.yaml
+            cfg["module_args"].setdefault("attention_pattern", "global")
         self.info_sharing = P.AlternatingAttentionIFR(**cfg["module_args"])
         # reference model.py:304-313: 2 taps -> the DPT also takes the (fused) encoder features; 3 taps -> it does not
         if len(self.info_sharing.indices) == 2:
@@ -372,6 +376,22 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             return self._forward(views, memory_efficient_inference)
 
     def _forward(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False) -> List[Dict[str, torch.Tensor]]:
+        per_scene, _ = self._forward_scenes(views, memory_efficient_inference)
+        num_views = len(views)
+        res = []
+        for i in range(num_views):
+            d = {}
+            for key in ("pts3d", "pts3d_cam", "ray_directions", "depth_along_ray", "cam_trans", "cam_quats", "conf",
+                        "non_ambiguous_mask", "non_ambiguous_mask_logits"):
+                parts = [s[key][i:i + 1] for s in per_scene]
+                d[key] = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
+            scales = [s["metric_scaling_factor"] for s in per_scene]
+            d["metric_scaling_factor"] = scales[0] if len(scales) == 1 else torch.cat(scales, dim=0)
+            res.append(d)
+        return res
+
+    def _forward_scenes(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False):
+        """-> (one dict of [V, ...] output tensors per batch item, the (V,3,H,W) image tensor of each batch item)."""
         batch_size_per_view, _, height, width = views[0]["img"].shape
         num_views = len(views)
         data_norm_type = views[0]["data_norm_type"][0]
@@ -394,10 +414,11 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             if counts[comm.rank] != num_views:
                 raise ValueError(f"rank {comm.rank} was given {num_views} views, views_per_rank says {counts[comm.rank]}")
             plan = ViewShardPlan(counts, comm.rank, N)
-        per_scene = []
+        per_scene, scene_imgs = [], []
         with torch.no_grad():
             for b in range(batch_size_per_view):
                 imgs = torch.cat([v["img"][b:b + 1] for v in views], dim=0).to(self.device, torch.float32)
+                scene_imgs.append(imgs)
                 feat = eng.encode(imgs)                       # fp32 [V*N][C]   DINOv2 x_norm_patchtokens
                 gates = self._sample_geometric_gates(views, comm)
                 if gates["active"]:
@@ -413,17 +434,7 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                         torch.empty(1, device=self.device, dtype=torch.float32)
                     comm.broadcast(scale_raw, src=0)
                 per_scene.append(ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width))
-        res = []
-        for i in range(num_views):
-            d = {}
-            for key in ("pts3d", "pts3d_cam", "ray_directions", "depth_along_ray", "cam_trans", "cam_quats", "conf",
-                        "non_ambiguous_mask", "non_ambiguous_mask_logits"):
-                parts = [s[key][i:i + 1] for s in per_scene]
-                d[key] = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
-            scales = [s["metric_scaling_factor"] for s in per_scene]
-            d["metric_scaling_factor"] = scales[0] if len(scales) == 1 else torch.cat(scales, dim=0)
-            res.append(d)
-        return res
+        return per_scene, scene_imgs
 
     # ------------------------------------------------------------------------------------------ infer
     def _configure_geometric_input_config(self, use_calibration: bool, use_depth: bool, use_pose: bool,
@@ -504,10 +515,22 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             use_pose=not ignore_pose_inputs, use_depth_scale=not ignore_depth_scale_inputs,
             use_pose_scale=not ignore_pose_scale_inputs,
         )
+        scene = None
         try:
-            preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference)
+            one_norm = all(v["data_norm_type"][0] == processed[0]["data_norm_type"][0] for v in processed)
+            if processed[0]["img"].shape[0] == 1 and one_norm:   # one scene: post-process all views with one launch set
+                scene = self._forward_scenes(processed, memory_efficient_inference)
+            else:
+                preds = self.forward(processed, memory_efficient_inference=memory_efficient_inference)
         finally:
             self._restore_original_geometric_input_config()
+        if scene is not None:
+            from .inference import postprocess_scene
+
+            return postprocess_scene(
+                scene[0][0], scene[1][0], processed[0]["data_norm_type"][0], apply_mask=apply_mask, mask_edges=mask_edges,
+                edge_normal_threshold=edge_normal_threshold, edge_depth_threshold=edge_depth_threshold,
+                apply_confidence_mask=apply_confidence_mask, confidence_percentile=confidence_percentile)
         return postprocess_model_outputs_for_inference(
             raw_outputs=preds, input_views=processed, apply_mask=apply_mask, mask_edges=mask_edges,
             edge_normal_threshold=edge_normal_threshold, edge_depth_threshold=edge_depth_threshold,

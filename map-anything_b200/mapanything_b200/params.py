@@ -118,20 +118,73 @@ class GlobalRepresentationEncoder(_NoForward):
 
 
 class AlternatingAttentionIFR(_NoForward):
+    """Multi-view transformer with intermediate-feature return.  Besides the YAML keys of
+    configs/model/info_sharing/*.yaml it takes the switches that settle the App. A.3 "VERIFY" items (the oracle has the same
+    ones; tests/test_variants_gpu.py runs each):
+      global_attention_first  even blocks global (default) or frame-wise
+      attention_pattern       "alternating" | "global" (model_type global_attention: every block attends over all views)
+      view_pe_variant         "ref_only" | "ref_vs_rest" | "per_view_index" (+ use_rand_idx_pe_for_non_reference_views)
+      use_entropy_scaling     softmax scale x log(n_keys) / log(entropy_scaling_ref_len)"""
+
     def __init__(self, name, input_embed_dim, indices=(11, 17), norm_intermediate=True, size=None, depth=24, dim=768,
                  num_heads=12, mlp_ratio=4.0, distinguish_ref_and_non_ref_views=True, use_pe_for_non_reference_views=False,
-                 max_num_views_for_pe=1000, gradient_checkpointing=False, custom_positional_encoding=None, **_):
+                 use_rand_idx_pe_for_non_reference_views=False, max_num_views_for_pe=1000, max_num_views=None,
+                 gradient_checkpointing=False, custom_positional_encoding=None, global_attention_first=True,
+                 attention_pattern="alternating", view_pe_variant=None, use_entropy_scaling=False,
+                 entropy_scaling_ref_len=None, **_):
         super().__init__()
-        if custom_positional_encoding is not None or use_pe_for_non_reference_views:
-            raise ValueError("custom / non-reference view positional encodings are not part of the released config")
+        if custom_positional_encoding is not None:
+            raise ValueError("custom positional encodings are not implemented by the reference either (model.py:262-268)")
         if dim // num_heads != 64:
             raise ValueError("the sm_100a attention kernel is specialised for head_dim 64")
+        if attention_pattern not in ("alternating", "global"):
+            raise ValueError(f"attention_pattern {attention_pattern!r}: 'alternating' or 'global'")
+        if view_pe_variant is None:
+            view_pe_variant = "per_view_index" if (use_rand_idx_pe_for_non_reference_views or use_pe_for_non_reference_views) \
+                else "ref_only"
+        if view_pe_variant not in ("ref_only", "ref_vs_rest", "per_view_index"):
+            raise ValueError(f"view_pe_variant {view_pe_variant!r}")
         self.name, self.dim, self.depth, self.num_heads = name, dim, depth, num_heads
         self.indices, self.norm_intermediate = list(indices), norm_intermediate
         self.distinguish_ref_and_non_ref_views = distinguish_ref_and_non_ref_views
+        self.global_attention_first, self.attention_pattern = bool(global_attention_first), attention_pattern
+        self.view_pe_variant, self.use_rand_idx = view_pe_variant, bool(use_rand_idx_pe_for_non_reference_views)
+        self.max_views = int(max_num_views or max_num_views_for_pe)
+        self.fixed_view_pe_indices = None  # tests / reproducible runs: table rows of views 1..V-1 instead of random draws
+        self.use_entropy_scaling, self.entropy_scaling_ref_len = bool(use_entropy_scaling), entropy_scaling_ref_len
         self.proj_embed = nn.Linear(input_embed_dim, dim) if input_embed_dim != dim else nn.Identity()
         self.self_attention_blocks = nn.ModuleList([Block(dim, num_heads, mlp_ratio, layer_scale=False) for _ in range(depth)])
         self.norm = nn.LayerNorm(dim, eps=1e-6)
+
+    def is_global(self, i: int) -> bool:
+        return self.attention_pattern == "global" or ((i % 2 == 0) == self.global_attention_first)
+
+    def view_pe_rows(self, v: int, first_view: int = 0):
+        """Sinusoid-table row per view (None = no PE) for the scene's views first_view .. first_view + v - 1."""
+        if not self.distinguish_ref_and_non_ref_views and self.view_pe_variant == "ref_only":
+            return None
+        rows = []
+        for g in range(first_view, first_view + v):
+            if g == 0:
+                rows.append(0)
+            elif self.view_pe_variant == "ref_only":
+                rows.append(None)
+            elif self.view_pe_variant == "ref_vs_rest":
+                rows.append(1)
+            elif self.fixed_view_pe_indices is not None:
+                rows.append(int(self.fixed_view_pe_indices[g - 1]))
+            elif self.use_rand_idx:
+                rows.append(int(torch.randint(1, self.max_views, (1,))))
+            else:
+                rows.append(g)
+        return rows
+
+    def softmax_scale_factor(self, n_keys: int) -> float:
+        if not self.use_entropy_scaling:
+            return 1.0
+        import math
+
+        return math.log(n_keys) / math.log(self.entropy_scaling_ref_len or n_keys)
 
 
 class ResidualConvUnit(_NoForward):
@@ -195,8 +248,12 @@ class ResConvBlock(_NoForward):
 
 
 class PoseHead(_NoForward):
-    def __init__(self, patch_size, input_feature_dim, num_resconv_block=2, rot_representation_dim=4, **_):
+    """final_relu_after_skip: relu(skip + conv3(y)) (default) or skip + relu(conv3(y)) -- SURVEY App. A.6 VERIFY item."""
+
+    def __init__(self, patch_size, input_feature_dim, num_resconv_block=2, rot_representation_dim=4,
+                 final_relu_after_skip=True, **_):
         super().__init__()
+        self.final_relu_after_skip = bool(final_relu_after_skip)
         c = input_feature_dim
         self.res_conv = nn.ModuleList([ResConvBlock(c, c) for _ in range(num_resconv_block)])
         self.more_mlps = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c), nn.ReLU())
@@ -205,12 +262,17 @@ class PoseHead(_NoForward):
 
 
 class MLPHead(_NoForward):
-    def __init__(self, input_feature_dim, output_dim, num_mlp_layers=2, hidden_dim=None, **_):
+    """num_mlp_layers / hidden_dim / activation ("relu" | "gelu"): SURVEY App. A.6 VERIFY items."""
+
+    def __init__(self, input_feature_dim, output_dim, num_mlp_layers=2, hidden_dim=None, activation="relu", **_):
         super().__init__()
+        if activation not in ("relu", "gelu"):
+            raise ValueError(f"MLPHead activation {activation!r}")
         hidden_dim = hidden_dim or input_feature_dim
+        self.activation = activation
         layers, d = [], input_feature_dim
         for _i in range(num_mlp_layers):
-            layers += [nn.Linear(d, hidden_dim), nn.ReLU()]
+            layers += [nn.Linear(d, hidden_dim), nn.ReLU() if activation == "relu" else nn.GELU()]
             d = hidden_dim
         layers.append(nn.Linear(d, output_dim))
         self.mlp = nn.Sequential(*layers)

@@ -54,7 +54,10 @@ class MapAnythingOracle(nn.Module):
         self.info_sharing_type = info_sharing_config["model_type"]
         self.info_sharing_return_type = info_sharing_config["model_return_type"]
         self.pred_head_type = pred_head_config["type"]
-        assert self.info_sharing_type == "alternating_attention" and self.info_sharing_return_type == "intermediate_features"
+        assert self.info_sharing_type in ("alternating_attention", "global_attention")
+        assert self.info_sharing_return_type == "intermediate_features"
+        if self.info_sharing_type == "global_attention":   # reference model.py:271-284 (gat_ifr_24_layers.yaml)
+            info_sharing_config["module_args"].setdefault("attention_pattern", "global")
         assert self.pred_head_type == "dpt+pose"
         assert pred_head_config["adaptor_type"] == "raydirs+depth+pose+confidence+mask"
         self.scene_rep_type = "raydirs+depth+pose+confidence+mask"

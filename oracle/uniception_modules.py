@@ -97,26 +97,82 @@ def sinusoid_table(n_rows: int, dim: int, base: float = 10000.0) -> torch.Tensor
 
 class MultiViewAlternatingAttentionTransformerIFR(nn.Module):
     """Even blocks attend globally over all V*N + T tokens, odd blocks per view over N tokens (extra tokens bypass
-    them).  Returns the final normed features plus normed snapshots after the blocks in `indices`."""
+    them).  Returns the final normed features plus normed snapshots after the blocks in `indices`.
+
+    Switches for what SURVEY App. A.3 marks VERIFY (a real checkpoint / the uniception source decides; the CUDA path
+    has the same switches, tests/test_variants_gpu.py):
+      global_attention_first   True: even blocks global (default) / False: even blocks frame-wise
+      attention_pattern        "alternating" (model_type alternating_attention) / "global" (model_type global_attention,
+                               configs/model/info_sharing/gat_ifr_24_layers.yaml: every block attends over all views)
+      view_pe_variant          "ref_only": view 0 gets table row 0, the others nothing (default, variant (i));
+                               "ref_vs_rest": view 0 row 0, every other view row 1 (variant (ii));
+                               "per_view_index": view v > 0 gets row idx[v] -- random in [1, max_num_views_for_pe) when
+                               use_rand_idx_pe_for_non_reference_views (aat_ifr_24_layers_w_view_pe.yaml), else v
+      use_entropy_scaling      softmax scale = head_dim^-0.5 * log(n_keys) / log(entropy_scaling_ref_len)
+                               (aat_ifr_*_escaling.yaml; the constant is an assumption)"""
 
     def __init__(self, name: str, input_embed_dim: int, indices: Sequence[int] = (11, 17), norm_intermediate: bool = True,
                  size: Optional[str] = None, depth: int = 24, dim: int = 768, num_heads: int = 12, mlp_ratio: float = 4.0,
                  distinguish_ref_and_non_ref_views: bool = True, use_pe_for_non_reference_views: bool = False,
-                 max_num_views_for_pe: int = 1000, gradient_checkpointing: bool = False,
-                 custom_positional_encoding=None, **_):
+                 use_rand_idx_pe_for_non_reference_views: bool = False, max_num_views_for_pe: int = 1000,
+                 max_num_views: Optional[int] = None, gradient_checkpointing: bool = False,
+                 custom_positional_encoding=None, global_attention_first: bool = True, attention_pattern: str = "alternating",
+                 view_pe_variant: Optional[str] = None, use_entropy_scaling: bool = False,
+                 entropy_scaling_ref_len: Optional[int] = None, **_):
         super().__init__()
-        assert custom_positional_encoding is None and not use_pe_for_non_reference_views
+        assert custom_positional_encoding is None
         self.name, self.dim, self.depth, self.num_heads = name, dim, depth, num_heads
         self.indices = list(indices)
         self.norm_intermediate = norm_intermediate
         self.distinguish_ref_and_non_ref_views = distinguish_ref_and_non_ref_views
+        self.global_attention_first, self.attention_pattern = global_attention_first, attention_pattern
+        if view_pe_variant is None:
+            view_pe_variant = "per_view_index" if (use_rand_idx_pe_for_non_reference_views or use_pe_for_non_reference_views) \
+                else "ref_only"
+        self.view_pe_variant = view_pe_variant
+        self.use_rand_idx = use_rand_idx_pe_for_non_reference_views
+        self.max_views = int(max_num_views or max_num_views_for_pe)
+        self.fixed_view_pe_indices = None  # tests: the indices of views 1..V-1 instead of random draws
+        self.use_entropy_scaling = use_entropy_scaling
+        self.entropy_scaling_ref_len = entropy_scaling_ref_len
         self.proj_embed = nn.Linear(input_embed_dim, dim) if input_embed_dim != dim else nn.Identity()
         self.self_attention_blocks = nn.ModuleList(
             [OracleBlock(dim, num_heads, mlp_ratio, layer_scale=False) for _ in range(depth)]
         )
         self.norm = nn.LayerNorm(dim, eps=1e-6)
-        # fixed (non-learned, non-persistent) view positional table; only row 0 (reference view) is used here
-        self.register_buffer("view_pos_table", sinusoid_table(max_num_views_for_pe, dim), persistent=False)
+        # fixed (non-learned, non-persistent) view positional table
+        self.register_buffer("view_pos_table", sinusoid_table(self.max_views, dim), persistent=False)
+
+    def view_pe_rows(self, v: int, first_view: int = 0) -> Optional[List[int]]:
+        """Table row per view (None entry = no PE), for views first_view .. first_view + v - 1 of the scene."""
+        if not self.distinguish_ref_and_non_ref_views and self.view_pe_variant == "ref_only":
+            return None
+        rows = []
+        for g in range(first_view, first_view + v):
+            if g == 0:
+                rows.append(0)
+            elif self.view_pe_variant == "ref_only":
+                rows.append(None)
+            elif self.view_pe_variant == "ref_vs_rest":
+                rows.append(1)
+            else:
+                if self.fixed_view_pe_indices is not None:
+                    rows.append(int(self.fixed_view_pe_indices[g - 1]))
+                elif self.use_rand_idx:
+                    rows.append(int(torch.randint(1, self.max_views, (1,))))
+                else:
+                    rows.append(g)
+        return rows
+
+    def is_global(self, i: int) -> bool:
+        return self.attention_pattern == "global" or ((i % 2 == 0) == self.global_attention_first)
+
+    def softmax_scale_factor(self, n_keys: int) -> float:
+        if not self.use_entropy_scaling:
+            return 1.0
+        import math
+
+        return math.log(n_keys) / math.log(self.entropy_scaling_ref_len or n_keys)
 
     def forward(self, features: List[torch.Tensor], additional_input_tokens: Optional[torch.Tensor] = None):
         """features: V x (B, C, h, w); additional_input_tokens: (B, C, T).
@@ -130,9 +186,13 @@ class MultiViewAlternatingAttentionTransformerIFR(nn.Module):
             t = additional_input_tokens.shape[2]
             x = torch.cat([x, additional_input_tokens.transpose(1, 2)], dim=1)
         x = self.proj_embed(x)
-        if self.distinguish_ref_and_non_ref_views:
-            pe = self.view_pos_table[0].to(x.dtype).view(1, 1, -1)
-            x = torch.cat([x[:, :n] + pe, x[:, n:]], dim=1)
+        rows = self.view_pe_rows(v)
+        if rows is not None:
+            parts = []
+            for i, r in enumerate(rows):
+                xi = x[:, i * n:(i + 1) * n]
+                parts.append(xi if r is None else xi + self.view_pos_table[r].to(x.dtype).view(1, 1, -1))
+            x = torch.cat(parts + [x[:, v * n:]], dim=1)
 
         def snapshot(y):
             y = self.norm(y)
@@ -142,10 +202,11 @@ class MultiViewAlternatingAttentionTransformerIFR(nn.Module):
 
         inter = []
         for i, blk in enumerate(self.self_attention_blocks):
-            if i % 2 == 0:
-                x = blk(x)
+            if self.is_global(i):
+                x = blk(x, scale_factor=self.softmax_scale_factor(x.shape[1]))
             else:
-                frames = blk(x[:, : v * n].reshape(b * v, n, self.dim)).reshape(b, v * n, self.dim)
+                frames = blk(x[:, : v * n].reshape(b * v, n, self.dim), scale_factor=self.softmax_scale_factor(n))
+                frames = frames.reshape(b, v * n, self.dim)
                 x = torch.cat([frames, x[:, v * n :]], dim=1) if t else frames
             if i in self.indices:
                 if self.norm_intermediate:
@@ -239,8 +300,12 @@ class DPTRegressionProcessor(nn.Module):
 # A.6 pose head, scale head
 # ------------------------------------------------------------------------------------------------
 class ResConvBlock(nn.Module):
-    def __init__(self, cin: int, cout: int):
+    """final_relu_after_skip=True: relu(skip + conv3(y)) (default); False: skip + relu(conv3(y)) -- the Reloc3r / ACE form
+    SURVEY App. A.6 cites (a VERIFY item: only the uniception source decides; the weights are the same either way)."""
+
+    def __init__(self, cin: int, cout: int, final_relu_after_skip: bool = True):
         super().__init__()
+        self.final_relu_after_skip = final_relu_after_skip
         self.head_skip = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
         self.res_conv1 = nn.Conv2d(cin, cout, 1)
         self.res_conv2 = nn.Conv2d(cout, cout, 3, padding=1)
@@ -250,15 +315,15 @@ class ResConvBlock(nn.Module):
         y = F.relu(self.res_conv1(x))
         y = F.relu(self.res_conv2(y))
         y = self.res_conv3(y)
-        return F.relu(self.head_skip(x) + y)
+        return F.relu(self.head_skip(x) + y) if self.final_relu_after_skip else self.head_skip(x) + F.relu(y)
 
 
 class PoseHead(nn.Module):
     def __init__(self, patch_size: int, input_feature_dim: int, num_resconv_block: int = 2,
-                 rot_representation_dim: int = 4, **_):
+                 rot_representation_dim: int = 4, final_relu_after_skip: bool = True, **_):
         super().__init__()
         c = input_feature_dim
-        self.res_conv = nn.ModuleList([ResConvBlock(c, c) for _ in range(num_resconv_block)])
+        self.res_conv = nn.ModuleList([ResConvBlock(c, c, final_relu_after_skip) for _ in range(num_resconv_block)])
         self.more_mlps = nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, c), nn.ReLU())
         self.fc_t = nn.Linear(c, 3)
         self.fc_rot = nn.Linear(c, rot_representation_dim)
@@ -271,13 +336,15 @@ class PoseHead(nn.Module):
 
 
 class MLPHead(nn.Module):
-    def __init__(self, input_feature_dim: int, output_dim: int, num_mlp_layers: int = 2, hidden_dim: Optional[int] = None, **_):
+    def __init__(self, input_feature_dim: int, output_dim: int, num_mlp_layers: int = 2, hidden_dim: Optional[int] = None,
+                 activation: str = "relu", **_):
         super().__init__()
         hidden_dim = hidden_dim or input_feature_dim
+        self.activation = activation
         layers: List[nn.Module] = []
         d = input_feature_dim
         for _ in range(num_mlp_layers):
-            layers += [nn.Linear(d, hidden_dim), nn.ReLU()]
+            layers += [nn.Linear(d, hidden_dim), nn.ReLU() if activation == "relu" else nn.GELU()]
             d = hidden_dim
         layers.append(nn.Linear(d, output_dim))
         self.mlp = nn.Sequential(*layers)

@@ -34,14 +34,15 @@ class OracleAttention(nn.Module):
         self.qkv = nn.Linear(dim, 3 * dim, bias=True)
         self.proj = nn.Linear(dim, dim, bias=True)
 
-    def forward(self, x):
+    def forward(self, x, scale_factor: float = 1.0):
         b, n, c = x.shape
         hd = c // self.num_heads
         qkv = self.qkv(x).view(b, n, 3, self.num_heads, hd).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
         if USE_SDPA:
-            return self.proj(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c))
-        att = torch.softmax((q * hd**-0.5) @ k.transpose(-1, -2), dim=-1)
+            o = F.scaled_dot_product_attention(q, k, v, scale=hd**-0.5 * scale_factor)
+            return self.proj(o.transpose(1, 2).reshape(b, n, c))
+        att = torch.softmax((q * (hd**-0.5 * scale_factor)) @ k.transpose(-1, -2), dim=-1)
         return self.proj((att @ v).transpose(1, 2).reshape(b, n, c))
 
 
@@ -76,8 +77,8 @@ class OracleBlock(nn.Module):
         self.mlp = OracleMlp(dim, int(dim * mlp_ratio))
         self.ls2 = OracleLayerScale(dim) if layer_scale else nn.Identity()
 
-    def forward(self, x):
-        x = x + self.ls1(self.attn(self.norm1(x)))
+    def forward(self, x, scale_factor: float = 1.0):
+        x = x + self.ls1(self.attn(self.norm1(x), scale_factor))
         return x + self.ls2(self.mlp(self.norm2(x)))
 
 

@@ -313,6 +313,24 @@ def test_memory_efficient_inference_is_identical():
             assert torch.equal(x[k], y[k]), k
 
 
+def test_infer_scene_postprocessing_equals_per_view_postprocessing():
+    """infer() post-processes a whole scene with one launch set (postprocess_scene); the per-view function of the reference's
+    surface (postprocess_model_outputs_for_inference) must give bit-identical results on the same forward outputs."""
+    from mapanything_b200.inference import postprocess_model_outputs_for_inference
+    from oracle.config import tiny_config
+
+    _, model = _build(tiny_config, seed=8, init="reference")
+    views = [{**v, "img": v["img"].cuda()} for v in _views(4, 70, seed=8)]
+    kw = dict(apply_confidence_mask=True, confidence_percentile=30)
+    a = model.infer([dict(v) for v in views], **kw)
+    b = postprocess_model_outputs_for_inference(model([dict(v) for v in views]), views, **kw)
+    assert len(a) == len(b) == 4
+    for x, y in zip(a, b):
+        assert set(x.keys()) == set(y.keys())
+        for k in x:
+            assert x[k].shape == y[k].shape and torch.equal(x[k], y[k]), k
+
+
 def test_infer_confidence_mask_removes_requested_fraction():
     """apply_confidence_mask=True (reference inference.py:393-415): per image, about `confidence_percentile` % of the pixels
     fall below the quantile threshold and leave the final mask."""
