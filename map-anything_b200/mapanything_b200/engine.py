@@ -249,6 +249,17 @@ class Engine:
                 Lin3(rb.res_conv2.weight.detach().permute(0, 2, 3, 1), rb.res_conv2.bias, group=cin),
                 Lin3(rb.res_conv3.weight, rb.res_conv3.bias),
             ))
+        # MA_POSE_HEAD=bf16 (default): the three convolutions of each ResConvBlock run with plain bf16 operands (fp32
+        # accumulate, fp32 residual chain) -- they act on 1369 tokens per view whose average is what the MLPs see, so bf16
+        # rounding averages out (measured: rotation / translation error vs the fp32 oracle unchanged),
+        # and the split-bf16 form cost 3x the MMA work (1.05 ms of a 26 ms step).  The pooled MLPs and the output layer,
+        # whose results are normalised / exponentiated, stay in split-bf16 (~fp32).  MA_POSE_HEAD=split restores round 1.
+        import os as _os
+
+        self.pose_bf16 = _os.environ.get("MA_POSE_HEAD", "bf16") != "split"
+        self.pose_blocks_bf16 = [(
+            Lin(rb.res_conv1.weight, rb.res_conv1.bias), _conv3x3(rb.res_conv2), Lin(rb.res_conv3.weight, rb.res_conv3.bias),
+        ) for rb in ph.res_conv]
         self.pose_mlp = [Lin3(ph.more_mlps[0].weight, ph.more_mlps[0].bias), Lin3(ph.more_mlps[2].weight, ph.more_mlps[2].bias)]
         self.pose_out = Lin3(torch.cat([ph.fc_t.weight, ph.fc_rot.weight], 0), torch.cat([ph.fc_t.bias, ph.fc_rot.bias], 0))
         self.scale_mlp = [Lin3(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
@@ -659,10 +670,34 @@ class Engine:
         ops.bilinear_ac(o, up, virtual_hw=up_virtual)
         return up
 
-    def pose_head(self, x32: torch.Tensor, n: int, hp: int, wp: int, out: torch.Tensor):
-        """Pose head in split-bf16 precision. x32 fp32 [n*N][D] (final info-sharing features) -> out fp32 [n][7] = (t | q)."""
+    def pose_head(self, x32: torch.Tensor, n: int, hp: int, wp: int, out: torch.Tensor, x16: Optional[torch.Tensor] = None):
+        """x32 fp32 [n*N][D] (final info-sharing features; x16 = the same in bf16) -> out fp32 [n][7] = (t | q)."""
         N = hp * wp
         D = x32.shape[1]
+        if self.pose_bf16 and self.pose_relu_after_skip and x16 is not None:
+            xb = x16
+            for c1, c2, c3 in self.pose_blocks_bf16:
+                u = self._lin(xb, c1, act=MA_ACT_RELU)
+                u2 = self._conv3(u.view(n, hp, wp, c1.n), c2, act=MA_ACT_RELU).reshape(n * N, c2.n)
+                xn = self._empty(n * N, c3.n, dtype=torch.float32)
+                xb = self._empty(n * N, c3.n)   # bf16 copy of relu(x + y) = the next block's GEMM operand, same launch
+                ops.gemm(u2, c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU, act_after_residual=True, out_relu=xb)
+                x32 = xn
+        else:
+            x32 = self._pose_blocks_split(x32, n, hp, wp)
+        pooled = self._empty(n, D, dtype=torch.float32)
+        ops.token_mean_f32(x32.view(n, N, D), pooled)
+        g = pooled
+        for lin in self.pose_mlp:
+            gn = self._empty(n, lin.n, dtype=torch.float32)
+            ops.gemm(ops.split3(g), lin.w, gn, bias=lin.b, act=MA_ACT_RELU)
+            g = gn
+        ops.gemm(ops.split3(g), self.pose_out.w, out, bias=self.pose_out.b)
+        return out
+
+    def _pose_blocks_split(self, x32: torch.Tensor, n: int, hp: int, wp: int) -> torch.Tensor:
+        """ResConvBlocks in split-bf16 (~fp32) precision."""
+        N = hp * wp
         for c1, c2, c3 in self.pose_blocks:
             u = self._empty(n * N, c1.n, dtype=torch.float32)
             ops.gemm(ops.split3(x32), c1.w, u, bias=c1.b, act=MA_ACT_RELU)
@@ -673,15 +708,7 @@ class Engine:
             ops.gemm(ops.split3(u2), c3.w, xn, bias=c3.b, residual=x32, act=MA_ACT_RELU,
                      act_after_residual=self.pose_relu_after_skip)
             x32 = xn
-        pooled = self._empty(n, D, dtype=torch.float32)
-        ops.token_mean_f32(x32.view(n, N, D), pooled)
-        g = pooled
-        for lin in self.pose_mlp:
-            gn = self._empty(n, lin.n, dtype=torch.float32)
-            ops.gemm(ops.split3(g), lin.w, gn, bias=lin.b, act=MA_ACT_RELU)
-            g = gn
-        ops.gemm(ops.split3(g), self.pose_out.w, out, bias=self.pose_out.b)
-        return out
+        return x32
 
     def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int,
                      final32: Optional[torch.Tensor] = None):
@@ -724,7 +751,7 @@ class Engine:
             else:
                 ops.gemm(g2f, self.reg3.w, rawv[:, :self.reg3.n], bias=self.reg3.b)
             # pose head on the final info-sharing features (split-bf16 precision)
-            self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n])
+            self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
         return raw, pose_raw
 
     def scale_head(self, tok_feat32: torch.Tensor) -> torch.Tensor:
