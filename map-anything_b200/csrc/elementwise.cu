@@ -317,6 +317,64 @@ __global__ void head_linear_small_kernel(const __nv_bfloat16* __restrict__ x, in
   }
 }
 
+// Warp-cooperative form for K = 8 * LPR (LPR = lanes per row, a power of two <= 32): LPR consecutive lanes read one row
+// as LPR 16-byte pieces -- every load instruction of a warp covers 32 / LPR whole rows, 512 contiguous bytes, instead of
+// 32 different rows (the thread-per-row kernel above reached 0.26 of the HBM roofline: ncu / bench, 550 MB in 0.32 ms).
+// Each lane keeps its 8 x N weights in registers, forms N partial dot products and the LPR lanes of a row combine them
+// with a shuffle tree.  Output: N (<= 8) fp32 per row.
+template <int LPR>
+__global__ void head_linear_small_warp_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+                                              int64_t ldw, const float* __restrict__ bias, float* __restrict__ out, int64_t ldo,
+                                              int64_t rows, int N) {
+  constexpr int RPW = 32 / LPR;  // rows per warp instruction
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rsel = lane / LPR;
+  float wr[8][8];  // [n][j]: weights of this lane's 8 input channels
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[n][j] = n < N ? __bfloat162float(w[(int64_t)n * ldw + sub * 8 + j]) : 0.f;
+  float bv = 0.f;
+  if (bias != nullptr && sub < N) bv = __ldg(bias + sub);
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  constexpr int U = 4;  // row groups in flight per warp: 4 x 512 B of loads issued before the first FMA
+  for (int64_t r0 = warp * (RPW * U); r0 < rows; r0 += nwarps * (RPW * U)) {
+    uint4 u[U];
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int64_t row = r0 + t * RPW + rsel;
+      u[t] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < rows) u[t] = __ldcs(reinterpret_cast<const uint4*>(x + row * ldx) + sub);  // streamed once
+    }
+#pragma unroll
+    for (int t = 0; t < U; ++t) {
+      const int64_t row = r0 + t * RPW + rsel;
+      const float xv[8] = {bf16_lo(u[t].x), bf16_hi(u[t].x), bf16_lo(u[t].y), bf16_hi(u[t].y),
+                           bf16_lo(u[t].z), bf16_hi(u[t].z), bf16_lo(u[t].w), bf16_hi(u[t].w)};
+      float acc[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        acc[n] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[n] = fmaf(xv[j], wr[n][j], acc[n]);
+      }
+      // shuffle tree over the LPR lanes of the row; afterwards every lane of the group holds all N sums
+#pragma unroll
+      for (int off = LPR / 2; off >= 1; off >>= 1)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], off);
+      // lane `sub` of the group writes output channel `sub`: N consecutive floats per row leave from N consecutive lanes
+      if (row < rows && sub < N) {
+        float v = acc[0];
+#pragma unroll
+        for (int n = 1; n < 8; ++n) v = sub == n ? acc[n] : v;
+        out[row * ldo + sub] = v + bv;
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Fused dense adaptor + factored-geometry decode + packaging (reference model.py:1683-1741, :1874-1907,
 // geometry.py:855-907, adaptor semantics SURVEY App. A.5/A.6):
@@ -541,8 +599,19 @@ extern "C" int ma_head_linear_small(const void* x, int64_t ldx, const void* w, i
   MA_REQUIRE(N >= 1 && N <= 8 && K >= 8 && K <= 256 && K % 8 == 0 && ldx % 8 == 0 && ldo >= N,
              "ma_head_linear_small: needs N <= 8, K <= 256, K %% 8 == 0 (N=%d K=%d)", N, K);
   MA_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "ma_head_linear_small: x not 16-byte aligned");
-  head_linear_small_kernel<<<grid_for(rows, 128, device_sm_count() * 16), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w), ldw, bias, out, ldo, rows, N, K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x);
+  const __nv_bfloat16* wb = static_cast<const __nv_bfloat16*>(w);
+  const int lpr = K / 8;
+  if (lpr >= 8 && lpr <= 32 && (lpr & (lpr - 1)) == 0) {
+    const int rpw = 32 / lpr;
+    const unsigned grid = grid_for((rows + 4 * rpw - 1) / (4 * rpw) * 32, 256, device_sm_count() * 8);
+    if (lpr == 8) head_linear_small_warp_kernel<8><<<grid, 256, 0, st>>>(xb, ldx, wb, ldw, bias, out, ldo, rows, N);
+    else if (lpr == 16) head_linear_small_warp_kernel<16><<<grid, 256, 0, st>>>(xb, ldx, wb, ldw, bias, out, ldo, rows, N);
+    else head_linear_small_warp_kernel<32><<<grid, 256, 0, st>>>(xb, ldx, wb, ldw, bias, out, ldo, rows, N);
+  } else {
+    head_linear_small_kernel<<<grid_for(rows, 128, device_sm_count() * 16), 128, 0, st>>>(xb, ldx, wb, ldw, bias, out, ldo, rows, N, K);
+  }
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

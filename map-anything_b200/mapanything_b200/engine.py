@@ -274,6 +274,7 @@ class Engine:
         # views 311.1 vs 301.6 views/s (fewer, larger launches); MA_DPT_CHUNK overrides for A/B runs
         self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "8")))
         self.dpt_chunk = self.dpt_chunk_default
+        self.proj_block_n = int(os.environ.get("MA_PROJ_BN", "0"))   # A/B knob: tile code of the attention-projection GEMMs
         # measurement aid (bench.py `strong` record): when a list, every sharded global block appends the CUDA events that
         # bracket its wait for the K/V all-gather on the compute stream
         self.ag_wait_events = None
@@ -370,7 +371,7 @@ class Engine:
         else:
             ops.attention(qkv[:, :dim], qkv[:, dim:2 * dim], qkv[:, 2 * dim:], a, num_heads=heads, num_seqs=num_seqs,
                           q_len=seq_len, kv_len=seq_len, q_seq_stride=seq_stride, kv_seq_stride=seq_stride, scale=scale)
-        ops.gemm(a, bw.proj.w, xr, bias=bw.proj.b, colscale=bw.ls1, residual=xr)
+        ops.gemm(a, bw.proj.w, xr, bias=bw.proj.b, colscale=bw.ls1, residual=xr, block_n=self.proj_block_n)
         ops.layernorm(xr, h, bw.n2w, bw.n2b)
         f = self._lin(h, bw.fc1, act=MA_ACT_GELU)
         ops.gemm(f, bw.fc2.w, xr, bias=bw.fc2.b, colscale=bw.ls2, residual=xr)
