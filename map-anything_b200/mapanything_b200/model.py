@@ -390,6 +390,15 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             res.append(d)
         return res
 
+    def _compute_adaptive_minibatch_size(self, memory_safety_factor: float = 0.95) -> int:
+        """Views per dense-head pass under memory_efficient_inference, by the reference's rule (model.py:1263-1300): free
+        device memory x safety factor / 680 MB per 518 x 518 sample, at least 1.  Memory torch's caching allocator holds
+        but does not use counts as free (the reference empties the cache first; this avoids the synchronising call).  The
+        result is further capped by the engine's normal chunk (8 views), which is what runs when memory is plentiful."""
+        free, _ = torch.cuda.mem_get_info(self.device)
+        free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+        return max(1, int(free * memory_safety_factor / (680 * 1024 * 1024)))
+
     def _forward_scenes(self, views: List[Dict[str, Any]], memory_efficient_inference: bool = False):
         """-> (one dict of [V, ...] output tensors per batch item, the (V,3,H,W) image tensor of each batch item)."""
         batch_size_per_view, _, height, width = views[0]["img"].shape
@@ -403,7 +412,8 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         if height % p or width % p:
             raise AssertionError(f"Input image size ({height}, {width}) must be a multiple of the patch size {p}")
         eng = self.engine()
-        eng.dpt_chunk = min(2, eng.dpt_chunk_default) if memory_efficient_inference else eng.dpt_chunk_default
+        eng.dpt_chunk = min(self._compute_adaptive_minibatch_size(), eng.dpt_chunk_default) if memory_efficient_inference \
+            else eng.dpt_chunk_default
         hp, wp = height // p, width // p
         N = hp * wp
         plan, comm = None, self._shard_comm
