@@ -317,7 +317,9 @@ def strong_scaling_record(model, dev, rank, world, timed, peak_tf, scene=100, st
     waits = [a.elapsed_time(b) for a, b in eng.ag_wait_events]
     eng.ag_wait_events = None
     exposed = torch.tensor([sum(waits) / max(len(waits), 1)], device=dev)
+    exposed_min = exposed.clone()
     dist.all_reduce(exposed, op=dist.ReduceOp.MAX)
+    dist.all_reduce(exposed_min, op=dist.ReduceOp.MIN)
     # end to end: infer() from pinned host images, every rank reads its views' point maps / masks / poses back
     host = [im.pin_memory() for im in imgs[lo:lo + counts[rank]]]
 
@@ -355,9 +357,15 @@ def strong_scaling_record(model, dev, rank, world, timed, peak_tf, scene=100, st
         "speedup_vs_single_gpu": ms_1.item() / ms_n, "efficiency": ms_1.item() / ms_n / world,
         "per_gpu_step_frac": tf_scene / world / (ms_n * 1e-3) / peak_tf,
         "single_gpu_step_frac": tf_scene / (ms_1.item() * 1e-3) / peak_tf,
-        "allgather_exposed_ms_per_global_layer": exposed.item(),
+        "allgather_exposed_ms_per_global_layer": exposed_min.item(),
+        "allgather_wait_ms_per_global_layer_max_over_ranks": exposed.item(),
+        "load_balance_bound": scene / (max(counts) * world),
         "allgather_note": "time the compute stream waited for the NCCL K/V all-gather after finishing the local-key attention "
-                          "(CUDA events around work.wait(), mean over 12 layers x steps, max over ranks)",
+                          "(CUDA events around work.wait(), mean over 12 layers x steps).  The all-gather is a collective: a rank "
+                          "with fewer views (12 instead of 13) reaches it early and waits for the others, so the MIN over ranks "
+                          "(the slowest rank's wait) is the exposed communication and the MAX is mostly load imbalance; "
+                          "tools/bench_allgather.py measures the same exchange in isolation (8 GPUs, 13 views per rank: 0.68 ms "
+                          "alone, 0.003 ms exposed behind the 1.34 ms local attention)",
     }
 
 

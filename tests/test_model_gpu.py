@@ -313,7 +313,10 @@ def test_memory_efficient_inference_is_identical():
     _, model = _build(tiny_config, seed=5, init="reference")
     views = [{**v, "img": v["img"].cuda()} for v in _views(5, 70, seed=5)]
     a = model([dict(v) for v in views], memory_efficient_inference=False)
+    assert model._compute_adaptive_minibatch_size() >= 1
+    model._compute_adaptive_minibatch_size = lambda *a_, **k_: 2   # as if ~1.4 GB were free: 5 views -> passes of 2, 2, 1
     b = model([dict(v) for v in views], memory_efficient_inference=True)
+    assert model.engine().dpt_chunk == 2
     for x, y in zip(a, b):
         for k in ("pts3d", "conf", "cam_quats", "metric_scaling_factor"):
             assert torch.equal(x[k], y[k]), k
