@@ -451,6 +451,48 @@ __device__ __forceinline__ void a2_exp_chunk(const uint32_t (&v)[32], uint32_t* 
   }
 }
 
+// MUFU-only exponentials of a whole 128-score row with the consumption of the results software-pipelined one 32-score chunk
+// behind their issue.  ptxas' own order puts the sum / pack of pair i two MUFU instructions behind pair i (16 clk of MUFU time,
+// less than the MUFU latency), so a warp alone drives the pipe at ~2/3 of its rate (ncu: a single warp's exponential phase takes
+// 1.5x the MUFU time).  Here chunk c+1's exponentials are issued BEFORE chunk c's results are summed, packed and stored, with a
+// warp-level fence between the groups so that the order survives instruction scheduling.
+template <typename StoreFn>
+__device__ __forceinline__ void a2_exp_row_pipelined(uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t (&v2)[32], uint32_t (&v3)[32],
+                                                     float sl2, float mref, uint64_t (&acc)[4], StoreFn&& store) {
+  auto issue = [&](uint32_t (&v)[32]) {   // in place: scores -> probabilities (fp32)
+    const uint64_t sl2_2 = pack2(sl2, sl2), nm2 = pack2(-mref, -mref);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float xa, xb;
+      unpack2(ffma2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), sl2_2, nm2), xa, xb);
+      v[2 * i] = __float_as_uint(fast_exp2(xa));
+      v[2 * i + 1] = __float_as_uint(fast_exp2(xb));
+    }
+  };
+  auto consume = [&](const uint32_t (&v)[32], int chunk) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float ea = __uint_as_float(v[2 * i]), eb = __uint_as_float(v[2 * i + 1]);
+      acc[i & 3] = fadd2(acc[i & 3], pack2(ea, eb));
+      pk[i] = pack_bf16x2(ea, eb);
+    }
+    store(chunk, pk);
+  };
+  issue(v0);
+  __syncwarp();
+  issue(v1);
+  consume(v0, 0);
+  __syncwarp();
+  issue(v2);
+  consume(v1, 1);
+  __syncwarp();
+  issue(v3);
+  consume(v2, 2);
+  __syncwarp();
+  consume(v3, 3);
+}
+
 template <int NQT, int NPOLY>
 __global__ void __launch_bounds__(A2Cfg<NQT>::THREADS, NQT == 2 ? 1 : 2)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -661,32 +703,38 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
         uint32_t v0[32], v1[32], v2[32], v3[32];  // the 128 scores of this thread's row
+        // the row maximum is reduced chunk by chunk UNDER the tensor-memory loads of the following chunks (a warp reads
+        // tensor memory at ~45 B/clk: the four 4 KB loads take ~360 clk whatever the order)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto chunk_max = [&](uint32_t (&v)[32], int c0, float& m) {
+          if (kv_valid < c0 + 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i >= kv_valid) v[i] = __float_as_uint(-INFINITY);
+          }
+          float a = -INFINITY, b = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            a = fmaxf(a, __uint_as_float(v[i]));
+            b = fmaxf(b, __uint_as_float(v[16 + i]));
+          }
+          m = fmaxf(a, b);
+        };
         tmem_ld_32x32b_x32(tmem_s, v0);
+        tmem_ld_wait();
         tmem_ld_32x32b_x32(tmem_s + 32, v1);
+        chunk_max(v0, 0, mx4[0]);
+        tmem_ld_wait();
         tmem_ld_32x32b_x32(tmem_s + 64, v2);
+        chunk_max(v1, 32, mx4[1]);
+        tmem_ld_wait();
         tmem_ld_32x32b_x32(tmem_s + 96, v3);
+        chunk_max(v2, 64, mx4[2]);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[t]);  // S is in registers: the tensor core may overwrite it
-
-        if (kv_valid < ATT_BN) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (i >= kv_valid) v0[i] = __float_as_uint(-INFINITY);
-            if (32 + i >= kv_valid) v1[i] = __float_as_uint(-INFINITY);
-            if (64 + i >= kv_valid) v2[i] = __float_as_uint(-INFINITY);
-            if (96 + i >= kv_valid) v3[i] = __float_as_uint(-INFINITY);
-          }
-        }
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx4[0] = fmaxf(mx4[0], __uint_as_float(v0[i]));
-          mx4[1] = fmaxf(mx4[1], __uint_as_float(v1[i]));
-          mx4[2] = fmaxf(mx4[2], __uint_as_float(v2[i]));
-          mx4[3] = fmaxf(mx4[3], __uint_as_float(v3[i]));
-        }
+        chunk_max(v3, 96, mx4[3]);
         const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
         // lazy rescale: adopt the new maximum only when it grew by more than 2^8
@@ -723,15 +771,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         const uint64_t nm2 = pack2(-mref, -mref);
         if (NPOLY == 0 || kv_valid < ATT_BN) {  // masked columns are -inf: MUFU only (ex2(-inf) = 0 exactly)
-          uint32_t pk[16];
-          a2_exp_chunk<0>(v0, pk, sl2_2, nm2, 0ull, 0.f, acc);
-          tmem_st_32x32b_x16(tmem_p, pk);
-          a2_exp_chunk<0>(v1, pk, sl2_2, nm2, 0ull, 0.f, acc);
-          tmem_st_32x32b_x16(tmem_p + 16, pk);
-          a2_exp_chunk<0>(v2, pk, sl2_2, nm2, 0ull, 0.f, acc);
-          tmem_st_32x32b_x16(tmem_p + 32, pk);
-          a2_exp_chunk<0>(v3, pk, sl2_2, nm2, 0ull, 0.f, acc);
-          tmem_st_32x32b_x16(tmem_p + 48, pk);
+          a2_exp_row_pipelined(v0, v1, v2, v3, sl2, mref, acc,
+                               [&](int chunk, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(tmem_p + 16 * chunk, pk); });
         } else {
           const float kk = 12582912.0f - mref;           // 1.5 * 2^23 - mref, exact for |mref| < 2^22
           const uint64_t k2 = pack2(kk, kk);
