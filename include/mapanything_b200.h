@@ -82,6 +82,15 @@ typedef struct ma_gemm_epilogue {
   int32_t rows_per_group_out;
   int32_t row_offset_out;
   int32_t flags; /* MA_GEMM_* bits */
+  /* Fused narrow head (optional; CTA-pair kernel, N = 128 only -- pass block_n = 2128): when head_out != NULL the tile
+   * values y (after bias / activation) are NOT stored; instead head_out[row][j] = head_bias[j] + sum_n head_w[j][n] * y[n]
+   * for j < 8 is written (fp32, row stride 8).  head_w: fp32 [8][N] (rows >= head_n zero), head_bias: fp32 [8].
+   * Replaces the last 1x1 convolution of the DPT regressor (128 -> 6 channels on every pixel; reference
+   * DPTRegressionProcessor.conv2[2], model.py:1326-1338) as the epilogue of the 3x3 convolution in front of it: the
+   * 128-channel full-resolution map (69 MB per view in bf16) is never written or re-read. */
+  const float* head_w;
+  const float* head_bias;
+  float* head_out;
 } ma_gemm_epilogue;
 
 /* act is applied after the residual add instead of before the column scale (ResConvBlock: relu(skip + y)). */

@@ -298,12 +298,23 @@ static int check_epilogue(const ma_gemm_epilogue* epi, int N, const char* who) {
 extern "C" int ma_conv3x3_bf16(const void* x, int n, int H, int W, int C, const void* w, int64_t ldw, int Cout,
                                const ma_gemm_epilogue* epi, int block_n, void* stream) {
   using namespace ma;
-  MA_REQUIRE(x && w && epi && epi->out, "ma_conv3x3_bf16: null pointer");
+  MA_REQUIRE(x && w && epi && (epi->out || epi->head_out), "ma_conv3x3_bf16: null pointer");
   MA_REQUIRE(n > 0 && H > 0 && W > 0 && C > 0 && Cout > 0, "ma_conv3x3_bf16: bad shape");
+  const bool head = epi->head_out != nullptr;
+  if (head) {  // fused narrow head: the tile values feed 8 dot products instead of being stored
+    MA_REQUIRE(Cout == 128 && (block_n == 0 || block_n == MA_GEMM_2CTA + 128),
+               "ma_conv3x3_bf16: the fused head needs Cout == 128 and the CTA-pair 256x128 tile (block_n 0 / 2128)");
+    MA_REQUIRE(epi->head_w && epi->head_bias && (reinterpret_cast<uintptr_t>(epi->head_w) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(epi->head_bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(epi->head_out) & 15) == 0,
+               "ma_conv3x3_bf16: fused head weights / bias / output missing or not 16-byte aligned");
+    MA_REQUIRE(!epi->residual && !epi->colscale && !epi->out_relu && epi->flags == 0,
+               "ma_conv3x3_bf16: the fused head takes bias + activation only");
+    block_n = MA_GEMM_2CTA + 128;
+  }
   MA_REQUIRE(C % 8 == 0 && ldw % 8 == 0 && ldw >= 9 * (int64_t)C, "ma_conv3x3_bf16: C / ldw must be multiples of 8, ldw >= 9C");
   MA_REQUIRE((int64_t)n * H * W < (1ll << 31), "ma_conv3x3_bf16: too many pixels");
   MA_REQUIRE(epi->rows_per_group_in == 0, "ma_conv3x3_bf16: row remapping is not supported");
-  int rc = check_epilogue(epi, Cout, "ma_conv3x3_bf16");
+  int rc = head ? MA_OK : check_epilogue(epi, Cout, "ma_conv3x3_bf16");
   if (rc != MA_OK) return rc;
 
   // pixel box of one M tile: maximise useful rows / 128 over all bw x bh <= 128 boxes
@@ -357,6 +368,7 @@ extern "C" int ma_gemm_bf16(const void* x, int64_t ldx, const void* w, int64_t l
                             const ma_gemm_epilogue* epi, int block_n, void* stream) {
   using namespace ma;
   MA_REQUIRE(x && w && epi && epi->out, "ma_gemm_bf16: null pointer");
+  MA_REQUIRE(epi->head_out == nullptr, "ma_gemm_bf16: the fused narrow head is implemented for ma_conv3x3_bf16 only");
   MA_REQUIRE(M > 0 && N > 0 && K > 0, "ma_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
   MA_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "ma_gemm_bf16: K/ldx/ldw must be multiples of 8 (K=%d ldx=%lld ldw=%lld)",
              K, (long long)ldx, (long long)ldw);

@@ -25,7 +25,7 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;  // this CTA's half of the N rows
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 1024;  // padded: the epilogue stages behind it stay 1024-byte aligned
-  static constexpr int EPI_BYTES = G2_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int EPI_BYTES = G2_EPI_WARPS * EPI_STAGE_BYTES;  // fused head: reused as hw[8][128] + partial sums
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;
 };
@@ -157,6 +157,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int quarter = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t leader_tempty0 = mapa_shared(smem_u32(&bar_tempty[0]), 0);
+    // fused narrow head (BN == 128 only): the epilogue stages are free (no TMA epilogue in this mode): stage 0 .. 3 hold
+    // the head weights hw[8][128] fp32 (4 KB), stages 4 .. 7 the partial sums of the upper column half, [tile parity][row][8]
+    const bool head = BN == 128 && ep.head_out != nullptr;
+    float* hw = reinterpret_cast<float*>(sEpi);
+    float* hpart = reinterpret_cast<float*>(sEpi + 4 * EPI_STAGE_BYTES);  // [2][128][8] fp32 = 8 KB
+    if (head) {
+      for (int i = threadIdx.x - 128; i < 8 * BN; i += G2_EPI_WARPS * 32) hw[i] = __ldg(ep.head_w + i);
+      named_bar_sync(1, G2_EPI_WARPS * 32);
+    }
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
       const int acc = it & 1;
@@ -180,6 +189,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
       mbar_wait(&bar_tfull[acc], acc_phase);
       tc_fence_after();
+      float hsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int c = 0; c < BN / 2; c += 32) {
         const int col0 = n0 + half * (BN / 2) + c;
@@ -187,7 +197,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (epi_mode) {  // warp-uniform: asynchronous bulk tensor store / reduce-add of the 32 x 32 chunk
+        if (head) {
+          epilogue_head_chunk(ep, v, col0, BN, hw, hsum);
+        } else if (epi_mode) {  // warp-uniform: asynchronous bulk tensor store / reduce-add of the 32 x 32 chunk
           if (col0 < N) epilogue_tma_chunk(&tmap_out, epi_mode, ep, v, tm * GEMM_BM + quarter * 32, col0, epi_stage, lane);
         } else if (row_ok && col0 < N) {
           epilogue_store_chunk(ep, v, m, col0, N);
@@ -195,7 +207,25 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(leader_tempty0 + acc * 8);
+      if (lane == 0) mbar_arrive_remote(leader_tempty0 + acc * 8);  // the accumulator is drained: the next tile's MMAs may start
+      if (head) {
+        // the two warps that own the same 32 rows (column halves 0 / 1) meet at a 64-thread named barrier: the upper half
+        // hands its 8 partial sums over through shared memory (double-buffered by tile parity), the lower half adds the
+        // head bias and writes 8 fp32 per pixel (consecutive rows -> 1 KB contiguous per warp)
+        float* mine = hpart + ((it & 1) * 128 + quarter * 32 + lane) * 8;
+        if (half == 1) {
+          *reinterpret_cast<float4*>(mine) = make_float4(hsum[0], hsum[1], hsum[2], hsum[3]);
+          *reinterpret_cast<float4*>(mine + 4) = make_float4(hsum[4], hsum[5], hsum[6], hsum[7]);
+        }
+        named_bar_sync(2 + quarter, 64);
+        if (half == 0 && row_ok) {
+          const float4 a = *reinterpret_cast<const float4*>(mine), b = *reinterpret_cast<const float4*>(mine + 4);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.head_bias)), b1 = __ldg(reinterpret_cast<const float4*>(ep.head_bias) + 1);
+          float4* o = reinterpret_cast<float4*>(ep.head_out + static_cast<size_t>(m) * 8);
+          o[0] = make_float4(hsum[0] + a.x + b0.x, hsum[1] + a.y + b0.y, hsum[2] + a.z + b0.z, hsum[3] + a.w + b0.w);
+          o[1] = make_float4(hsum[4] + b.x + b1.x, hsum[5] + b.y + b1.y, hsum[6] + b.z + b1.z, hsum[7] + b.w + b1.w);
+        }
+      }
     }
     if (epi_mode && lane == 0) tma_store_wait<0>();
   }

@@ -185,6 +185,40 @@ __device__ __forceinline__ void epilogue_store_chunk(const ma_gemm_epilogue& ep,
 }
 
 
+// Fused narrow head: this thread's 32 accumulator columns [col0, col0 + 32) of its row get bias + activation and are folded
+// into 8 running dot products with the head weights (shared memory copy hw[8][N], read as broadcast float4).
+__device__ __forceinline__ void epilogue_head_chunk(const ma_gemm_epilogue& ep, const uint32_t (&acc)[32], int col0, int N,
+                                                    const float* __restrict__ hw, float (&h)[8]) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (ep.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (ep.act == MA_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (ep.act == MA_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const float4* w4 = reinterpret_cast<const float4*>(hw + n * N + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 w = w4[j];
+      h[n] = fmaf(v[4 * j], w.x, h[n]); h[n] = fmaf(v[4 * j + 1], w.y, h[n]);
+      h[n] = fmaf(v[4 * j + 2], w.z, h[n]); h[n] = fmaf(v[4 * j + 3], w.w, h[n]);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // TMA epilogue (plain GEMMs whose output rows are the GEMM rows): the warp's 32 x 32 accumulator chunk gets
 // bias / activation / column scale applied per thread (thread = row), is written to a warp-private, hardware-swizzled

@@ -40,6 +40,9 @@ class GemmEpilogue(C.Structure):
         ("rows_per_group_out", C.c_int32),
         ("row_offset_out", C.c_int32),
         ("flags", C.c_int32),
+        ("head_w", C.c_void_p),
+        ("head_bias", C.c_void_p),
+        ("head_out", C.c_void_p),
     ]
 
 

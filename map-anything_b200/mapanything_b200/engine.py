@@ -233,6 +233,19 @@ class Engine:
             })
         reg = model.dpt_regressor_head
         self.reg1, self.reg2, self.reg3 = _conv3x3(reg.conv1), _conv3x3(reg.conv2[0]), _conv1x1(reg.conv2[2])
+        # the last 1x1 conv (hidden -> 6) as the epilogue of the 3x3 conv in front of it (ma_gemm_epilogue.head_*): fp32
+        # weights [8][128] (the kernel form needs hidden = 128 and <= 8 outputs; MA_FUSED_HEAD=0 keeps the separate kernel)
+        import os as _os2
+
+        self.reg3_fused = None
+        w3 = reg.conv2[2].weight.detach().reshape(reg.conv2[2].weight.shape[0], -1)
+        if w3.shape[1] == 128 and w3.shape[0] <= 8 and self.reg2.n == 128 and _os2.environ.get("MA_FUSED_HEAD", "1") != "0":
+            hw = torch.zeros(8, 128, device=self.device, dtype=torch.float32)
+            hb = torch.zeros(8, device=self.device, dtype=torch.float32)
+            hw[:w3.shape[0]] = w3.float()
+            if reg.conv2[2].bias is not None:
+                hb[:w3.shape[0]] = reg.conv2[2].bias.detach().float()
+            self.reg3_fused = (hw.contiguous(), hb.contiguous())
 
         ph = model.pose_head
         self.pose_relu_after_skip = bool(getattr(ph, "final_relu_after_skip", True))
@@ -745,8 +758,13 @@ class Engine:
             g1 = self._conv3(p1, self.reg1)
             g1u = self._empty(n, H, W, g1.shape[3])
             ops.bilinear_ac(g1, g1u)
+            rawv = raw[s * H * W:(s + n) * H * W]
+            if self.reg3_fused is not None and raw.shape[1] == 8:
+                ops.conv3x3_head(g1u, self.reg2.w, self.reg2.b, MA_ACT_RELU, self.reg3_fused[0], self.reg3_fused[1], rawv)
+                self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
+                continue
             g2 = self._conv3(g1u, self.reg2, act=MA_ACT_RELU)
-            g2f, rawv = g2.reshape(n * H * W, -1), raw[s * H * W:(s + n) * H * W]
+            g2f = g2.reshape(n * H * W, -1)
             if self.reg3.n <= 8 and self.reg3.k <= 256 and self.reg3.k % 8 == 0:
                 ops.head_linear_small(g2f, self.reg3.w, self.reg3.b, rawv)   # 128 -> 6 per pixel: streaming kernel
             else:

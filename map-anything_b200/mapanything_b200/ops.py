@@ -166,6 +166,33 @@ def gemm(
     return out
 
 
+def conv3x3_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int, head_w: torch.Tensor,
+                 head_bias: torch.Tensor, head_out: torch.Tensor) -> torch.Tensor:
+    """3x3 conv (Cout = 128) whose output is consumed in the epilogue by a narrow linear head instead of being stored:
+    head_out[pixel][j] = head_bias[j] + sum_c head_w[j][c] * act(conv(x)[pixel][c] + bias[c]), j < 8 (fp32, row stride 8).
+    x NHWC bf16, w [128, 9*C] bf16, head_w fp32 [8][128], head_bias fp32 [8].  See ma_gemm_epilogue.head_*."""
+    _req(x, torch.bfloat16, "x")
+    n, H, W, C_ = x.shape
+    Cout = w.shape[0]
+    if Cout != 128 or w.shape[1] != 9 * C_ or head_w.shape != (8, 128) or head_out.shape[-1] != 8:
+        raise ValueError("conv3x3_head: needs Cout == 128, head_w [8,128], head_out [..., 8]")
+    _req(head_w, torch.float32, "head_w")
+    _req(head_bias, torch.float32, "head_bias")
+    _req(head_out, torch.float32, "head_out")
+    ep = GemmEpilogue()
+    ep.out_dtype = MA_BF16
+    ep.act = act
+    ep.bias = _ptr(_f32c(bias, Cout, "bias"))
+    ep.head_w, ep.head_bias, ep.head_out = head_w.data_ptr(), head_bias.data_ptr(), head_out.data_ptr()
+    n_alg, k_alg = ALGO_NK.get(w.data_ptr(), (Cout, 9 * C_))
+    with launch("conv3x3", 2.0 * n * H * W * (n_alg * k_alg + 8 * Cout), tag=f"{n}x{H}x{W}x{C_}->{Cout}+head") as rec:
+        check(_lib.load().ma_conv3x3_bf16(x.data_ptr(), n, H, W, C_, w.data_ptr(), w.stride(0), Cout, C.byref(ep), 0, _stream()),
+              "ma_conv3x3_bf16")
+        if PROFILE is not None:
+            rec.tag = f"{n}x{H}x{W}x{C_}->{Cout}+head|{_gemm_kernel_name()}"
+    return head_out
+
+
 def conv3x3(
     x: torch.Tensor,
     w: torch.Tensor,

@@ -43,7 +43,7 @@ def test_struct_layouts_match_header_sizes():
     """ma_gemm_epilogue / ma_attn_ext field-for-field sizes (LP64): guards against a header edit without a binding edit."""
     from mapanything_b200 import _lib
 
-    assert ctypes.sizeof(_lib.GemmEpilogue) == 8 + 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 8 + 4 * 4
+    assert ctypes.sizeof(_lib.GemmEpilogue) == 8 + 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 8 + 4 * 4 + 3 * 8
     assert ctypes.sizeof(_lib.AttnExt) == 4 + 4 + 64 + 64 + 8 + 8 + 8 + 4 + 4 + 8 + 8
 
 
@@ -91,8 +91,12 @@ def test_info_sharing_variants_construct_with_reference_key_layout():
     ma = cfg["info_sharing_config"]["module_args"]
     assert (ma["depth"], ma["dim"], ma["num_heads"], ma["indices"]) == (48, 1024, 16, [11, 23, 35])
     assert ma["distinguish_ref_and_non_ref_views"] is False
+    gat = mapanything_variant_config("gat_ifr_24_layers")   # round 2: global attention in every block + view-index PE
+    assert gat["info_sharing_config"]["model_type"] == "global_attention"
+    m = MapAnything(**tiny_config())
+    assert m.info_sharing.is_global(0) and not m.info_sharing.is_global(1)
     with pytest.raises(ValueError, match="info_sharing must be one of"):
-        mapanything_variant_config("gat_ifr_24_layers")
+        mapanything_variant_config("cat_ifr_dust3r")
 
 
 def test_header_is_plain_c_and_library_links_from_c(tmp_path):
