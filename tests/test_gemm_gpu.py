@@ -137,3 +137,33 @@ def test_conv3x3_implicit_gemm_matches_torch(n, H, W, C, Cout, bn):
         o3 = torch.empty(n * H * W, Cout, device="cuda", dtype=torch.bfloat16)
         ops.conv3x3(x, w, o3, bias=bias, act=MA_ACT_RELU, block_n=bn)
         _check(o3, torch.relu(ref), 1e-2, "conv3x3 + relu")
+
+
+@pytest.mark.parametrize("n,H,W,C", [(2, 70, 70, 128), (1, 518, 301, 128), (3, 9, 5, 64)])
+def test_conv3x3_fused_narrow_head_matches_torch(n, H, W, C):
+    """ma_gemm_epilogue.head_*: conv3x3 (Cout = 128) + bias + ReLU consumed by a 128 -> 6 linear head in the epilogue (two
+    64-column half-row warps combine through shared memory) vs F.conv2d -> relu -> F.linear in fp32 on the same bf16 operands.
+    The hidden map is kept in fp32 here (the separate-kernel path rounds it to bf16 first)."""
+    import torch.nn.functional as F
+
+    from mapanything_b200 import ops
+    from mapanything_b200.ops import MA_ACT_RELU
+
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(H * 7 + W)
+    x = torch.randn(n, H, W, C, device="cuda", generator=g).bfloat16()
+    w4 = (torch.randn(128, C, 3, 3, device="cuda", generator=g) / (9 * C) ** 0.5).bfloat16()
+    bias = torch.randn(128, device="cuda", generator=g)
+    w = w4.permute(0, 2, 3, 1).reshape(128, 9 * C).contiguous()
+    hw = torch.zeros(8, 128, device="cuda")
+    hw[:6] = torch.randn(6, 128, device="cuda", generator=g) / 128 ** 0.5
+    hb = torch.zeros(8, device="cuda")
+    hb[:6] = torch.randn(6, device="cuda", generator=g)
+    hidden = torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), bias, padding=1)).permute(0, 2, 3, 1).reshape(-1, 128)
+    ref = hidden @ hw.t() + hb
+    out = torch.full((n * H * W, 8), float("nan"), device="cuda")
+    ops.conv3x3_head(x, w, bias, MA_ACT_RELU, hw, hb, out)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    _check(out[:, :6], ref[:, :6], 2e-3, "conv3x3 + fused head")
+    assert out[:, 6:].abs().max().item() == 0.0
