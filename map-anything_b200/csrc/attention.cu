@@ -53,6 +53,7 @@ struct AttnParams {
   // kv_split > 1: the kv tile range is cut into kv_split equal parts, each handled by its own CTA, which writes its
   // partial softmax state to state_o + part * split_stride_o / state_m + part * split_stride_m (ma_attention_merge joins
   // them).  Doubles / triples the CTA count when (query blocks x heads) fills the last wave of SMs badly.
+  int pingpong;              // two-tile kernel: alternate the exponential phases of the two softmax warpgroups
   int kv_split, split_from;  // CTAs of slots >= split_from are split (tail-only splitting); 0 = every slot
   int64_t split_stride_o, split_stride_m;
 };
@@ -456,9 +457,10 @@ __device__ __forceinline__ void a2_exp_chunk(const uint32_t (&v)[32], uint32_t* 
 // less than the MUFU latency), so a warp alone drives the pipe at ~2/3 of its rate (ncu: a single warp's exponential phase takes
 // 1.5x the MUFU time).  Here chunk c+1's exponentials are issued BEFORE chunk c's results are summed, packed and stored, with a
 // warp-level fence between the groups so that the order survives instruction scheduling.
-template <typename StoreFn>
+template <typename StoreFn, typename HandoverFn>
 __device__ __forceinline__ void a2_exp_row_pipelined(uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t (&v2)[32], uint32_t (&v3)[32],
-                                                     float sl2, float mref, uint64_t (&acc)[4], StoreFn&& store) {
+                                                     float sl2, float mref, uint64_t (&acc)[4], StoreFn&& store,
+                                                     HandoverFn&& handover) {
   auto issue = [&](uint32_t (&v)[32]) {   // in place: scores -> probabilities (fp32)
     const uint64_t sl2_2 = pack2(sl2, sl2), nm2 = pack2(-mref, -mref);
 #pragma unroll
@@ -488,6 +490,8 @@ __device__ __forceinline__ void a2_exp_row_pipelined(uint32_t (&v0)[32], uint32_
   consume(v1, 1);
   __syncwarp();
   issue(v3);
+  handover(v3[31]);  // every exponential of the row has been issued: the MUFU pipe can go to the other warpgroup (ping-pong;
+                     // handing over one chunk earlier measured 750 / 836 instead of 756 / 850 TFLOP/s)
   consume(v2, 2);
   __syncwarp();
   consume(v3, 3);
@@ -695,6 +699,12 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       const uint64_t sl2_2 = pack2(sl2, sl2);
       const float inv_sl2 = 1.0f / sl2;
+      // Ping-pong (two-tile form only): left free-running, the two softmax warps of a scheduler settle IN PHASE -- both read
+      // S and reduce maxima together, then share the MUFU pipe at half rate each: period n + 2e per tile pair (n ~ 1150 clk
+      // outside the exponential phase, e = 1024 clk of MUFU work; ncu: MUFU 71 % = 2e / (n + 2e)).  Two named barriers force
+      // the exponential phases of the two warpgroups to ALTERNATE, so one owns the pipe at full rate while the other does its
+      // tensor-memory reads, maximum and stores: period n + e.
+      const bool pingpong = NQT == 2 && n_qt == 2 && p.pingpong != 0;
 
       KvCursor cur;
       cur.skip(p, kv_tile0);
@@ -766,13 +776,23 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         // exponentials -> bf16 pairs (two per 32-bit P column), stored to tensor memory chunk by chunk (16 columns = 32
         // scores at a time, so the packed probabilities never occupy more than 16 registers).  P.V of the previous tile
         // still reads the single P buffer: it was issued a whole tile ago, so this wait is normally already satisfied
+        // P.V of tile j-1 still reads the single P buffer.  Measured placements of this wait (TFLOP/s, 8- / 24-view global
+        // shape, two-tile ping-pong form): here, before the exponential phase 756 / 850; at the first P store inside the phase
+        // 665 / 751; after the phase with all four stores deferred 592 / 668.
         if (!waited && j > 0) mbar_wait(&p_empty[t], (j - 1) & 1);
         tc_fence_after();
         uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
         const uint64_t nm2 = pack2(-mref, -mref);
         if (NPOLY == 0 || kv_valid < ATT_BN) {  // masked columns are -inf: MUFU only (ex2(-inf) = 0 exactly)
-          a2_exp_row_pipelined(v0, v1, v2, v3, sl2, mref, acc,
-                               [&](int chunk, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(tmem_p + 16 * chunk, pk); });
+          float mref_turn = mref;
+          // wait for the turn; the barrier carries the reference maximum so that no exponential can be scheduled above it
+          if (pingpong && (t == 1 || j > 0)) asm volatile("bar.sync %1, 256;" : "+f"(mref_turn) : "r"(1 + t) : "memory");
+          a2_exp_row_pipelined(v0, v1, v2, v3, sl2, mref_turn, acc,
+                               [&](int chunk, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(tmem_p + 16 * chunk, pk); },
+                               [&](uint32_t& last) {
+                                 if (pingpong && (t == 0 || j + 1 < n_kv_tiles))
+                                   asm volatile("bar.arrive %1, 256;" : "+r"(last) : "r"(2 - t) : "memory");
+                               });
         } else {
           const float kk = 12582912.0f - mref;           // 1.5 * 2^23 - mref, exact for |mref| < 2^22
           const uint64_t k2 = pack2(kk, kk);
@@ -1274,6 +1294,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
   p.num_seqs = num_seqs;
   p.flags = flags;
   p.kv_split = 1;
+  p.pingpong = 0;
   p.split_from = 0;
   p.split_stride_o = 0;
   p.split_stride_m = 0;
@@ -1371,7 +1392,15 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     // attention) 586 / 572 and 552 / 535 at 8 views, 658 / 622 and 634 / 604 at 24 views -> v3; one long sequence (global
     // attention) 740 / 766 at 8 views, 786 / 799 at 24 views -> v2<1>.  Every exponential on the MUFU (NPOLY = 0): moving a
     // share of them to the FMA pipe was slower in both kernels (v2<1>: 766 -> 646 at 7 of 16; v3: 740 -> 720).
-    const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : (kv_len <= 4096 ? 3 : 1);
+    static const int pingpong_env = [] {
+      const char* e = getenv("MA_ATTN_PINGPONG");
+      return e ? atoi(e) : -1;
+    }();
+    // One long sequence (global attention, > 4096 keys): two query tiles per CTA with ping-pong -- K / V shared by 256 query
+    // rows, MUFU 82 % busy instead of 71 %: 881 vs 795 TFLOP/s at 16 views, 850 vs 799 at 24; at 8 views 756 vs 766 as a plain
+    // launch (516 CTAs = 3.5 waves of 148), 860 with the last partial wave split over the key range (Engine._pick_tail_split).
+    const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : (kv_len <= 4096 ? 3 : 2);
+    p.pingpong = (nqt == 2 && pingpong_env != 0) ? 1 : 0;
     const int want_poly = poly_env >= 0 ? poly_env : A2_DEFAULT_POLY;
     const Variant* pick = nullptr;
     for (const Variant& v : variants)

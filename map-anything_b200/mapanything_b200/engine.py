@@ -280,9 +280,11 @@ class Engine:
 
         self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "2")))
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-        # tail-wave splitting of long attention: implemented and tested, but A/B runs on B200 (8 views, same box, same
-        # call) show no gain (26.8 / 27.0 ms without vs 27.1 / 27.3 ms with it) -> off unless MA_ATTN_KV_SPLIT=1
-        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "0") == "1"
+        # tail-wave splitting of long attention (the slots of the last, partially filled wave of SMs are cut over the key range,
+        # ma_attention_merge joins them): neutral with the free-running kernels of round 1, but with the ping-pong two-tile
+        # kernel the 8-view global attention drops from 6.34 to 5.67 + 0.15 (merge) ms per step (same-box A/B, 320 -> 332
+        # views/s); MA_ATTN_KV_SPLIT=0 turns it off
+        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "1") != "0"
         # views per DPT pass (bounds the activation scratch: ~0.6 GB per view at 518 px).  8 instead of 4: same-box A/B at 8
         # views 311.1 vs 301.6 views/s (fewer, larger launches); MA_DPT_CHUNK overrides for A/B runs
         self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "8")))
