@@ -242,3 +242,28 @@ def test_attention_sharded_protocol_100_views():
     err = (out[pick].double() - ref).abs().max().item()
     print(f"\n[sharded attention protocol, 136901 keys in 8 slots] max abs err {err:.3e}")
     assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("views", [3, 5, 8, 9, 12])
+def test_engine_global_attention_tail_split_matches_sdpa(views):
+    """Engine._attention_one_sequence (what every global block of a single-GPU scene calls): the two-tile ping-pong kernel with
+    the last partial wave of CTAs split over the key range (2-4 parts, Engine._pick_tail_split) + ma_attention_merge, against
+    F.scaled_dot_product_attention.  The view counts cover 2 parts (3, 8), 4 parts (5), 3 parts (12) and no split (9) on 148 SMs."""
+    import torch.nn.functional as F
+
+    from mapanything_b200 import MapAnything, tiny_config
+
+    eng = MapAnything(**tiny_config()).to("cuda").eval().engine()
+    H, D, L = 12, 768, 1369 * views + 1
+    pick = eng._pick_tail_split(L, L, H)
+    g = torch.Generator(device="cuda").manual_seed(100 + views)
+    qkv = (torch.randn(L, 3 * D, device="cuda", generator=g) * 1.5).bfloat16()
+    out = torch.full((L, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+    eng._attention_one_sequence(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, H, L, L)
+    q, k, v = (qkv[:, i * D:(i + 1) * D].view(L, H, 64).transpose(0, 1)[None] for i in range(3))
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float())[0].transpose(0, 1).reshape(L, D)
+    got = out.float()
+    assert torch.isfinite(got).all(), f"non-finite output (split {pick})"
+    err = (got - ref).abs().max().item()
+    print(f"\n[global attention, {views} views, {L} tokens] tail split {pick}: max abs err {err:.2e}")
+    assert err < 3e-2, (pick, err)
