@@ -705,7 +705,6 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       // the exponential phases of the two warpgroups to ALTERNATE, so one owns the pipe at full rate while the other does its
       // tensor-memory reads, maximum and stores: period n + e.
       const bool pingpong = NQT == 2 && n_qt == 2 && p.pingpong != 0;
-      const bool pair_turns = p.pingpong == 2;  // one barrier pair per scheduler (the two warps of a TMEM lane quarter) instead of per warpgroup
 
       KvCursor cur;
       cur.skip(p, kv_tile0);
@@ -787,17 +786,12 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         if (NPOLY == 0 || kv_valid < ATT_BN) {  // masked columns are -inf: MUFU only (ex2(-inf) = 0 exactly)
           float mref_turn = mref;
           // wait for the turn; the barrier carries the reference maximum so that no exponential can be scheduled above it
-          if (pingpong && (t == 1 || j > 0)) {
-            if (pair_turns) asm volatile("bar.sync %1, 64;" : "+f"(mref_turn) : "r"(1 + 2 * quarter + t) : "memory");
-            else asm volatile("bar.sync %1, 256;" : "+f"(mref_turn) : "r"(1 + t) : "memory");
-          }
+          if (pingpong && (t == 1 || j > 0)) asm volatile("bar.sync %1, 256;" : "+f"(mref_turn) : "r"(1 + t) : "memory");
           a2_exp_row_pipelined(v0, v1, v2, v3, sl2, mref_turn, acc,
                                [&](int chunk, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(tmem_p + 16 * chunk, pk); },
                                [&](uint32_t& last) {
-                                 if (pingpong && (t == 0 || j + 1 < n_kv_tiles)) {
-                                   if (pair_turns) asm volatile("bar.arrive %1, 64;" : "+r"(last) : "r"(2 + 2 * quarter - t) : "memory");
-                                   else asm volatile("bar.arrive %1, 256;" : "+r"(last) : "r"(2 - t) : "memory");
-                                 }
+                                 if (pingpong && (t == 0 || j + 1 < n_kv_tiles))
+                                   asm volatile("bar.arrive %1, 256;" : "+r"(last) : "r"(2 - t) : "memory");
                                });
         } else {
           const float kk = 12582912.0f - mref;           // 1.5 * 2^23 - mref, exact for |mref| < 2^22
@@ -1406,10 +1400,7 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     // rows, MUFU 82 % busy instead of 71 %: 881 vs 795 TFLOP/s at 16 views, 850 vs 799 at 24; at 8 views 756 vs 766 as a plain
     // launch (516 CTAs = 3.5 waves of 148), 860 with the last partial wave split over the key range (Engine._pick_tail_split).
     const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : (kv_len <= 4096 ? 3 : 2);
-    // MA_ATTN_PINGPONG: 0 off, 1 one pair of 256-thread barriers for the two warpgroups, 2 (default) one pair of 64-thread
-    // barriers per scheduler -- the two warps that share a MUFU alternate without waiting for the other three schedulers
-    // (same box, 8 / 16 / 24 views: 662 / 797 / 785 against 650 / 791 / 784 TFLOP/s)
-    p.pingpong = (nqt == 2 && pingpong_env != 0) ? (pingpong_env == 1 ? 1 : 2) : 0;
+    p.pingpong = (nqt == 2 && pingpong_env != 0) ? 1 : 0;
     const int want_poly = poly_env >= 0 ? poly_env : A2_DEFAULT_POLY;
     const Variant* pick = nullptr;
     for (const Variant& v : variants)
