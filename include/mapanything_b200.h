@@ -218,6 +218,13 @@ int ma_split_bf16x3(const float* in, int64_t ld_in, void* out, int rows, int C, 
 int ma_head_linear_small(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, float* out, int64_t ldo,
                          int64_t rows, int N, int K, void* stream);
 
+/* fp32 Linear on a handful of rows: out[r][0:N] = act(b + W[N][K] . x[r]), 1 <= rows <= 16, K % 4 == 0, rows * K * 4 <= 48 KB,
+ * plain fp32 arithmetic (act: MA_ACT_NONE / MA_ACT_RELU / MA_ACT_GELU, exact erf).  The pooled MLPs of the pose head and the
+ * scale head (uniception PoseHead.more_mlps / fc_t / fc_rot and MLPHead on the scale token, invoked at reference
+ * model.py:1449-1469 with autocast disabled): 8 x 768 and 1 x 768 inputs. */
+int ma_linear_rows_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int act, float* out,
+                       int64_t ldo, int rows, int N, int K, void* stream);
+
 /* fp32 variant of ma_token_mean. */
 int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* stream);
 

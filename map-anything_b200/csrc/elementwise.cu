@@ -485,19 +485,80 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ in, int64_t ld_in,
 }
 
 // fp32 token mean: [n][T][C] -> [n][C]
-__global__ void token_mean_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C) {
-  __shared__ float red[4][64];
+// block = 64 channels x 16 row lanes, four independent loads in flight per thread (the first form -- 4 row lanes, one load in
+// flight -- took 58 us for 8 x 1369 x 768: 96 blocks cannot hide the latency of 342 dependent steps each)
+__global__ void __launch_bounds__(1024) token_mean_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int C) {
+  __shared__ float red[16][64];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);
-  const int rl = threadIdx.x >> 6;
+  const int rl = threadIdx.x >> 6;  // 0..15
   const float* base = in + (size_t)blockIdx.y * T * C;
-  float s = 0.f;
-  if (c < C)
-    for (int t = rl; t < T; t += 4) s += base[(size_t)t * C + c];
-  red[rl][threadIdx.x & 63] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < C) {
+    int t = rl;
+    for (; t + 48 < T; t += 64) {
+      s0 += base[(size_t)t * C + c];
+      s1 += base[(size_t)(t + 16) * C + c];
+      s2 += base[(size_t)(t + 32) * C + c];
+      s3 += base[(size_t)(t + 48) * C + c];
+    }
+    for (; t < T; t += 16) s0 += base[(size_t)t * C + c];
+  }
+  red[rl][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (rl == 0 && c < C) {
-    const float tot = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tot += red[i][threadIdx.x];
     out[(size_t)blockIdx.y * C + c] = tot / T;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// fp32 Linear on a handful of rows: out[r][n] = act(b[n] + sum_k x[r][k] * w[n][k]), rows <= 16 (the pooled MLPs of the pose
+// head and the scale head: 8 x 768 or 1 x 768 inputs).  A tensor-core tile would carry 8 useful rows of 128 and, in the
+// split-bf16 form those layers otherwise use, a single CTA walks K' = 3K alone (23 - 37 us per launch).  Here x sits in shared
+// memory, one warp owns an output column: lanes stride over k with float4 loads of the weight row, 16 accumulators, one
+// shuffle reduction per row.  Plain fp32 FMAs.
+// ----------------------------------------------------------------------------------------------
+constexpr int LIN_ROWS_MAX = 16;
+__global__ void __launch_bounds__(256) linear_rows_f32_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                              int64_t ldw, const float* __restrict__ bias, float* __restrict__ out,
+                                                              int64_t ldo, int rows, int N, int K, int act) {
+  extern __shared__ float sx[];  // [rows][K]
+  for (int i = threadIdx.x; i < rows * (K >> 2); i += blockDim.x) {
+    const int r = i / (K >> 2), q = i - r * (K >> 2);
+    reinterpret_cast<float4*>(sx)[i] = *reinterpret_cast<const float4*>(x + r * ldx + 4 * q);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[LIN_ROWS_MAX];
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS_MAX; ++r) acc[r] = 0.f;
+  const float4* wr = reinterpret_cast<const float4*>(w + (int64_t)n * ldw);
+  for (int q = lane; q < (K >> 2); q += 32) {
+    const float4 wv = __ldg(wr + q);
+#pragma unroll
+    for (int r = 0; r < LIN_ROWS_MAX; ++r) {
+      if (r < rows) {
+        const float4 xv = reinterpret_cast<const float4*>(sx + r * K)[q];
+        acc[r] = fmaf(xv.x, wv.x, acc[r]);
+        acc[r] = fmaf(xv.y, wv.y, acc[r]);
+        acc[r] = fmaf(xv.z, wv.z, acc[r]);
+        acc[r] = fmaf(xv.w, wv.w, acc[r]);
+      }
+    }
+  }
+  const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+  for (int r = 0; r < LIN_ROWS_MAX; ++r) {
+    if (r < rows) {
+      float v = warp_sum(acc[r]) + b;
+      if (act == MA_ACT_RELU) v = fmaxf(v, 0.f);
+      else if (act == MA_ACT_GELU) v = gelu_erf(v);
+      if (lane == 0) out[r * ldo + n] = v;
+    }
   }
 }
 
@@ -628,7 +689,21 @@ extern "C" int ma_split_bf16x3(const float* in, int64_t ld_in, void* out, int ro
 extern "C" int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* stream) {
   MA_REQUIRE(in && out && n > 0 && T > 0 && C > 0, "ma_token_mean_f32: bad arguments");
   dim3 grid((C + 63) / 64, n);
-  token_mean_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, T, C);
+  token_mean_f32_kernel<<<grid, 1024, 0, static_cast<cudaStream_t>(stream)>>>(in, out, T, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_linear_rows_f32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int act, float* out,
+                                  int64_t ldo, int rows, int N, int K, void* stream) {
+  MA_REQUIRE(x && w && out && rows >= 1 && rows <= LIN_ROWS_MAX && N >= 1 && K >= 4 && K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0 &&
+                 ldo >= N, "ma_linear_rows_f32: needs 1 <= rows <= %d, K %% 4 == 0, strides %% 4 == 0 (rows=%d N=%d K=%d)",
+             LIN_ROWS_MAX, rows, N, K);
+  MA_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "ma_linear_rows_f32: x / w not 16-byte aligned");
+  MA_REQUIRE(act == MA_ACT_NONE || act == MA_ACT_RELU || act == MA_ACT_GELU, "ma_linear_rows_f32: bad activation %d", act);
+  const size_t smem = (size_t)rows * K * sizeof(float);
+  MA_REQUIRE(smem <= 48 * 1024, "ma_linear_rows_f32: rows * K = %d floats do not fit 48 KB of shared memory", rows * K);
+  linear_rows_f32_kernel<<<(N + 7) / 8, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, ldx, w, ldw, bias, out, ldo, rows, N, K, act);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

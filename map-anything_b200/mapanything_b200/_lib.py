@@ -91,6 +91,7 @@ SIGNATURES = {
     "ma_head_linear_small": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _p]),
     "ma_split_bf16x3": (_i, [_p, _i64, _p, _i, _i, _p]),
     "ma_token_mean_f32": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ma_linear_rows_f32": (_i, [_p, _i64, _p, _i64, _p, _i, _p, _i64, _i, _i, _i, _p]),
     "ma_rays_from_intrinsics": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_normalize_rays": (_i, [_p, _p, _i64, _p]),
     "ma_depth_z_to_along_ray": (_i, [_p, _p, _p, _i64, _p]),

@@ -56,6 +56,7 @@ class Lin3:
         hi = w.to(torch.bfloat16)
         lo = (w - hi.float()).to(torch.bfloat16)
         self.w = torch.cat([hi, hi, lo], dim=2).reshape(n, 3 * k).contiguous()
+        self.w32 = w2d.contiguous() if group == k else None   # plain fp32 copy for the few-row kernel (ops.linear_rows_f32)
         self.b = _f32(b) if b is not None else None
         self.n, self.k = n, 3 * k
         ops.register_algorithmic_shape(self.w, *(algo_nk or (n, k)))   # the 3x of the split is not algorithmic work
@@ -492,6 +493,14 @@ class Engine:
                 main.wait_stream(streams[g])
         return feat
 
+    def _lin3(self, x32: torch.Tensor, lin: "Lin3", out: torch.Tensor, act: int = MA_ACT_NONE) -> torch.Tensor:
+        """fp32-accurate Linear: the few-row fp32 kernel for up to 16 rows (pooled pose / scale MLPs, per-view global
+        encoders), else the split-bf16 tensor-core GEMM."""
+        rows, k = x32.shape
+        if lin.w32 is not None and rows <= ops.LINEAR_ROWS_MAX and rows * k * 4 <= 48 * 1024 and k % 4 == 0:
+            return ops.linear_rows_f32(x32, lin.w32, lin.b, out, act)
+        return ops.gemm(ops.split3(x32), lin.w, out, bias=lin.b, act=act)
+
     def _side_streams(self, k: int):
         if len(getattr(self, "_streams", [])) < k:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(k)]
@@ -544,7 +553,7 @@ class Engine:
         g = x8
         for i, lin in enumerate(w.lins):
             o = self._empty(g.shape[0], lin.n, dtype=torch.float32)
-            ops.gemm(ops.split3(g), lin.w, o, bias=lin.b, act=MA_ACT_GELU if i + 1 < len(w.lins) else MA_ACT_NONE)
+            self._lin3(g, lin, o, MA_ACT_GELU if i + 1 < len(w.lins) else MA_ACT_NONE)
             g = o
         f = self._empty(g.shape[0], g.shape[1], dtype=torch.float32)
         ops.layernorm(g, f, w.nw, w.nb, eps=w.eps)
@@ -706,9 +715,9 @@ class Engine:
         g = pooled
         for lin in self.pose_mlp:
             gn = self._empty(n, lin.n, dtype=torch.float32)
-            ops.gemm(ops.split3(g), lin.w, gn, bias=lin.b, act=MA_ACT_RELU)
+            self._lin3(g, lin, gn, MA_ACT_RELU)
             g = gn
-        ops.gemm(ops.split3(g), self.pose_out.w, out, bias=self.pose_out.b)
+        self._lin3(g, self.pose_out, out)
         return out
 
     def _pose_blocks_split(self, x32: torch.Tensor, n: int, hp: int, wp: int) -> torch.Tensor:
@@ -780,8 +789,8 @@ class Engine:
         x = tok_feat32
         for lin in self.scale_mlp[:-1]:
             xn = self._empty(x.shape[0], lin.n, dtype=torch.float32)
-            ops.gemm(ops.split3(x), lin.w, xn, bias=lin.b, act=self.scale_act)
+            self._lin3(x, lin, xn, self.scale_act)
             x = xn
         out = self._empty(1, self.scale_mlp[-1].n, dtype=torch.float32)
-        ops.gemm(ops.split3(x), self.scale_mlp[-1].w, out, bias=self.scale_mlp[-1].b)
+        self._lin3(x, self.scale_mlp[-1], out)
         return out.reshape(-1)[:1].contiguous()

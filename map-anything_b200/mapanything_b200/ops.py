@@ -463,6 +463,25 @@ def token_mean_f32(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
+LINEAR_ROWS_MAX = 16
+
+
+def linear_rows_f32(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor, act: int = MA_ACT_NONE):
+    """out[r] = act(b + W x[r]) in plain fp32 for x of at most LINEAR_ROWS_MAX rows (ma_linear_rows_f32)."""
+    _req(x, torch.float32, "x")
+    _req(w, torch.float32, "w")
+    _req(out, torch.float32, "out")
+    rows, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or out.shape != (rows, N) or x.stride(1) != 1 or w.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError(f"linear_rows_f32: shape mismatch x {tuple(x.shape)} w {tuple(w.shape)} out {tuple(out.shape)}")
+    with launch("linear_rows"):
+        check(_lib.load().ma_linear_rows_f32(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0),
+                                             _ptr(_f32c(bias, N, "bias")) if bias is not None else None, act, out.data_ptr(),
+                                             out.stride(0), rows, N, K, _stream()), "ma_linear_rows_f32")
+    return out
+
+
 def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Tensor, n: int, H: int, W: int):
     """Fused adaptor + decode (ma_decode_dense). raw fp32 [n*H*W, ld>=6]; returns the dict of forward() tensors."""
     if raw.dtype != torch.float32 or raw.stride(-1) != 1:

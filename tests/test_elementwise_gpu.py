@@ -85,3 +85,36 @@ def test_bilinear_align_corners_matches_torch(n, Hin, Win, C, Ho, Wo, virt):
     ref = F.interpolate(x.float().permute(0, 3, 1, 2), size=(Hv, Wv), mode="bilinear", align_corners=True)
     ref = ref[:, :, :Ho, :Wo].permute(0, 2, 3, 1)
     assert (out.float() - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("rows,N,K,act", [(8, 768, 768, "relu"), (1, 768, 768, "gelu"), (8, 7, 768, None), (1, 1, 768, None),
+                                          (16, 128, 8, "gelu"), (3, 1024, 512, None), (12, 77, 1024, "relu")])
+def test_linear_rows_f32_matches_torch(rows, N, K, act):
+    """ma_linear_rows_f32 (the pooled MLPs of the pose / scale heads and the per-view global encoders): plain fp32 Linear on up
+    to 16 rows against torch (float64 accumulation as the yardstick)."""
+    import torch.nn.functional as F
+
+    from mapanything_b200 import ops
+    from mapanything_b200._lib import MA_ACT_GELU, MA_ACT_NONE, MA_ACT_RELU
+
+    g = torch.Generator(device="cuda").manual_seed(rows * 1000 + N + K)
+    x = torch.randn(rows, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((rows, N), float("nan"), device="cuda")
+    ops.linear_rows_f32(x, w, b, out, {"relu": MA_ACT_RELU, "gelu": MA_ACT_GELU, None: MA_ACT_NONE}[act])
+    ref = x.double() @ w.double().t() + b.double()
+    ref = F.relu(ref) if act == "relu" else F.gelu(ref) if act == "gelu" else ref
+    assert torch.isfinite(out).all()
+    assert (out.double() - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_token_mean_f32_matches_torch():
+    from mapanything_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for n, T, C in ((8, 1369, 768), (2, 25, 96), (1, 70, 64)):
+        x = torch.randn(n, T, C, device="cuda", generator=g) + 0.5
+        out = torch.full((n, C), float("nan"), device="cuda")
+        ops.token_mean_f32(x, out)
+        assert (out.double() - x.double().mean(1)).abs().max().item() < 1e-5
