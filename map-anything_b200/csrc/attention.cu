@@ -860,6 +860,346 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
 
 // ================================================================================================================
+// v5: persistent CTAs, two INDEPENDENT attention streams per CTA with ping-pong (many short sequences: encoder / frame
+// attention, 1370 keys = 11 steps per 128-row query tile).
+//   * a work item is one 128-row query tile of one (sequence, head); stream t of CTA c takes the items r * 2G + 2c + t
+//     (G = grid size = number of SMs), so 1408 items fill 296 streams in 4.76 -> 5 rounds (the one-tile-per-CTA kernels:
+//     3.17 -> 4 waves of 444 resident CTAs);
+//   * each stream has its own Q tile, its own 3-stage K / V ring, its own TMA producer warp, MMA issuer warp and softmax
+//     warpgroup, its own S / O / P tensor-memory columns -- two v2<1> pipelines inside one CTA.  What the CTA buys is the
+//     ping-pong of v2<2>: the two softmax warps of a scheduler alternate their exponential phases through a pair of named
+//     barriers instead of falling into step (MUFU 82 % instead of 63 - 71 % busy);
+//   * every barrier phase runs on across items (global step counters), the producer loads the next item's Q as soon as the
+//     last Q.K^T of the current one is issued, and the MMA issuer issues the next item's first Q.K^T right after the current
+//     item's last P.V: an item's epilogue (O out of tensor memory, normalise, store) and the next item's ramp run under the
+//     OTHER stream's exponential phase.
+//   * both streams execute the same number of ping-pong turns (equal steps per item; a stream without an item in the last
+//     round only passes the turn), so every bar.sync has its bar.arrive.
+// No key segments, carried state or kv split here (ma_attention_fwd routes those to v2).
+// ================================================================================================================
+constexpr int A5_THREADS = 12 * 32;  // warp 0 / 11: TMA producer of stream 0 / 1; warp 1 / 10: MMA issuer; warps 2-5 / 6-9: softmax
+constexpr int A5_KV_STAGES = 3;
+constexpr int A5_SMEM_BYTES = (2 + 2 * 2 * A5_KV_STAGES) * ATT_TILE_BYTES + 1024;
+constexpr int A5_BARS_PER_STREAM = 6 + 4 * A5_KV_STAGES;
+
+__global__ void __launch_bounds__(A5_THREADS, 1)
+attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = A2Cfg<2>;  // tensor-memory column map of the two-tile kernel
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                              // [2] tiles
+  uint8_t* sKV = sQ + 2 * ATT_TILE_BYTES;                          // per stream: K[stages], V[stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + 2 * 2 * A5_KV_STAGES * ATT_TILE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * A5_BARS_PER_STREAM);
+
+  const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
+  const int lane = lane_id();
+  const int n_qt = (p.q_len + ATT_BM - 1) / ATT_BM;
+  const int n_items = n_qt * p.num_heads * p.num_seqs;
+  const int S = p.n_kv_tiles;                                      // steps per item (the same for every item)
+  const int G = gridDim.x;
+  const int c = blockIdx.x;
+  // rounds this CTA takes part in = rounds in which its stream 0 has an item
+  const int n_rounds = n_items > 2 * c ? (n_items - 2 * c + 2 * G - 1) / (2 * G) : 0;
+  const int g_total = n_rounds * S;                                // ping-pong turns per stream
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("[ma] attention v5: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  if (warp == 1 && lane == 0) {
+    for (int t = 0; t < 2; ++t) {
+      uint64_t* b = bars + t * A5_BARS_PER_STREAM;
+      mbar_init(b + 0, 1);   // q_full
+      mbar_init(b + 1, 1);   // q_empty (tcgen05.commit after the item's last Q.K^T)
+      mbar_init(b + 2, 1);   // s_full
+      mbar_init(b + 3, 4);   // s_empty
+      mbar_init(b + 4, 4);   // p_full
+      mbar_init(b + 5, 1);   // p_empty (= P.V of the step has completed)
+      for (int i = 0; i < 4 * A5_KV_STAGES; ++i) mbar_init(b + 6 + i, 1);  // k_full, k_empty, v_full, v_empty [stages]
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // no global memory access before this point
+
+  // role -> stream
+  const int t = (warp == 0 || warp == 1 || (warp >= 2 && warp <= 5)) ? 0 : 1;
+  uint64_t* b = bars + t * A5_BARS_PER_STREAM;
+  uint64_t* q_full = b + 0;
+  uint64_t* q_empty = b + 1;
+  uint64_t* s_full = b + 2;
+  uint64_t* s_empty = b + 3;
+  uint64_t* p_full = b + 4;
+  uint64_t* p_empty = b + 5;
+  uint64_t* k_full = b + 6;
+  uint64_t* k_empty = k_full + A5_KV_STAGES;
+  uint64_t* v_full = k_empty + A5_KV_STAGES;
+  uint64_t* v_empty = v_full + A5_KV_STAGES;
+  uint8_t* sQt = sQ + t * ATT_TILE_BYTES;
+  uint8_t* sK = sKV + t * 2 * A5_KV_STAGES * ATT_TILE_BYTES;
+  uint8_t* sV = sK + A5_KV_STAGES * ATT_TILE_BYTES;
+  auto item_of = [&](int r) { return r * 2 * G + 2 * c + t; };
+  auto decode = [&](int item, int& qb, int& head, int& seq) {
+    const int hs = item / n_qt;
+    qb = item - hs * n_qt;
+    head = hs % p.num_heads;
+    seq = hs / p.num_heads;
+  };
+
+  if (warp == 0 || warp == 11) {
+    // ---- TMA producer of stream t ------------------------------------------------------------------------------
+    if (lane == 0) {
+      int gs = 0;  // global step counter = K / V ring position
+      for (int r = 0; r < n_rounds; ++r) {
+        const int item = item_of(r);
+        if (item >= n_items) break;
+        int qb, head, seq;
+        decode(item, qb, head, seq);
+        const int q_row = static_cast<int>(seq * p.q_seq_stride) + qb * ATT_BM;
+        const int kv_row0 = static_cast<int>(seq * p.kv_seq_stride);
+        if (r > 0) mbar_wait(q_empty, (r - 1) & 1);  // the previous item's last Q.K^T has read the Q tile
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+        tma_load_2d(sQt, &tmap_q, q_full, p.q_col0 + head * ATT_D, q_row);
+        for (int j = 0; j < S; ++j, ++gs) {
+          const int st = gs % A5_KV_STAGES;
+          const uint32_t ph = (gs / A5_KV_STAGES) & 1;
+          const int row = kv_row0 + j * ATT_BN;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+          tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_k, &k_full[st], p.k_col0 + head * ATT_D, row);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], p.v_col0 + head * ATT_D, row);
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 10) {
+    // ---- MMA issuer of stream t -------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(sQt);
+      const uint32_t tmem_s = tmem_base + t * ATT_BN;
+      const uint32_t tmem_o = tmem_base + Cfg::O_COL0 + t * ATT_D;
+      const uint32_t p_tmem = tmem_base + Cfg::P_COL0 + t * 64;
+      auto issue_qk = [&](int gs, bool last_of_item) {
+        const int st = gs % A5_KV_STAGES;
+        const uint32_t ph = (gs / A5_KV_STAGES) & 1;
+        mbar_wait(&k_full[st], ph);
+        mbar_wait(s_empty, (gs & 1) ^ 1);  // the softmax warps hold S of the previous step in registers
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          umma_bf16_ss(tmem_s, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                       idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+        umma_commit(&k_empty[st]);
+        if (last_of_item) umma_commit(q_empty);  // the Q tile may be overwritten once these MMAs have completed
+      };
+      int gs0 = 0;
+      bool first_qk_issued = false;
+      for (int r = 0; r < n_rounds; ++r) {
+        if (item_of(r) >= n_items) break;
+        if (!first_qk_issued) {
+          mbar_wait(q_full, r & 1);
+          issue_qk(gs0, S == 1);
+        }
+        for (int j = 0; j < S; ++j) {
+          const int gs = gs0 + j;
+          if (j + 1 < S) issue_qk(gs + 1, j + 2 == S);
+          const int st = gs % A5_KV_STAGES;
+          const uint32_t ph = (gs / A5_KV_STAGES) & 1;
+          mbar_wait(&v_full[st], ph);
+          mbar_wait(p_full, gs & 1);
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k)
+            umma_bf16_ts(tmem_o, p_tmem + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 1024, 1024), idesc_pv,
+                         (k != 0 || j > 0) ? 1u : 0u);
+          umma_commit(p_empty);
+          umma_commit(&v_empty[st]);
+        }
+        gs0 += S;
+        // the next item's first Q.K^T, so that its scores are ready when the softmax warps leave this item's epilogue
+        first_qk_issued = false;
+        if (r + 1 < n_rounds && item_of(r + 1) < n_items) {
+          mbar_wait(q_full, (r + 1) & 1);
+          issue_qk(gs0, S == 1);
+          first_qk_issued = true;
+        }
+      }
+    }
+  } else {
+    // ---- softmax warps of stream t: TMEM lane quarter = warp & 3; thread = query row ----------------------------
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t tmem_s = tmem_base + lane_base + t * ATT_BN;
+    const uint32_t tmem_o = tmem_base + lane_base + Cfg::O_COL0 + t * ATT_D;
+    const uint32_t tmem_p = tmem_base + lane_base + Cfg::P_COL0 + t * 64;
+    const float sl2 = p.scale_log2;
+    const int kv_len = p.seg_len[0];
+    int gs0 = 0;
+    for (int r = 0; r < n_rounds; ++r) {
+      const int item = item_of(r);
+      if (item >= n_items) {
+        // no item for this stream in the CTA's last round: pass the turns so that the other stream's barriers pair up
+        for (int j = 0; j < S; ++j) {
+          const int gs = gs0 + j;
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");          // t == 1 here: always waits
+          if (gs + 1 < g_total) asm volatile("bar.arrive %0, 256;" ::"r"(2 - t) : "memory");
+        }
+        gs0 += S;
+        continue;
+      }
+      int qb, head, seq;
+      decode(item, qb, head, seq);
+      const int q_idx = qb * ATT_BM + row;
+      const bool q_ok = q_idx < p.q_len;
+      const int64_t q_grow = static_cast<int64_t>(seq) * p.q_seq_stride + q_idx;
+      float mref = 0.f, l_run = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const int gs = gs0 + j;
+        const int kv_valid = kv_len - j * ATT_BN;
+        mbar_wait(s_full, gs & 1);
+        tc_fence_after();
+        uint32_t v0[32], v1[32], v2[32], v3[32];  // the 128 scores of this thread's row
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto chunk_max = [&](uint32_t (&v)[32], int c0, float& m) {
+          if (kv_valid < c0 + 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i >= kv_valid) v[i] = __float_as_uint(-INFINITY);
+          }
+          float a = -INFINITY, bb = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            a = fmaxf(a, __uint_as_float(v[i]));
+            bb = fmaxf(bb, __uint_as_float(v[16 + i]));
+          }
+          m = fmaxf(a, bb);
+        };
+        tmem_ld_32x32b_x32(tmem_s, v0);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(tmem_s + 32, v1);
+        chunk_max(v0, 0, mx4[0]);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(tmem_s + 64, v2);
+        chunk_max(v1, 32, mx4[1]);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(tmem_s + 96, v3);
+        chunk_max(v2, 64, mx4[2]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the tensor core may overwrite it
+        chunk_max(v3, 96, mx4[3]);
+        const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+
+        // lazy rescale: adopt the new maximum only when it grew by more than 2^8
+        const float mt2 = m_tile * sl2;
+        float m_new = mref;
+        bool need = false;
+        if (j == 0) m_new = rintf(mt2);
+        else if (mt2 - mref > A2_RESCALE_LOG2) { need = true; m_new = rintf(mt2); }
+        bool waited = false;
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(p_empty, (gs - 1) & 1);  // j > 0 here: P.V of the previous step has completed
+          waited = true;
+          tc_fence_after();
+          const float alpha = need ? fast_exp2(mref - m_new) : 1.f;  // an exact power of two
+#pragma unroll 1
+          for (int cc = 0; cc < ATT_D; cc += 8) {  // rare path
+            uint32_t o[8];
+            tmem_ld_32x32b_x8(tmem_o + cc, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x8(tmem_o + cc, o);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          l_run *= alpha;
+        }
+        mref = m_new;
+
+        // P.V of the previous step (of this item, or the last one of the previous item -- whose completion the epilogue has
+        // already waited for) still reads the single P buffer
+        if (!waited && j > 0) mbar_wait(p_empty, (gs - 1) & 1);
+        tc_fence_after();
+        uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+        float mref_turn = mref;
+        // wait for the turn; the barrier carries the reference maximum so that no exponential can be scheduled above it
+        if (t == 1 || gs > 0) asm volatile("bar.sync %1, 256;" : "+f"(mref_turn) : "r"(1 + t) : "memory");
+        a2_exp_row_pipelined(v0, v1, v2, v3, sl2, mref_turn, acc,
+                             [&](int chunk, const uint32_t (&pk)[16]) { tmem_st_32x32b_x16(tmem_p + 16 * chunk, pk); },
+                             [&](uint32_t& last) {
+                               if (t == 0 || gs + 1 < g_total)
+                                 asm volatile("bar.arrive %1, 256;" : "+r"(last) : "r"(2 - t) : "memory");
+                             });
+        {
+          float a0, a1, a2, a3;
+          unpack2(fadd2(acc[0], acc[1]), a0, a1);
+          unpack2(fadd2(acc[2], acc[3]), a2, a3);
+          l_run += (a0 + a1) + (a2 + a3);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      gs0 += S;
+
+      // ---- finish the item: normalise, store (runs under the other stream's exponential phase) ----
+      mbar_wait(p_empty, (gs0 - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      uint32_t o[32];
+#pragma unroll 1
+      for (int cc = 0; cc < ATT_D; cc += 32) {
+        tmem_ld_32x32b_x32(tmem_o + cc, o);
+        tmem_ld_wait();
+        if (q_ok) {
+          __nv_bfloat16* optr = p.out + q_grow * p.ldo + p.o_col0 + head * ATT_D + cc;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            reinterpret_cast<uint4*>(optr)[q] =
+                make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * inv_l, __uint_as_float(o[8 * q + 1]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 2]) * inv_l, __uint_as_float(o[8 * q + 3]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 4]) * inv_l, __uint_as_float(o[8 * q + 5]) * inv_l),
+                           pack_bf16x2(__uint_as_float(o[8 * q + 6]) * inv_l, __uint_as_float(o[8 * q + 7]) * inv_l));
+        }
+      }
+      tc_fence_before();   // the tensor-memory reads of O are ordered before the p_full arrive that lets the next P.V overwrite it
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// ================================================================================================================
 // v3: three CTAs per SM.
 //   * one 128-row query tile per CTA as in v2<1>, but key / value steps of 64 rows: a softmax thread holds 64 scores
 //     (112 registers instead of 168) and a CTA needs 64 (S) + 64 (O) + 32 (P) = 160 tensor-memory columns, taken as TWO
@@ -1399,6 +1739,28 @@ extern "C" int ma_attention_fwd_ex(const void* q, int64_t ldq, int64_t q_rows, i
     // One long sequence (global attention, > 4096 keys): two query tiles per CTA with ping-pong -- K / V shared by 256 query
     // rows, MUFU 82 % busy instead of 71 %: 881 vs 795 TFLOP/s at 16 views, 850 vs 799 at 24; at 8 views 756 vs 766 as a plain
     // launch (516 CTAs = 3.5 waves of 148), 860 with the last partial wave split over the key range (Engine._pick_tail_split).
+    // v5 (persistent, two independent streams per CTA with ping-pong): many short sequences, plain self / cross attention
+    // (MA_ATTN_V5=0 turns it off) when the (query tile x head x sequence) items fill the 2 x SMs streams for at least three
+    // rounds.  Same-box A/B against v3 (TFLOP/s): 8 x 16 x 1370 (encoder, 1408 items) 637 vs 572, 8 x 12 x 1369 (frame, 1056
+    // items) 592 vs 539, 24 x 16 x 1370 698 vs 655; 3 x 12 x 1369 (396 items, 1.3 rounds) 411 vs 468 -> v3 stays for few items.
+    static const int v5_env = [] {
+      const char* e = getenv("MA_ATTN_V5");
+      return e ? atoi(e) : 1;
+    }();
+    const int n_items5 = ((q_len + ATT_BM - 1) / ATT_BM) * num_heads * num_seqs;
+    if (v5_env != 0 && nqt_env == 0 && kv_len <= 4096 && p.n_segs == 1 && p.seg_row0[0] == 0 && p.kv_split == 1 &&
+        !(flags & (MA_ATTN_STATE_IN | MA_ATTN_STATE_OUT)) && n_items5 >= 6 * device_sm_count()) {
+      static bool configured5[MA_MAX_DEVICES] = {};
+      if (!configured5[dev]) {
+        MA_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM_BYTES));
+        configured5[dev] = true;
+      }
+      const int grid5 = device_sm_count() < (n_items5 + 1) / 2 ? device_sm_count() : (n_items5 + 1) / 2;
+      MA_CHECK_CUDA(launch_kernel(attention_fwd_v5_kernel, dim3(grid5), dim3(A5_THREADS), A5_SMEM_BYTES,
+                                  static_cast<cudaStream_t>(stream), pdl_enabled(), tq, tk, tv, p));
+      MA_CHECK_CUDA(cudaGetLastError());
+      return MA_OK;
+    }
     const int nqt = p.kv_split > 1 ? 2 : (nqt_env >= 1 && nqt_env <= 3) ? nqt_env : (kv_len <= 4096 ? 3 : 2);
     p.pingpong = (nqt == 2 && pingpong_env != 0) ? 1 : 0;
     const int want_poly = poly_env >= 0 ? poly_env : A2_DEFAULT_POLY;

@@ -279,7 +279,10 @@ class Engine:
         self.scale_mlp = [Lin3(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
         import os
 
-        self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "2")))
+        # view groups of the encoder on separate CUDA streams: +1 % before programmatic dependent launch existed, equal with
+        # it, and now slower than one stream (same-box A/B at 8 views: 327-328 views/s with two, 332 with one, 335 with one
+        # and the persistent two-stream attention kernel, which wants all views in one launch)
+        self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "1")))
         self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
         # tail-wave splitting of long attention (the slots of the last, partially filled wave of SMs are cut over the key range,
         # ma_attention_merge joins them): neutral with the free-running kernels of round 1, but with the ping-pong two-tile
