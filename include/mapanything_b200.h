@@ -200,6 +200,12 @@ int ma_im2col3x3(const void* in, void* out, int n, int H, int W, int C, int stri
  * NHWC out[(i, y*s+ky, x*s+kx)][c]  (DPT act_postprocess). bf16. */
 int ma_pixel_shuffle(const void* in, void* out, int n, int h, int w, int C, int s, void* stream);
 
+/* The same permutation in fp32 with row strides: the `linear` prediction head (reference model.py:339-343, a 1x1 conv
+ * to output_dim * patch^2 channels + F.pixel_shuffle) as GEMM (weight rows reordered to [(ky,kx), c]) + this scatter
+ * into the per-pixel rows [(i, y*s+ky, x*s+kx)][0:C] (row stride ld_out) that ma_decode_scene reads. */
+int ma_pixel_shuffle_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, int n, int h, int w, int C, int s,
+                         void* stream);
+
 /* F.interpolate(mode="bilinear", align_corners=True) over NHWC bf16.  (Hv,Wv) is the full output size that
  * defines the scale; only the top-left (Ho,Wo) window is written (refinenet4 crop 38 -> 37). */
 int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win, int C, int Hv, int Wv, int Ho, int Wo,
@@ -236,6 +242,37 @@ int ma_token_mean_f32(const float* in, float* out, int n, int T, int C, void* st
 int ma_decode_dense(const float* raw, int ld_raw, const float* pose_raw, const float* scale_raw, int n, int HW,
                     float* pts3d, float* pts3d_cam, float* rays, float* depth, float* conf, float* logits, uint8_t* mask,
                     float* cam_trans, float* cam_quats, float* scale_out, void* stream);
+
+/* The same decode for every scene representation the reference model can be configured with (model.py:407-587 adaptor
+ * table, :1618-1907 decode branches).  Head-output channel order: [representation | confidence logit | mask logit].
+ *   MA_REP_POINTMAP                    xyz                       -> pts3d
+ *   MA_REP_RAYMAP_DEPTH                origin xyz, ray xyz, depth -> pts3d = o + r d, ray_origins, rays, depth
+ *   MA_REP_RAYDIRS_DEPTH_POSE          ray xyz, depth   (+ pose)  -> what ma_decode_dense writes (the released model)
+ *   MA_REP_CAMPOINTMAP_POSE            xyz camera frame (+ pose)  -> depth = |p|, rays = p / depth, pts3d = R (rays depth) + t
+ *   MA_REP_POINTMAP_RAYDIRS_DEPTH_POSE xyz, ray xyz, depth (+ pose) -> pts3d predicted, or factored when use_factored != 0
+ * point_mode (the three point channels): MA_PTS_LINEAR, MA_PTS_EXP (unit direction x expm1(norm)), MA_PTS_Z_EXP
+ * ((x z, y z, z), z = exp(raw z)).  Rays are normalised to the unit sphere, depth = exp, confidence = conf_vmin + exp,
+ * mask = sigmoid(logit) > 0.5.  Output pointers the representation does not produce (and conf / logits / mask without
+ * has_conf / has_mask, pose_raw / cam_trans / cam_quats without a pose) must be NULL.  Metric scale as in ma_decode_dense. */
+#define MA_REP_POINTMAP 0
+#define MA_REP_RAYMAP_DEPTH 1
+#define MA_REP_RAYDIRS_DEPTH_POSE 2
+#define MA_REP_CAMPOINTMAP_POSE 3
+#define MA_REP_POINTMAP_RAYDIRS_DEPTH_POSE 4
+#define MA_PTS_LINEAR 0
+#define MA_PTS_EXP 1
+#define MA_PTS_Z_EXP 2
+typedef struct ma_decode_spec {
+  int rep;          /* MA_REP_* */
+  int has_conf;     /* a confidence channel follows the representation */
+  int has_mask;     /* a mask-logit channel follows (after the confidence channel when both) */
+  int point_mode;   /* MA_PTS_*: activation of the point channels (reps 0, 3, 4) */
+  int use_factored; /* rep 4: world points from rays, depth and pose instead of the predicted ones */
+  float conf_vmin;  /* confidence = conf_vmin + exp(logit) */
+} ma_decode_spec;
+int ma_decode_scene(const ma_decode_spec* spec, const float* raw, int ld_raw, const float* pose_raw, const float* scale_raw,
+                    int n, int HW, float* pts3d, float* pts3d_cam, float* rays, float* ray_origins, float* depth, float* conf,
+                    float* logits, uint8_t* mask, float* cam_trans, float* cam_quats, float* scale_out, void* stream);
 
 /* ---- infer() input preprocessing (reference mapanything/utils/inference.py:202-291) ------------ */
 

@@ -215,6 +215,27 @@ __global__ void pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ in, __nv_
   }
 }
 
+// The same permutation in fp32 with row strides, for the `linear` prediction head (reference model.py:339-343: a 1x1
+// conv to output_dim * patch^2 channels + F.pixel_shuffle): the GEMM writes [(i,y,x)][(ky*s+kx)*C + c] (weight rows
+// reordered at pack time), this kernel scatters it to the per-pixel rows [(i, y*s+ky, x*s+kx)][0:C] the decode reads.
+__global__ void pixel_shuffle_f32_kernel(const float* __restrict__ in, int64_t ld_in, float* __restrict__ out, int64_t ld_out,
+                                         int n, int h, int w, int C, int s) {
+  const int64_t total = (int64_t)n * h * w * s * s * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    int64_t t = idx / C;
+    const int kk = static_cast<int>(t % (s * s));
+    t /= (s * s);
+    const int x = static_cast<int>(t % w);
+    const int64_t row = t;   // (i*h + y)*w + x
+    t /= w;
+    const int y = static_cast<int>(t % h);
+    const int i = static_cast<int>(t / h);
+    const int ky = kk / s, kx = kk - ky * s;
+    out[(((int64_t)i * h * s + (y * s + ky)) * (w * s) + (x * s + kx)) * ld_out + c] = __ldg(in + row * ld_in + kk * C + c);
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // bilinear resize, align_corners=True, NHWC bf16.  The scale is defined by the VIRTUAL output size (Hv, Wv);
 // only the top-left (Ho, Wo) window is produced (refinenet4: 19 -> 38, cropped to 37).
@@ -454,6 +475,120 @@ __global__ void decode_dense_kernel(const DecodeParams p) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// The same decode for the other scene representations of the reference (model.py:407-587, :1618-1907); the
+// representation / activation selectors are uniform over the launch.  See ma_decode_scene in the header.
+// ----------------------------------------------------------------------------------------------
+struct DecodeSceneParams {
+  ma_decode_spec spec;
+  const float* raw;
+  int ld_raw;
+  const float* pose_raw;
+  const float* scale_raw;
+  float *pts3d, *pts3d_cam, *rays, *origins, *depth, *conf, *logits;
+  uint8_t* mask;
+  float *cam_trans, *cam_quats, *scale_out;
+  int n, HW;
+};
+
+__device__ __forceinline__ void point_activation(int mode, float& x, float& y, float& z) {
+  if (mode == MA_PTS_EXP) {  // unit direction x expm1(norm)
+    const float d = sqrtf(x * x + y * y + z * z);
+    const float f = expm1f(d) / fmaxf(d, 1e-8f);
+    x *= f; y *= f; z *= f;
+  } else if (mode == MA_PTS_Z_EXP) {
+    z = expf(z);
+    x *= z; y *= z;
+  }
+}
+
+__device__ __forceinline__ void store3(float* p, size_t g, float x, float y, float z) {
+  p[g * 3 + 0] = x; p[g * 3 + 1] = y; p[g * 3 + 2] = z;
+}
+
+__global__ void decode_scene_kernel(const DecodeSceneParams p) {
+  const int view = blockIdx.y;
+  const int rep = p.spec.rep;
+  const float scale = fmaxf(expf(p.scale_raw[0]), 1e-8f);
+  float tx = 0.f, ty = 0.f, tz = 0.f;
+  float r00 = 1, r01 = 0, r02 = 0, r10 = 0, r11 = 1, r12 = 0, r20 = 0, r21 = 0, r22 = 1;
+  if (p.pose_raw != nullptr) {
+    const float* pr = p.pose_raw + view * 7;
+    float qx = pr[3], qy = pr[4], qz = pr[5], qw = pr[6];
+    const float inv = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx *= inv; qy *= inv; qz *= inv; qw *= inv;
+    tx = pr[0]; ty = pr[1]; tz = pr[2];
+    r00 = 1 - 2 * (qy * qy + qz * qz); r01 = 2 * (qx * qy - qw * qz); r02 = 2 * (qx * qz + qw * qy);
+    r10 = 2 * (qx * qy + qw * qz); r11 = 1 - 2 * (qx * qx + qz * qz); r12 = 2 * (qy * qz - qw * qx);
+    r20 = 2 * (qx * qz - qw * qy); r21 = 2 * (qy * qz + qw * qx); r22 = 1 - 2 * (qx * qx + qy * qy);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      store3(p.cam_trans, view, tx * scale, ty * scale, tz * scale);
+      p.cam_quats[view * 4 + 0] = qx; p.cam_quats[view * 4 + 1] = qy;
+      p.cam_quats[view * 4 + 2] = qz; p.cam_quats[view * 4 + 3] = qw;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && view == 0) p.scale_out[0] = scale;
+  const int rep_ch = rep == MA_REP_POINTMAP || rep == MA_REP_CAMPOINTMAP_POSE ? 3 : rep == MA_REP_RAYDIRS_DEPTH_POSE ? 4 : 7;
+  const int total_ch = rep_ch + (p.spec.has_conf ? 1 : 0) + (p.spec.has_mask ? 1 : 0);
+  for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < p.HW; px += gridDim.x * blockDim.x) {
+    const size_t g = (size_t)view * p.HW + px;
+    const float* r = p.raw + g * p.ld_raw;
+    float a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = i < total_ch ? r[i] : 0.f;
+    if (rep == MA_REP_POINTMAP) {
+      point_activation(p.spec.point_mode, a[0], a[1], a[2]);
+      store3(p.pts3d, g, a[0] * scale, a[1] * scale, a[2] * scale);
+    } else if (rep == MA_REP_RAYMAP_DEPTH) {
+      const float inv = 1.0f / sqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5]);
+      const float dx = a[3] * inv, dy = a[4] * inv, dz = a[5] * inv;
+      const float depth = expf(a[6]);
+      store3(p.origins, g, a[0] * scale, a[1] * scale, a[2] * scale);
+      store3(p.rays, g, dx, dy, dz);
+      store3(p.pts3d, g, (a[0] + dx * depth) * scale, (a[1] + dy * depth) * scale, (a[2] + dz * depth) * scale);
+      p.depth[g] = depth * scale;
+    } else {
+      // the three posed representations: rays + depth (+ predicted world points), camera points = rays x depth
+      float dx, dy, dz, depth, cx, cy, cz, wx = 0.f, wy = 0.f, wz = 0.f;
+      bool world_predicted = false;
+      if (rep == MA_REP_CAMPOINTMAP_POSE) {
+        point_activation(p.spec.point_mode, a[0], a[1], a[2]);
+        depth = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        dx = a[0] / depth; dy = a[1] / depth; dz = a[2] / depth;
+        cx = a[0]; cy = a[1]; cz = a[2];   // pts3d_cam is the prediction itself (model.py:1751)
+      } else {
+        const int o = rep == MA_REP_RAYDIRS_DEPTH_POSE ? 0 : 3;
+        const float inv = 1.0f / sqrtf(a[o] * a[o] + a[o + 1] * a[o + 1] + a[o + 2] * a[o + 2]);
+        dx = a[o] * inv; dy = a[o + 1] * inv; dz = a[o + 2] * inv;
+        depth = expf(a[o + 3]);
+        cx = dx * depth; cy = dy * depth; cz = dz * depth;
+        if (rep == MA_REP_POINTMAP_RAYDIRS_DEPTH_POSE && !p.spec.use_factored) {
+          point_activation(p.spec.point_mode, a[0], a[1], a[2]);
+          wx = a[0]; wy = a[1]; wz = a[2];
+          world_predicted = true;
+        }
+      }
+      if (!world_predicted) {  // geometry.py:855-907 on rays x depth
+        const float fx = dx * depth, fy = dy * depth, fz = dz * depth;
+        wx = r00 * fx + r01 * fy + r02 * fz + tx;
+        wy = r10 * fx + r11 * fy + r12 * fz + ty;
+        wz = r20 * fx + r21 * fy + r22 * fz + tz;
+      }
+      store3(p.rays, g, dx, dy, dz);
+      store3(p.pts3d_cam, g, cx * scale, cy * scale, cz * scale);
+      store3(p.pts3d, g, wx * scale, wy * scale, wz * scale);
+      p.depth[g] = depth * scale;
+    }
+    int c = rep_ch;
+    if (p.spec.has_conf) p.conf[g] = p.spec.conf_vmin + expf(a[c++]);
+    if (p.spec.has_mask) {
+      const float l = a[c];
+      p.logits[g] = l;
+      p.mask[g] = (1.0f / (1.0f + expf(-l))) > 0.5f ? 1 : 0;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // split_bf16x3: fp32 [rows][C] -> bf16 [rows][3C] = [hi | lo | hi] per group of C channels, hi = bf16(x),
 // lo = bf16(x - hi).  Against weights packed as [w_hi | w_hi | w_lo] one bf16 tensor-core GEMM over K' = 3K computes
 // a_hi*w_hi + a_lo*w_hi + a_hi*w_lo with fp32 accumulation: ~2^-16 relative error per product instead of 2^-8.
@@ -635,6 +770,17 @@ extern "C" int ma_pixel_shuffle(const void* in, void* out, int n, int h, int w, 
   return MA_OK;
 }
 
+extern "C" int ma_pixel_shuffle_f32(const float* in, int64_t ld_in, float* out, int64_t ld_out, int n, int h, int w, int C,
+                                    int s, void* stream) {
+  MA_REQUIRE(in && out && n > 0 && h > 0 && w > 0 && C > 0 && s > 0 && ld_in >= (int64_t)s * s * C && ld_out >= C,
+             "ma_pixel_shuffle_f32: bad arguments");
+  const int64_t total = (int64_t)n * h * w * s * s * C;
+  pixel_shuffle_f32_kernel<<<grid_for(total, 256, device_sm_count() * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, out, ld_out, n, h, w, C, s);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
 extern "C" int ma_bilinear_align_corners(const void* in, void* out, int n, int Hin, int Win, int C, int Hv, int Wv, int Ho,
                                          int Wo, void* stream) {
   MA_REQUIRE(in && out && n > 0 && C % 8 == 0 && Ho <= Hv && Wo <= Wv && Hin > 0 && Win > 0, "ma_bilinear_align_corners: bad arguments");
@@ -718,6 +864,35 @@ extern "C" int ma_decode_dense(const float* raw, int ld_raw, const float* pose_r
                  scale_out, n, HW};
   dim3 grid(grid_for(HW, 256, 1024), n);
   decode_dense_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_decode_scene(const ma_decode_spec* spec, const float* raw, int ld_raw, const float* pose_raw,
+                               const float* scale_raw, int n, int HW, float* pts3d, float* pts3d_cam, float* rays,
+                               float* ray_origins, float* depth, float* conf, float* logits, uint8_t* mask, float* cam_trans,
+                               float* cam_quats, float* scale_out, void* stream) {
+  MA_REQUIRE(spec && raw && scale_raw && pts3d && scale_out && n > 0 && HW > 0, "ma_decode_scene: bad arguments");
+  const int rep = spec->rep;
+  MA_REQUIRE(rep >= MA_REP_POINTMAP && rep <= MA_REP_POINTMAP_RAYDIRS_DEPTH_POSE, "ma_decode_scene: unknown representation %d", rep);
+  MA_REQUIRE(spec->point_mode >= MA_PTS_LINEAR && spec->point_mode <= MA_PTS_Z_EXP, "ma_decode_scene: unknown point_mode %d",
+             spec->point_mode);
+  const bool posed = rep >= MA_REP_RAYDIRS_DEPTH_POSE;
+  const int rep_ch = rep == MA_REP_POINTMAP || rep == MA_REP_CAMPOINTMAP_POSE ? 3 : rep == MA_REP_RAYDIRS_DEPTH_POSE ? 4 : 7;
+  MA_REQUIRE(ld_raw >= rep_ch + (spec->has_conf ? 1 : 0) + (spec->has_mask ? 1 : 0), "ma_decode_scene: ld_raw %d too small", ld_raw);
+  MA_REQUIRE(posed == (pose_raw != nullptr) && posed == (cam_trans != nullptr) && posed == (cam_quats != nullptr) &&
+                 posed == (pts3d_cam != nullptr),
+             "ma_decode_scene: pose_raw / cam_trans / cam_quats / pts3d_cam are given exactly for the posed representations");
+  MA_REQUIRE((rep == MA_REP_RAYMAP_DEPTH) == (ray_origins != nullptr), "ma_decode_scene: ray_origins is for MA_REP_RAYMAP_DEPTH");
+  MA_REQUIRE((rep != MA_REP_POINTMAP) == (rays != nullptr) && (rep != MA_REP_POINTMAP) == (depth != nullptr),
+             "ma_decode_scene: rays / depth are given for every representation but MA_REP_POINTMAP");
+  MA_REQUIRE((spec->has_conf != 0) == (conf != nullptr), "ma_decode_scene: conf pointer vs has_conf");
+  MA_REQUIRE((spec->has_mask != 0) == (logits != nullptr) && (spec->has_mask != 0) == (mask != nullptr),
+             "ma_decode_scene: logits / mask pointers vs has_mask");
+  DecodeSceneParams p{*spec, raw, ld_raw, pose_raw, scale_raw, pts3d, pts3d_cam, rays, ray_origins, depth, conf, logits, mask,
+                      cam_trans, cam_quats, scale_out, n, HW};
+  dim3 grid(grid_for(HW, 256, 1024), n);
+  decode_scene_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

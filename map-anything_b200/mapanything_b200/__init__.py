@@ -7,8 +7,9 @@
 All arithmetic runs in `libmapanything_b200.so` (hand-written CUDA, C ABI in include/mapanything_b200.h).
 """
 from . import _lib  # noqa: F401
-from .config import mapanything_config, tiny_config  # noqa: F401
+from .config import mapanything_config, mapanything_variant_config, pred_head_variant_config, tiny_config  # noqa: F401
 from .image import load_images  # noqa: F401
 from .model import MapAnything  # noqa: F401
 
-__all__ = ["MapAnything", "load_images", "mapanything_config", "tiny_config"]
+__all__ = ["MapAnything", "load_images", "mapanything_config", "mapanything_variant_config", "pred_head_variant_config",
+           "tiny_config"]

@@ -65,6 +65,15 @@ class AttnExt(C.Structure):
     ]
 
 
+class DecodeSpec(C.Structure):
+    """ma_decode_spec (include/mapanything_b200.h)."""
+    _fields_ = [("rep", C.c_int), ("has_conf", C.c_int), ("has_mask", C.c_int), ("point_mode", C.c_int),
+                ("use_factored", C.c_int), ("conf_vmin", C.c_float)]
+
+
+MA_REP = {"pointmap": 0, "raymap+depth": 1, "raydirs+depth+pose": 2, "campointmap+pose": 3, "pointmap+raydirs+depth+pose": 4}
+MA_PTS = {"linear": 0, "exp": 1, "z_exp": 2}
+
 # name -> (restype, argtypes); must list every symbol include/mapanything_b200.h declares.
 _i, _i64, _p, _f = C.c_int, C.c_int64, C.c_void_p, C.c_float
 SIGNATURES = {
@@ -85,9 +94,11 @@ SIGNATURES = {
     "ma_set_rows": (_i, [_p, _i64, _i, _i64, _i64, _p, _p, _i, _p]),
     "ma_im2col3x3": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ma_pixel_shuffle": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ma_pixel_shuffle_f32": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _i, _i, _p]),
     "ma_bilinear_align_corners": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ma_token_mean": (_i, [_p, _p, _i, _i, _i, _p]),
     "ma_decode_dense": (_i, [_p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ma_decode_scene": (_i, [C.POINTER(DecodeSpec), _p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ma_head_linear_small": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i, _i, _p]),
     "ma_split_bf16x3": (_i, [_p, _i64, _p, _i, _i, _p]),
     "ma_token_mean_f32": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -96,7 +96,8 @@ INFO_SHARING_VARIANTS = {
 }
 
 
-def mapanything_variant_config(info_sharing: str = "aat_ifr_24_layers", **overrides) -> dict:
+def mapanything_variant_config(info_sharing: str = "aat_ifr_24_layers", adaptor_config: str = None, head_type: str = None,
+                               adaptor_type: str = None, **overrides) -> dict:
     """mapanything_config() with another info-sharing YAML of the reference (`model/info_sharing=<name>` on its Hydra
     command line): the 48-layer / width-1024 transformer with three taps, and the variants without reference-view embedding."""
     if info_sharing not in INFO_SHARING_VARIANTS:
@@ -107,6 +108,83 @@ def mapanything_variant_config(info_sharing: str = "aat_ifr_24_layers", **overri
                                                  **copy.deepcopy(INFO_SHARING_VARIANTS[info_sharing])}
     if info_sharing.startswith("gat_"):
         cfg["info_sharing_config"]["model_type"] = "global_attention"
+    if adaptor_config is not None or head_type is not None or adaptor_type is not None:
+        cfg["pred_head_config"] = pred_head_variant_config(adaptor_config or "raydirs_depth_pose_confidence_mask_scale",
+                                                           head_type, adaptor_type)
+    return cfg
+
+
+# configs/model/pred_head/adaptor_config/*.yaml of the reference (the *_scale forms: every working MapAnything config
+# carries a scale head, model.py:352,388), keyed by file name.  (rep channels, point mode, posed, extra keys)
+_DENSE_RAYS_DEPTH = {
+    "ray_directions_mode": "linear", "ray_directions_normalize_to_unit_sphere": True,
+    "ray_directions_normalize_to_unit_image_plane": False, "ray_directions_vmin": -INF, "ray_directions_vmax": INF,
+    "ray_directions_clamp_min_of_z_dir": False, "ray_directions_z_dir_min": -INF, "depth_mode": "exp", "depth_vmin": 0,
+    "depth_vmax": INF,
+}
+_CONF = {"confidence_type": "exp", "confidence_vmin": 1, "confidence_vmax": INF}
+ADAPTOR_CONFIGS = {
+    "raydirs_depth_pose_confidence_mask_scale": {
+        "input_dim": 6, "scene_rep_dim": 4, "type": "raydirs+depth+pose+confidence+mask", "scene_rep_type": "raydirs+depth+pose",
+        "dense": {**_DENSE_RAYS_DEPTH, **_CONF}},
+    "pointmap_confidence_mask_scale": {
+        "input_dim": 5, "scene_rep_dim": 3, "type": "pointmap+confidence+mask", "scene_rep_type": "pointmap",
+        "dense": {"pointmap_mode": "exp", "pointmap_vmin": -INF, "pointmap_vmax": INF, **_CONF}},
+    "campointmap_pose_confidence_mask_scale": {
+        "input_dim": 5, "scene_rep_dim": 3, "type": "campointmap+pose+confidence+mask", "scene_rep_type": "campointmap+pose",
+        "dense": {"pointmap_mode": "z_exp", "pointmap_vmin": -INF, "pointmap_vmax": INF, **_CONF}},
+    "pointmap_raydirs_depth_pose_confidence_mask_scale": {
+        "input_dim": 9, "scene_rep_dim": 7, "type": "pointmap+raydirs+depth+pose+confidence+mask",
+        "scene_rep_type": "pointmap+raydirs+depth+pose", "use_factored_predictions_for_global_pointmaps": False,
+        "dense": {"pointmap_mode": "exp", "pointmap_vmin": -INF, "pointmap_vmax": INF, **_DENSE_RAYS_DEPTH, **_CONF}},
+    "pointmap_factored_raydirs_depth_pose_confidence_mask_scale": {
+        "input_dim": 9, "scene_rep_dim": 7, "type": "pointmap+raydirs+depth+pose+confidence+mask",
+        "scene_rep_type": "pointmap+raydirs+depth+pose", "use_factored_predictions_for_global_pointmaps": True,
+        "dense": {"pointmap_mode": "exp", "pointmap_vmin": -INF, "pointmap_vmax": INF, **_DENSE_RAYS_DEPTH, **_CONF}},
+}
+
+
+def pred_head_variant_config(adaptor_config: str = "raydirs_depth_pose_confidence_mask_scale", head_type: str = None,
+                             adaptor_type: str = None) -> dict:
+    """`pred_head_config` for another adaptor YAML of the reference (Hydra: `model/pred_head=dpt_pose_scale
+    model/pred_head/adaptor_config=<name>`, or `model/pred_head=dpt_scale` for the pose-free representations).
+    head_type defaults to "dpt+pose" for the posed representations and "dpt" otherwise ("linear" is accepted for the
+    pose-free ones); adaptor_type overrides the YAML's type with one of its confidence / mask subsets
+    (e.g. "pointmap+confidence": reference model.py:407-587 lists all twenty)."""
+    if adaptor_config not in ADAPTOR_CONFIGS:
+        raise ValueError(f"adaptor_config must be one of {sorted(ADAPTOR_CONFIGS)}, got {adaptor_config!r}")
+    ac = copy.deepcopy(ADAPTOR_CONFIGS[adaptor_config])
+    dense = ac.pop("dense")
+    rep = ac["scene_rep_type"]
+    posed = "pose" in rep
+    name = ac["type"] + "+scale"
+    if adaptor_type is not None:
+        if not adaptor_type.startswith(rep):
+            raise ValueError(f"adaptor_type {adaptor_type!r} is not a variant of {rep!r}")
+        ac["type"] = adaptor_type
+        ac["input_dim"] = ac["scene_rep_dim"] + ("confidence" in adaptor_type) + ("mask" in adaptor_type)
+    head_type = head_type or ("dpt+pose" if posed else "dpt")
+    dense = {"name": name, **dense}
+    scale = {"name": name, "mode": "exp", "vmin": 1e-08, "vmax": INF}
+    cfg = {"type": head_type, "adaptor_type": ac["type"], "scale_head": {"output_dim": 1}, "scale_adaptor": scale,
+           "gradient_checkpointing": False}
+    if head_type == "linear":
+        cfg["feature_head"] = {"output_dim": ac["input_dim"]}
+    else:
+        cfg["feature_head"] = {"feature_dim": 256, "hooks": [0, 1, 2, 3], "checkpoint_gradient": False}
+        cfg["regressor_head"] = {"output_dim": ac["input_dim"], "checkpoint_gradient": False}
+    if posed:
+        cfg["pose_head"] = {"num_resconv_block": 2, "rot_representation_dim": 4}
+        cfg["dpt_adaptor"] = dense
+        cfg["pose_adaptor"] = {"name": name, "cam_trans_mode": "linear", "cam_trans_vmin": -INF, "cam_trans_vmax": INF,
+                               "quaternions_mode": "linear", "quaternions_normalize": True, "quaternions_vmin": -INF,
+                               "quaternions_vmax": INF}
+        ac["dense_pred_init_dict"], ac["pose_pred_init_dict"] = dense, cfg["pose_adaptor"]
+    else:
+        cfg["adaptor"] = dense
+        ac["init_dict"] = dense
+    ac["scale_pred_init_dict"] = scale
+    cfg["adaptor_config"] = ac   # Hydra nests the chosen adaptor YAML here; model.py:1822 reads it
     return cfg
 
 

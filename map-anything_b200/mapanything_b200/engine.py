@@ -215,6 +215,41 @@ class Engine:
         self.scale_tok_proj = torch.empty(1, self.D, device=self.device, dtype=torch.float32)
         ops.gemm(tok, self.proj_embed.w, self.scale_tok_proj, bias=self.proj_embed.b)
 
+        # prediction heads (reference model.py:320-388): "dpt+pose" (released), "dpt" (no pose head), "linear"
+        self.head_type = getattr(model, "pred_head_type", "dpt+pose")
+        self.reg3_fused, self.linear_head = None, None
+        if "dpt" in self.head_type:
+            self._init_dpt(model)
+            self.head_out_dim = self.reg3.n
+        else:
+            self._init_linear_head(model)
+        self.raw_ld = 8 if self.head_out_dim <= 8 else (self.head_out_dim + 3) // 4 * 4
+        self.scale_act = MA_ACT_GELU if getattr(model.scale_head, "activation", "relu") == "gelu" else MA_ACT_RELU
+        if self.head_type == "dpt+pose":
+            self._init_pose(model)
+        self.scale_mlp = [Lin3(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
+        import os
+
+        # view groups of the encoder on separate CUDA streams: +1 % before programmatic dependent launch existed, equal with
+        # it, and now slower than one stream (same-box A/B at 8 views: 327-328 views/s with two, 332 with one, 335 with one
+        # and the persistent two-stream attention kernel, which wants all views in one launch)
+        self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "1")))
+        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        # tail-wave splitting of long attention (the slots of the last, partially filled wave of SMs are cut over the key range,
+        # ma_attention_merge joins them): neutral with the free-running kernels of round 1, but with the ping-pong two-tile
+        # kernel the 8-view global attention drops from 6.34 to 5.67 + 0.15 (merge) ms per step (same-box A/B, 320 -> 332
+        # views/s); MA_ATTN_KV_SPLIT=0 turns it off
+        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "1") != "0"
+        # views per DPT pass (bounds the activation scratch: ~0.6 GB per view at 518 px).  8 instead of 4: same-box A/B at 8
+        # views 311.1 vs 301.6 views/s (fewer, larger launches); MA_DPT_CHUNK overrides for A/B runs
+        self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "8")))
+        self.dpt_chunk = self.dpt_chunk_default
+        self.proj_block_n = int(os.environ.get("MA_PROJ_BN", "0"))   # A/B knob: tile code of the attention-projection GEMMs
+        # measurement aid (bench.py `strong` record): when a list, every sharded global block appends the CUDA events that
+        # bracket its wait for the K/V all-gather on the compute stream
+        self.ag_wait_events = None
+
+    def _init_dpt(self, model):
         dpt = model.dpt_feature_head
         ap = dpt.act_postprocess
         self.feat = dpt.feature_dim
@@ -248,9 +283,9 @@ class Engine:
                 hb[:w3.shape[0]] = reg.conv2[2].bias.detach().float()
             self.reg3_fused = (hw.contiguous(), hb.contiguous())
 
+    def _init_pose(self, model):
         ph = model.pose_head
         self.pose_relu_after_skip = bool(getattr(ph, "final_relu_after_skip", True))
-        self.scale_act = MA_ACT_GELU if getattr(model.scale_head, "activation", "relu") == "gelu" else MA_ACT_RELU
         self.pose_blocks = []
         for rb in ph.res_conv:
             if not isinstance(rb.head_skip, nn.Identity):
@@ -276,27 +311,17 @@ class Engine:
         ) for rb in ph.res_conv]
         self.pose_mlp = [Lin3(ph.more_mlps[0].weight, ph.more_mlps[0].bias), Lin3(ph.more_mlps[2].weight, ph.more_mlps[2].bias)]
         self.pose_out = Lin3(torch.cat([ph.fc_t.weight, ph.fc_rot.weight], 0), torch.cat([ph.fc_t.bias, ph.fc_rot.bias], 0))
-        self.scale_mlp = [Lin3(m.weight, m.bias) for m in model.scale_head.mlp if isinstance(m, nn.Linear)]
-        import os
 
-        # view groups of the encoder on separate CUDA streams: +1 % before programmatic dependent launch existed, equal with
-        # it, and now slower than one stream (same-box A/B at 8 views: 327-328 views/s with two, 332 with one, 335 with one
-        # and the persistent two-stream attention kernel, which wants all views in one launch)
-        self.encoder_streams = max(1, int(os.environ.get("MA_ENCODER_STREAMS", "1")))
-        self.sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-        # tail-wave splitting of long attention (the slots of the last, partially filled wave of SMs are cut over the key range,
-        # ma_attention_merge joins them): neutral with the free-running kernels of round 1, but with the ping-pong two-tile
-        # kernel the 8-view global attention drops from 6.34 to 5.67 + 0.15 (merge) ms per step (same-box A/B, 320 -> 332
-        # views/s); MA_ATTN_KV_SPLIT=0 turns it off
-        self.kv_split_enabled = os.environ.get("MA_ATTN_KV_SPLIT", "1") != "0"
-        # views per DPT pass (bounds the activation scratch: ~0.6 GB per view at 518 px).  8 instead of 4: same-box A/B at 8
-        # views 311.1 vs 301.6 views/s (fewer, larger launches); MA_DPT_CHUNK overrides for A/B runs
-        self.dpt_chunk_default = max(1, int(os.environ.get("MA_DPT_CHUNK", "8")))
-        self.dpt_chunk = self.dpt_chunk_default
-        self.proj_block_n = int(os.environ.get("MA_PROJ_BN", "0"))   # A/B knob: tile code of the attention-projection GEMMs
-        # measurement aid (bench.py `strong` record): when a list, every sharded global block appends the CUDA events that
-        # bracket its wait for the K/V all-gather on the compute stream
-        self.ag_wait_events = None
+    def _init_linear_head(self, model):
+        """pred_head_type "linear": the 1x1 conv as a split-bf16 (~fp32: the reference runs the heads with autocast disabled,
+        model.py:1599) GEMM whose rows are reordered from F.pixel_shuffle's channel order (c, ky, kx) to (ky, kx, c), so that
+        ma_pixel_shuffle_f32 scatters contiguous channel groups."""
+        lf = model.dense_head
+        p, od = lf.patch_size, lf.output_dim
+        w = lf.proj.weight.detach().reshape(od, p * p, -1).permute(1, 0, 2).reshape(p * p * od, -1)
+        b = lf.proj.bias.detach().reshape(od, p * p).t().reshape(-1) if lf.proj.bias is not None else None
+        self.linear_head = Lin3(w, b)
+        self.head_out_dim = od
 
     # ------------------------------------------------------------------------------------------ helpers
     def _empty(self, *shape, dtype=torch.bfloat16):
@@ -740,13 +765,23 @@ class Engine:
 
     def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int,
                      final32: Optional[torch.Tensor] = None):
-        """taps4: 4 x bf16 [V*N][C_i] (+ final32 fp32 [V*N][D] for the pose head; defaults to taps4[3] upcast)
-        -> raw dense fp32 [V*H*W][8] (6 used), pose_raw fp32 [V][7]."""
+        """taps4: 4 x bf16 [V*N][C_i] (+ final32 fp32 [V*N][D] for the pose / linear head; defaults to taps4[3] upcast)
+        -> raw dense fp32 [V*H*W][raw_ld] (head_out_dim used), pose_raw fp32 [V][7] (None without a pose head)."""
         if final32 is None:
             final32 = taps4[3].float()
         N = hp * wp
-        raw = self._empty(V * H * W, 8, dtype=torch.float32)
-        pose_raw = self._empty(V, 7, dtype=torch.float32)
+        raw = self._empty(V * H * W, self.raw_ld, dtype=torch.float32)
+        if self.head_type == "linear":
+            # reference model.py:1310-1320: the dense head sees the final features only; rows = tokens, fp32-accurate GEMM
+            od, ps = self.head_out_dim, self.patch
+            for s in range(0, V, self.dpt_chunk):
+                n = min(self.dpt_chunk, V - s)
+                y = self._empty(n * N, self.linear_head.n, dtype=torch.float32)
+                self._lin3(final32[s * N:(s + n) * N], self.linear_head, y)
+                ops.pixel_shuffle_f32(y, raw[s * H * W:(s + n) * H * W], n, hp, wp, od, ps)
+            return raw, None
+        with_pose = self.head_type == "dpt+pose"
+        pose_raw = self._empty(V, 7, dtype=torch.float32) if with_pose else None
         for s in range(0, V, self.dpt_chunk):
             n = min(self.dpt_chunk, V - s)
             t = [x[s * N:(s + n) * N] for x in taps4]
@@ -775,7 +810,8 @@ class Engine:
             rawv = raw[s * H * W:(s + n) * H * W]
             if self.reg3_fused is not None and raw.shape[1] == 8:
                 ops.conv3x3_head(g1u, self.reg2.w, self.reg2.b, MA_ACT_RELU, self.reg3_fused[0], self.reg3_fused[1], rawv)
-                self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
+                if with_pose:
+                    self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
                 continue
             g2 = self._conv3(g1u, self.reg2, act=MA_ACT_RELU)
             g2f = g2.reshape(n * H * W, -1)
@@ -784,7 +820,8 @@ class Engine:
             else:
                 ops.gemm(g2f, self.reg3.w, rawv[:, :self.reg3.n], bias=self.reg3.b)
             # pose head on the final info-sharing features (split-bf16 precision)
-            self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
+            if with_pose:
+                self.pose_head(final32[s * N:(s + n) * N], n, hp, wp, pose_raw[s:s + n], x16=t[3])
         return raw, pose_raw
 
     def scale_head(self, tok_feat32: torch.Tensor) -> torch.Tensor:

@@ -198,15 +198,11 @@ def _postprocess(raw_outputs, input_views, apply_mask, mask_edges, edge_normal_t
                 cm = quantile_mask(out["conf"], confidence_percentile / 100.0)
                 final = cm if final is None else mask_and(final, cm)
             if mask_edges and final is not None and "pts3d" in out:
+                if "pts3d_cam" not in out:   # the reference reads processed_output["depth_z"] here (inference.py:440)
+                    raise KeyError("depth_z")
                 final = edge_mask(out["pts3d"], out["pts3d_cam"], final, edge_normal_threshold, edge_depth_threshold)
             if final is not None:
-                m = final.contiguous()
-                pts_cam = out["pts3d_cam"]
-                out["pts3d"] = _masked(out["pts3d"], m, 3)
-                out["depth_z"] = _masked(pts_cam, m, 1, in_stride=3, in_offset=2)
-                out["pts3d_cam"] = _masked(pts_cam, m, 3)
-                out["depth_along_ray"] = _masked(out["depth_along_ray"], m, 1)
-                out["mask"] = m.unsqueeze(-1)
+                _apply_final_mask(out, final.contiguous())
         processed.append(out)
     return processed
 
@@ -222,22 +218,24 @@ def postprocess_scene(stacked: Dict[str, torch.Tensor], imgs: torch.Tensor, norm
         V = imgs.shape[0]
         out = dict(stacked)
         out["img_no_norm"] = denorm_image(imgs, norm_type)
-        out["depth_z"] = out["pts3d_cam"][..., 2:3]
-        out["intrinsics"] = intrinsics_from_rays(out["ray_directions"])
-        out["camera_poses"] = pose_matrices(out["cam_quats"], out["cam_trans"])
+        # which fields exist follows the model's scene representation (reference inference.py:350-379)
+        if "pts3d_cam" in out:
+            out["depth_z"] = out["pts3d_cam"][..., 2:3]
+        if "ray_directions" in out:
+            out["intrinsics"] = intrinsics_from_rays(out["ray_directions"])
+        if "cam_trans" in out and "cam_quats" in out:
+            out["camera_poses"] = pose_matrices(out["cam_quats"], out["cam_trans"])
         if apply_mask:
-            final = out["non_ambiguous_mask"]
-            if apply_confidence_mask:
-                final = mask_and(final, quantile_mask(out["conf"], confidence_percentile / 100.0))
-            if mask_edges:
+            final = out.get("non_ambiguous_mask")
+            if apply_confidence_mask and "conf" in out:
+                cm = quantile_mask(out["conf"], confidence_percentile / 100.0)
+                final = cm if final is None else mask_and(final, cm)
+            if mask_edges and final is not None and "pts3d" in out:
+                if "pts3d_cam" not in out:   # the reference reads processed_output["depth_z"] here (inference.py:440)
+                    raise KeyError("depth_z")
                 final = edge_mask(out["pts3d"], out["pts3d_cam"], final, edge_normal_threshold, edge_depth_threshold)
-            m = final.contiguous()
-            pts_cam = out["pts3d_cam"]
-            out["pts3d"] = _masked(out["pts3d"], m, 3)
-            out["depth_z"] = _masked(pts_cam, m, 1, in_stride=3, in_offset=2)
-            out["pts3d_cam"] = _masked(pts_cam, m, 3)
-            out["depth_along_ray"] = _masked(out["depth_along_ray"], m, 1)
-            out["mask"] = m.unsqueeze(-1)
+            if final is not None:
+                _apply_final_mask(out, final.contiguous())
         scale = out.pop("metric_scaling_factor")
         res = []
         for i in range(V):
@@ -245,6 +243,18 @@ def postprocess_scene(stacked: Dict[str, torch.Tensor], imgs: torch.Tensor, norm
             d["metric_scaling_factor"] = scale
             res.append(d)
         return res
+
+
+def _apply_final_mask(out: Dict[str, torch.Tensor], m: torch.Tensor) -> None:
+    """Zero the dense geometry outside the mask and attach it (reference inference.py:452-476); absent keys are skipped."""
+    pts_cam = out.get("pts3d_cam")
+    out["pts3d"] = _masked(out["pts3d"], m, 3)
+    if pts_cam is not None:
+        out["depth_z"] = _masked(pts_cam, m, 1, in_stride=3, in_offset=2)
+        out["pts3d_cam"] = _masked(pts_cam, m, 3)
+    if "depth_along_ray" in out:
+        out["depth_along_ray"] = _masked(out["depth_along_ray"], m, 1)
+    out["mask"] = m.unsqueeze(-1)
 
 
 def _masked(x, m, width, in_stride=None, in_offset=0):

@@ -135,55 +135,109 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
             )
 
     def _initialize_prediction_heads(self, cfg):
-        if self.pred_head_type != "dpt+pose":
-            raise ValueError(f"Invalid pred_head_type: {self.pred_head_type}. This build supports 'dpt+pose'.")
+        """reference model.py:320-388: "linear" (one 1x1 conv + pixel shuffle on the final features), "dpt" (DPT + regressor),
+        "dpt+pose" (+ pose head); the scale head always."""
         cfg["feature_head"]["patch_size"] = self.encoder.patch_size
-        if self.use_encoder_features_for_dpt:
-            cfg["feature_head"]["input_feature_dims"] = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+        if self.pred_head_type == "linear":
+            cfg["feature_head"]["input_feature_dim"] = self.info_sharing.dim
+        elif "dpt" in self.pred_head_type:
+            if self.use_encoder_features_for_dpt:
+                cfg["feature_head"]["input_feature_dims"] = [self.encoder.enc_embed_dim] + [self.info_sharing.dim] * 3
+            else:
+                cfg["feature_head"]["input_feature_dims"] = [self.info_sharing.dim] * 4
+            cfg["regressor_head"]["input_feature_dim"] = cfg["feature_head"]["feature_dim"]
+            if "pose" in self.pred_head_type:
+                cfg["pose_head"]["patch_size"] = self.encoder.patch_size
+                cfg["pose_head"]["input_feature_dim"] = self.info_sharing.dim
         else:
-            cfg["feature_head"]["input_feature_dims"] = [self.info_sharing.dim] * 4
-        cfg["regressor_head"]["input_feature_dim"] = cfg["feature_head"]["feature_dim"]
-        cfg["pose_head"]["patch_size"] = self.encoder.patch_size
-        cfg["pose_head"]["input_feature_dim"] = self.info_sharing.dim
+            raise ValueError(
+                f"Invalid pred_head_type: {self.pred_head_type}. Valid options: ['linear', 'dpt', 'dpt+pose']"
+            )
         cfg["scale_head"]["input_feature_dim"] = self.info_sharing.dim
-        self.dpt_feature_head = P.DPTFeature(**cfg["feature_head"])
-        self.dpt_regressor_head = P.DPTRegressionProcessor(**cfg["regressor_head"])
-        self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)
-        self.pose_head = P.PoseHead(**cfg["pose_head"])
+        if self.pred_head_type == "linear":
+            self.dense_head = P.LinearFeature(**cfg["feature_head"])
+        else:
+            self.dpt_feature_head = P.DPTFeature(**cfg["feature_head"])
+            self.dpt_regressor_head = P.DPTRegressionProcessor(**cfg["regressor_head"])
+            self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)
+            if "pose" in self.pred_head_type:
+                self.pose_head = P.PoseHead(**cfg["pose_head"])
         self.scale_head = P.MLPHead(**cfg["scale_head"])
 
+    # scene representation -> channels of the dense head it consumes (before the optional confidence / mask channels)
+    _SCENE_REP_CHANNELS = {"pointmap": 3, "raymap+depth": 7, "raydirs+depth+pose": 4, "campointmap+pose": 3,
+                           "pointmap+raydirs+depth+pose": 7}
+
     def _initialize_adaptors(self, cfg):
-        if cfg["adaptor_type"] != "raydirs+depth+pose+confidence+mask":
+        """reference model.py:390-588: the 20 adaptor types = 5 scene representations x {-, confidence} x {-, mask}.  The
+        adaptors are parameter-free; here they are the selectors of the fused decode kernels (ma_decode_dense for the
+        released representation, ma_decode_scene for the others), which implement the parameter values of the reference's
+        adaptor YAMLs (configs/model/pred_head/adaptor_config/*.yaml) -- anything else raises instead of decoding differently."""
+        adaptor_type = cfg["adaptor_type"]
+        parts = adaptor_type.split("+")
+        has_mask = parts[-1] == "mask"
+        parts = parts[:-1] if has_mask else parts
+        has_conf = parts[-1] == "confidence"
+        parts = parts[:-1] if has_conf else parts
+        rep = "+".join(parts)
+        if rep not in self._SCENE_REP_CHANNELS:
             raise ValueError(
-                f"Invalid adaptor_type: {cfg['adaptor_type']}. This build supports 'raydirs+depth+pose+confidence+mask'."
+                f"Invalid adaptor_type: {adaptor_type}. Valid options: ['pointmap', 'raymap+depth', 'raydirs+depth+pose', "
+                f"'campointmap+pose', 'pointmap+raydirs+depth+pose'], each optionally followed by '+confidence', '+mask' or "
+                f"'+confidence+mask'")
+        posed = "pose" in rep
+        if posed:
+            assert self.pred_head_type == "dpt+pose", (
+                f"{rep} can only be used as scene representation with dpt + pose head."
             )
-        a = cfg.get("dpt_adaptor", {})
-        ok = (a.get("ray_directions_mode", "linear") == "linear" and a.get("ray_directions_normalize_to_unit_sphere", True)
-              and a.get("depth_mode", "exp") == "exp" and a.get("confidence_type", "exp") == "exp"
-              and float(a.get("confidence_vmin", 1)) == 1.0 and float(a.get("depth_vmin", 0)) == 0.0)
         inf = float("inf")
-        ok = (ok and a.get("ray_directions_vmin", -inf) == -inf and a.get("ray_directions_vmax", inf) == inf
-              and not a.get("ray_directions_normalize_to_unit_image_plane", False)
-              and not a.get("ray_directions_clamp_min_of_z_dir", False)
-              and a.get("depth_vmax", inf) == inf and a.get("confidence_vmax", inf) == inf)
+        a = cfg.get("dpt_adaptor" if posed else "adaptor", {})
+
+        def unbounded(prefix):
+            return a.get(f"{prefix}_vmin", -inf) == -inf and a.get(f"{prefix}_vmax", inf) == inf
+
+        ok = True
+        self._point_mode = "exp"
+        if rep in ("pointmap", "campointmap+pose", "pointmap+raydirs+depth+pose"):
+            self._point_mode = a.get("pointmap_mode", "exp")
+            ok = ok and self._point_mode in ("linear", "exp", "z_exp") and unbounded("pointmap")
+        if rep != "pointmap" and rep != "campointmap+pose":
+            ok = (ok and a.get("ray_directions_mode", "linear") == "linear"
+                  and a.get("ray_directions_normalize_to_unit_sphere", True)
+                  and not a.get("ray_directions_normalize_to_unit_image_plane", False)
+                  and not a.get("ray_directions_clamp_min_of_z_dir", False) and unbounded("ray_directions")
+                  and a.get("depth_mode", "exp") == "exp" and float(a.get("depth_vmin", 0)) == 0.0
+                  and a.get("depth_vmax", inf) == inf)
+            if rep == "raymap+depth":
+                ok = ok and a.get("ray_origins_mode", "linear") == "linear" and unbounded("ray_origins")
+        if has_conf:
+            ok = ok and a.get("confidence_type", "exp") == "exp" and a.get("confidence_vmax", inf) == inf
         if not ok:
-            raise ValueError("the fused decode kernel implements the released dense adaptor parameters only")
-        # the same kernel hard-codes the pose adaptor (linear translation, linear + normalised quaternion) and the scale
-        # adaptor (exp, clamped below at 1e-8): reject anything else instead of silently decoding it differently
-        pa = cfg.get("pose_adaptor", {})
-        ok = (pa.get("cam_trans_mode", "linear") == "linear" and pa.get("quaternions_mode", "linear") == "linear"
-              and pa.get("quaternions_normalize", True) and pa.get("cam_trans_vmin", -inf) == -inf
-              and pa.get("cam_trans_vmax", inf) == inf and pa.get("quaternions_vmin", -inf) == -inf
-              and pa.get("quaternions_vmax", inf) == inf)
-        if not ok:
-            raise ValueError("the fused decode kernel implements the released pose adaptor parameters only "
-                             "(linear translation, linear normalised quaternion, no clamping)")
+            raise ValueError("the fused decode kernels implement the dense adaptor parameters of the reference's adaptor YAMLs "
+                             "only (linear unit-sphere rays, exp depth, exp confidence, linear / exp / z_exp points, no clamping)")
+        self._conf_vmin = float(a.get("confidence_vmin", 1))
+        if posed:
+            # the kernels hard-code the pose adaptor (linear translation, linear + normalised quaternion)
+            pa = cfg.get("pose_adaptor", {})
+            ok = (pa.get("cam_trans_mode", "linear") == "linear" and pa.get("quaternions_mode", "linear") == "linear"
+                  and pa.get("quaternions_normalize", True) and pa.get("cam_trans_vmin", -inf) == -inf
+                  and pa.get("cam_trans_vmax", inf) == inf and pa.get("quaternions_vmin", -inf) == -inf
+                  and pa.get("quaternions_vmax", inf) == inf)
+            if not ok:
+                raise ValueError("the fused decode kernel implements the released pose adaptor parameters only "
+                                 "(linear translation, linear normalised quaternion, no clamping)")
         sa = cfg.get("scale_adaptor", {})
         ok = (sa.get("mode", "exp") == "exp" and abs(float(sa.get("vmin", 1e-8)) - 1e-8) < 1e-12
               and sa.get("vmax", inf) == inf)
         if not ok:
             raise ValueError("the fused decode kernel implements the released scale adaptor parameters only (exp, vmin 1e-8)")
-        self.scene_rep_type = "raydirs+depth+pose+confidence+mask"
+        head_dim = (cfg["feature_head"] if self.pred_head_type == "linear" else cfg["regressor_head"])["output_dim"]
+        need = self._SCENE_REP_CHANNELS[rep] + int(has_conf) + int(has_mask)
+        if head_dim != need:
+            raise ValueError(f"adaptor_type {adaptor_type!r} consumes {need} channels, the dense head produces {head_dim}")
+        self.scene_rep_type = adaptor_type
+        self._scene_rep, self._has_conf, self._has_mask = rep, has_conf, has_mask
+        self._released_decode = (adaptor_type == "raydirs+depth+pose+confidence+mask" and self._conf_vmin == 1.0)
 
     def _load_pretrained_weights(self):
         if self.pretrained_checkpoint_path is None:
@@ -381,8 +435,10 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         res = []
         for i in range(num_views):
             d = {}
-            for key in ("pts3d", "pts3d_cam", "ray_directions", "depth_along_ray", "cam_trans", "cam_quats", "conf",
-                        "non_ambiguous_mask", "non_ambiguous_mask_logits"):
+            for key in ("pts3d", "pts3d_cam", "ray_origins", "ray_directions", "depth_along_ray", "cam_trans", "cam_quats",
+                        "conf", "non_ambiguous_mask", "non_ambiguous_mask_logits"):
+                if key not in per_scene[0]:   # keys follow the scene representation (reference model.py:1618-1907)
+                    continue
                 parts = [s[key][i:i + 1] for s in per_scene]
                 d[key] = parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)
             scales = [s["metric_scaling_factor"] for s in per_scene]
@@ -443,8 +499,19 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                     scale_raw = eng.scale_head(final32[num_views * N:]) if plan.rank == 0 else \
                         torch.empty(1, device=self.device, dtype=torch.float32)
                     comm.broadcast(scale_raw, src=0)
-                per_scene.append(ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width))
+                per_scene.append(self._decode(raw, pose_raw, scale_raw, num_views, height, width))
         return per_scene, scene_imgs
+
+    def _decode(self, raw, pose_raw, scale_raw, num_views, height, width):
+        """dense / pose / scale adaptors + the scene-representation branch of reference model.py:1618-1907, one launch."""
+        if self._released_decode:
+            return ops.decode_dense(raw, pose_raw, scale_raw, num_views, height, width)
+        use_factored = False
+        if self._scene_rep == "pointmap+raydirs+depth+pose":   # reference model.py:1822-1833
+            use_factored = bool(self.pred_head_config["adaptor_config"]["use_factored_predictions_for_global_pointmaps"])
+        return ops.decode_scene(raw, pose_raw, scale_raw, num_views, height, width, rep=self._scene_rep,
+                                has_conf=self._has_conf, has_mask=self._has_mask, point_mode=self._point_mode,
+                                use_factored=use_factored, conf_vmin=self._conf_vmin)
 
     # ------------------------------------------------------------------------------------------ infer
     def _configure_geometric_input_config(self, use_calibration: bool, use_depth: bool, use_pose: bool,

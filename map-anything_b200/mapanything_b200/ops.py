@@ -405,6 +405,18 @@ def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C_
     return out
 
 
+def pixel_shuffle_f32(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C_: int, s: int) -> torch.Tensor:
+    """fp32 rows [(i,y,x)][(ky*s+kx)*C + c] (row stride x.stride(0)) -> out rows [(i, y*s+ky, x*s+kx)][0:C] (ma_pixel_shuffle_f32)."""
+    if x.dtype != torch.float32 or out.dtype != torch.float32 or x.stride(-1) != 1 or out.stride(-1) != 1:
+        raise ValueError("pixel_shuffle_f32: fp32 tensors with contiguous rows")
+    if x.shape[0] != n * h * w or out.shape[0] != n * h * w * s * s:
+        raise ValueError("pixel_shuffle_f32: row counts do not match (n, h, w, s)")
+    with launch("pixel_shuffle"):
+        check(_lib.load().ma_pixel_shuffle_f32(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n, h, w, C_, s, _stream()),
+              "ma_pixel_shuffle_f32")
+    return out
+
+
 def bilinear_ac(x: torch.Tensor, out: torch.Tensor, virtual_hw=None) -> torch.Tensor:
     """NHWC bf16 bilinear resize with align_corners=True; out (n,Ho,Wo,C); virtual_hw = uncropped output size."""
     _req(x, torch.bfloat16, "x")
@@ -507,6 +519,54 @@ def decode_dense(raw: torch.Tensor, pose_raw: torch.Tensor, scale_raw: torch.Ten
                 o["cam_trans"].data_ptr(), o["cam_quats"].data_ptr(), o["metric_scaling_factor"].data_ptr(), _stream(),
             ),
             "ma_decode_dense",
+        )
+    return o
+
+
+def decode_scene(raw: torch.Tensor, pose_raw: Optional[torch.Tensor], scale_raw: torch.Tensor, n: int, H: int, W: int, *,
+                 rep: str, has_conf: bool, has_mask: bool, point_mode: str = "exp", use_factored: bool = False,
+                 conf_vmin: float = 1.0):
+    """ma_decode_scene: the fused adaptor + decode for every scene representation of reference model.py:407-587 / :1618-1907.
+    raw fp32 [n*H*W, ld]; pose_raw fp32 [n, 7] for the posed representations, else None.  Returns the forward() tensors the
+    representation defines (as [n, ...]) + metric_scaling_factor [1, 1]."""
+    if raw.dtype != torch.float32 or raw.stride(-1) != 1:
+        raise ValueError("decode_scene: raw must be fp32 with contiguous rows")
+    if rep not in _lib.MA_REP or point_mode not in _lib.MA_PTS:
+        raise ValueError(f"decode_scene: unknown representation {rep!r} / pointmap_mode {point_mode!r}")
+    posed = "pose" in rep
+    if posed != (pose_raw is not None):
+        raise ValueError("decode_scene: pose_raw is given exactly for the posed representations")
+    _req(scale_raw, torch.float32, "scale_raw")
+    dev = raw.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    o = {"pts3d": torch.empty(n, H, W, 3, **f32), "metric_scaling_factor": torch.empty(1, 1, **f32)}
+    if posed:
+        _req(pose_raw, torch.float32, "pose_raw")
+        o.update(pts3d_cam=torch.empty(n, H, W, 3, **f32), cam_trans=torch.empty(n, 3, **f32), cam_quats=torch.empty(n, 4, **f32))
+    if rep == "raymap+depth":
+        o["ray_origins"] = torch.empty(n, H, W, 3, **f32)
+    if rep != "pointmap":
+        o.update(ray_directions=torch.empty(n, H, W, 3, **f32), depth_along_ray=torch.empty(n, H, W, 1, **f32))
+    if has_conf:
+        o["conf"] = torch.empty(n, H, W, **f32)
+    if has_mask:
+        o["non_ambiguous_mask_logits"] = torch.empty(n, H, W, **f32)
+        o["non_ambiguous_mask"] = torch.empty(n, H, W, device=dev, dtype=torch.bool)
+    spec = _lib.DecodeSpec(_lib.MA_REP[rep], int(has_conf), int(has_mask), _lib.MA_PTS[point_mode], int(use_factored),
+                           float(conf_vmin))
+
+    def ptr(key):
+        return o[key].data_ptr() if key in o else None
+
+    with launch("decode"):
+        check(
+            _lib.load().ma_decode_scene(
+                C.byref(spec), raw.data_ptr(), raw.stride(0), _ptr(pose_raw), scale_raw.data_ptr(), n, H * W, ptr("pts3d"),
+                ptr("pts3d_cam"), ptr("ray_directions"), ptr("ray_origins"), ptr("depth_along_ray"), ptr("conf"),
+                ptr("non_ambiguous_mask_logits"), ptr("non_ambiguous_mask"), ptr("cam_trans"), ptr("cam_quats"),
+                o["metric_scaling_factor"].data_ptr(), _stream(),
+            ),
+            "ma_decode_scene",
         )
     return o
 

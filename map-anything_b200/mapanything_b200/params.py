@@ -238,6 +238,15 @@ class DPTRegressionProcessor(_NoForward):
                                    nn.Conv2d(hidden_dims[1], output_dim, 1))
 
 
+class LinearFeature(_NoForward):
+    """pred_head_type "linear" (reference model.py:339-343, :363-365): 1x1 conv D -> output_dim * patch^2, then pixel shuffle."""
+
+    def __init__(self, input_feature_dim, output_dim, patch_size, **_):
+        super().__init__()
+        self.output_dim, self.patch_size = output_dim, patch_size
+        self.proj = nn.Conv2d(input_feature_dim, output_dim * patch_size * patch_size, 1)
+
+
 class ResConvBlock(_NoForward):
     def __init__(self, cin, cout):
         super().__init__()

@@ -1,9 +1,8 @@
 """Oracle MapAnything: fp32 PyTorch restatement of the reference model class (test infrastructure only).
 
 Follows /root/reference/mapanything/models/mapanything/model.py:
-  __init__                         :90-214, :224-318, :320-388, :390-588 (only the released configuration:
-                                    alternating attention + intermediate features, dpt+pose heads,
-                                    scene_rep_type "raydirs+depth+pose+confidence+mask")
+  __init__                         :90-214, :224-318, :320-388, :390-588 (alternating / global attention + intermediate
+                                    features; pred_head types linear / dpt / dpt+pose; every scene_rep_type of :407-587)
   _encode_n_views                  :622-645
   _compute_pose_..._in_ref_view    :647-751
   _encode_and_fuse_ray_dirs        :753-825
@@ -58,9 +57,12 @@ class MapAnythingOracle(nn.Module):
         assert self.info_sharing_return_type == "intermediate_features"
         if self.info_sharing_type == "global_attention":   # reference model.py:271-284 (gat_ifr_24_layers.yaml)
             info_sharing_config["module_args"].setdefault("attention_pattern", "global")
-        assert self.pred_head_type == "dpt+pose"
-        assert pred_head_config["adaptor_type"] == "raydirs+depth+pose+confidence+mask"
-        self.scene_rep_type = "raydirs+depth+pose+confidence+mask"
+        assert self.pred_head_type in ("linear", "dpt", "dpt+pose")  # reference model.py:339-372
+        self.scene_rep_type = pred_head_config["adaptor_type"]             # reference model.py:407-587
+        self.scene_rep, self.has_conf, self.has_mask = U.split_adaptor_type(self.scene_rep_type)
+        if "pose" in self.scene_rep:
+            assert self.pred_head_type == "dpt+pose", f"{self.scene_rep} can only be used with dpt + pose head."
+        self.dense_adaptor_cfg = pred_head_config.get("dpt_adaptor" if "pose" in self.scene_rep else "adaptor", {})
 
         enc_cfg = dict(encoder_config)
         enc_cfg.pop("uses_torch_hub", None)
@@ -90,15 +92,20 @@ class MapAnythingOracle(nn.Module):
         d = self.info_sharing.dim
         ph = pred_head_config
         ph["feature_head"]["patch_size"] = self.encoder.patch_size
-        ph["feature_head"]["input_feature_dims"] = [c] + [d] * 3 if self.use_encoder_features_for_dpt else [d] * 4
-        ph["regressor_head"]["input_feature_dim"] = ph["feature_head"]["feature_dim"]
-        ph["pose_head"]["patch_size"] = self.encoder.patch_size
-        ph["pose_head"]["input_feature_dim"] = d
+        if self.pred_head_type == "linear":
+            ph["feature_head"]["input_feature_dim"] = d
+            self.dense_head = U.LinearFeature(**ph["feature_head"])
+        else:
+            ph["feature_head"]["input_feature_dims"] = [c] + [d] * 3 if self.use_encoder_features_for_dpt else [d] * 4
+            ph["regressor_head"]["input_feature_dim"] = ph["feature_head"]["feature_dim"]
+            self.dpt_feature_head = U.DPTFeature(**ph["feature_head"])
+            self.dpt_regressor_head = U.DPTRegressionProcessor(**ph["regressor_head"])
+            self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)  # aliases, for key parity
+            if "pose" in self.pred_head_type:
+                ph["pose_head"]["patch_size"] = self.encoder.patch_size
+                ph["pose_head"]["input_feature_dim"] = d
+                self.pose_head = U.PoseHead(**ph["pose_head"])
         ph["scale_head"]["input_feature_dim"] = d
-        self.dpt_feature_head = U.DPTFeature(**ph["feature_head"])
-        self.dpt_regressor_head = U.DPTRegressionProcessor(**ph["regressor_head"])
-        self.dense_head = nn.Sequential(self.dpt_feature_head, self.dpt_regressor_head)  # aliases, for key parity
-        self.pose_head = U.PoseHead(**ph["pose_head"])
         self.scale_head = U.MLPHead(**ph["scale_head"])
 
     @property
@@ -245,12 +252,24 @@ class MapAnythingOracle(nn.Module):
         dense_raw, pose_raw = [], []
         for s in range(0, n, chunk):
             sl = [x[s : s + chunk] for x in dpt_in]
-            dense_raw.append(self.dpt_regressor_head(self.dpt_feature_head(sl), (h, w)))
-            pose_raw.append(self.pose_head(sl[-1]))
-        dense_raw, pose_raw = torch.cat(dense_raw, 0), torch.cat(pose_raw, 0)
+            if self.pred_head_type == "linear":  # reference model.py:1310-1320: the last features only
+                dense_raw.append(self.dense_head(sl[-1]))
+            else:
+                dense_raw.append(self.dpt_regressor_head(self.dpt_feature_head(sl), (h, w)))
+            if self.pred_head_type == "dpt+pose":
+                pose_raw.append(self.pose_head(sl[-1]))
+        dense_raw = torch.cat(dense_raw, 0)
+        pose_raw = torch.cat(pose_raw, 0) if pose_raw else None
+        scale = U.scale_adaptor_exp(self.scale_head(final_extra)).squeeze(-1)  # (B, 1)
+        if self.scene_rep_type != "raydirs+depth+pose+confidence+mask":
+            res = self._decode_other_scene_reps(dense_raw, pose_raw, scale, v, b)
+            if return_internals:
+                internals = {"enc": torch.cat(enc, 0), "fused": dpt_in[0], "tap1": dpt_in[1], "tap2": dpt_in[2],
+                             "final": dpt_in[3], "scale_token_feat": final_extra, "dense_raw": dense_raw, "pose_raw": pose_raw}
+                return res, internals
+            return res
         value, conf, mask, logits = U.dense_adaptor_raydirs_depth_conf_mask(dense_raw)
         pose = U.pose_adaptor_trans_quats(pose_raw)
-        scale = U.scale_adaptor_exp(self.scale_head(final_extra)).squeeze(-1)  # (B, 1)
 
         dense = value.permute(0, 2, 3, 1).contiguous()
         rays, depth = dense.split([3, 1], dim=-1)
@@ -276,6 +295,51 @@ class MapAnythingOracle(nn.Module):
             internals = {"enc": torch.cat(enc, 0), "fused": dpt_in[0], "tap1": dpt_in[1], "tap2": dpt_in[2],
                          "final": dpt_in[3], "scale_token_feat": final_extra, "dense_raw": dense_raw, "pose_raw": pose_raw}
             return res, internals
+        return res
+
+    def _decode_other_scene_reps(self, dense_raw, pose_raw, scale, v, b):
+        """reference model.py:1618-1907 for every scene_rep_type (the released one keeps its own code path above)."""
+        value, conf, mask, logits = U.dense_adaptor(dense_raw, self.scene_rep_type, self.dense_adaptor_cfg)
+        dense = value.permute(0, 2, 3, 1).contiguous()
+        s4 = scale.unsqueeze(-1).unsqueeze(-1)
+        rep = self.scene_rep
+        trans = quats = None
+        if "pose" in rep:
+            trans, quats = U.pose_adaptor_trans_quats(pose_raw).split([3, 4], dim=-1)
+        out = {}
+        if rep == "pointmap":
+            out["pts3d"] = dense * 1.0
+        elif rep == "raymap+depth":
+            origins, rays, depth = dense.split([3, 3, 1], dim=-1)
+            out.update(pts3d=origins + rays * depth, ray_origins=origins, ray_directions=rays, depth_along_ray=depth)
+        elif rep == "raydirs+depth+pose":
+            rays, depth = dense.split([3, 1], dim=-1)
+            out.update(pts3d=G.pointmap_from_rays_depth_pose(rays, depth, trans, quats), pts3d_cam=rays * depth,
+                       ray_directions=rays, depth_along_ray=depth)
+        elif rep == "campointmap+pose":
+            depth = torch.norm(dense, dim=-1, keepdim=True)
+            rays = dense / depth
+            out.update(pts3d=G.pointmap_from_rays_depth_pose(rays, depth, trans, quats), pts3d_cam=dense,
+                       ray_directions=rays, depth_along_ray=depth)
+        else:  # pointmap+raydirs+depth+pose
+            pts, rays, depth = dense.split([3, 3, 1], dim=-1)
+            if self.pred_head_config["adaptor_config"]["use_factored_predictions_for_global_pointmaps"]:
+                pts = G.pointmap_from_rays_depth_pose(rays, depth, trans, quats)
+            out.update(pts3d=pts, pts3d_cam=rays * depth, ray_directions=rays, depth_along_ray=depth)
+        res = []
+        for i in range(v):
+            sl = slice(i * b, (i + 1) * b)
+            d = {"metric_scaling_factor": scale}
+            for k, t in out.items():
+                d[k] = t[sl] if k == "ray_directions" else t[sl] * s4
+            if trans is not None:
+                d["cam_trans"], d["cam_quats"] = trans[sl] * scale, quats[sl]
+            if conf is not None:
+                d["conf"] = conf.permute(0, 2, 3, 1).squeeze(-1).contiguous()[sl]
+            if mask is not None:
+                d["non_ambiguous_mask"] = mask.permute(0, 2, 3, 1).squeeze(-1).contiguous()[sl] > 0.5
+                d["non_ambiguous_mask_logits"] = logits.permute(0, 2, 3, 1).squeeze(-1).contiguous()[sl]
+            res.append(d)
         return res
 
     # ---------------------------------------------------------------------------------- infer

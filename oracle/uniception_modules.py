@@ -368,6 +368,85 @@ def dense_adaptor_raydirs_depth_conf_mask(x: torch.Tensor):
     return torch.cat([ray, depth], dim=1), conf, torch.sigmoid(logits), logits
 
 
+# ------------------------------------------------------------------------------------------------
+# The other dense adaptors MapAnything can be configured with (reference model.py:407-587; YAMLs
+# configs/model/pred_head/adaptor_config/{pointmap_confidence*, campointmap_pose_*, pointmap_*raydirs_depth_pose_*}.yaml).
+# [UPSTREAM-RECALL] like everything in this file: the activations follow the published DUSt3R / MoGe forms the uniception
+# adaptors wrap -- "exp": unit direction x expm1(norm) (DUSt3R reg_dense_depth), "z_exp": (x*z, y*z, z) with z = exp(raw z)
+# (MoGe), "linear": identity; depth "exp" = exp; confidence "exp" = vmin + exp; mask = sigmoid(logits).
+# Channel order of the head output: [scene representation | confidence logit (if any) | mask logit (if any)].
+# ------------------------------------------------------------------------------------------------
+SCENE_REP_CHANNELS = {"pointmap": 3, "raymap+depth": 7, "raydirs+depth+pose": 4, "campointmap+pose": 3,
+                      "pointmap+raydirs+depth+pose": 7}
+
+
+def split_adaptor_type(adaptor_type: str):
+    """'pointmap+raydirs+depth+pose+confidence+mask' -> ('pointmap+raydirs+depth+pose', has_conf, has_mask)."""
+    parts = adaptor_type.split("+")
+    has_mask = parts[-1] == "mask"
+    if has_mask:
+        parts = parts[:-1]
+    has_conf = parts[-1] == "confidence"
+    if has_conf:
+        parts = parts[:-1]
+    rep = "+".join(parts)
+    if rep not in SCENE_REP_CHANNELS:
+        raise ValueError(f"Invalid adaptor_type: {adaptor_type}")
+    return rep, has_conf, has_mask
+
+
+def point_activation(xyz: torch.Tensor, mode: str) -> torch.Tensor:
+    """(n, 3, H, W) raw -> points."""
+    if mode == "linear":
+        return xyz
+    if mode == "exp":
+        d = xyz.norm(dim=1, keepdim=True)
+        return xyz / d.clamp(min=1e-8) * torch.expm1(d)
+    if mode == "z_exp":
+        z = torch.exp(xyz[:, 2:3])
+        return torch.cat([xyz[:, 0:2] * z, z], dim=1)
+    raise ValueError(f"unsupported pointmap_mode {mode}")
+
+
+def _unit(x: torch.Tensor) -> torch.Tensor:
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def dense_adaptor(x: torch.Tensor, adaptor_type: str, cfg: dict):
+    """x (n, C, H, W) head output -> (value (n, rep_channels, H, W), confidence | None, mask | None, logits | None)."""
+    rep, has_conf, has_mask = split_adaptor_type(adaptor_type)
+    c = SCENE_REP_CHANNELS[rep]
+    if rep in ("pointmap", "campointmap+pose"):
+        value = point_activation(x[:, 0:3], cfg.get("pointmap_mode", "exp"))
+    elif rep == "raymap+depth":
+        value = torch.cat([x[:, 0:3], _unit(x[:, 3:6]), torch.exp(x[:, 6:7])], dim=1)
+    elif rep == "raydirs+depth+pose":
+        value = torch.cat([_unit(x[:, 0:3]), torch.exp(x[:, 3:4]).clamp(min=0.0)], dim=1)
+    else:  # pointmap+raydirs+depth+pose
+        value = torch.cat([point_activation(x[:, 0:3], cfg.get("pointmap_mode", "exp")), _unit(x[:, 3:6]),
+                           torch.exp(x[:, 6:7]).clamp(min=0.0)], dim=1)
+    conf = mask = logits = None
+    if has_conf:
+        conf = float(cfg.get("confidence_vmin", 1)) + torch.exp(x[:, c:c + 1])
+        c += 1
+    if has_mask:
+        logits = x[:, c:c + 1]
+        mask = torch.sigmoid(logits)
+    return value, conf, mask, logits
+
+
+class LinearFeature(nn.Module):
+    """pred_head_type 'linear' (reference model.py:339-343, :363-365): 1x1 conv D -> output_dim * patch^2, pixel shuffle."""
+
+    def __init__(self, input_feature_dim: int, output_dim: int, patch_size: int, **_):
+        super().__init__()
+        self.patch_size = patch_size
+        self.proj = nn.Conv2d(input_feature_dim, output_dim * patch_size * patch_size, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F.pixel_shuffle(self.proj(x), self.patch_size)
+
+
 def pose_adaptor_trans_quats(x: torch.Tensor) -> torch.Tensor:
     """(n, 7) -> [trans (linear) | quats normalised]."""
     q = x[:, 3:7]
