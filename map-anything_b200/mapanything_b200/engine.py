@@ -765,10 +765,10 @@ class Engine:
 
     def dpt_and_pose(self, taps4: List[torch.Tensor], V: int, hp: int, wp: int, H: int, W: int,
                      final32: Optional[torch.Tensor] = None):
-        """taps4: 4 x bf16 [V*N][C_i] (+ final32 fp32 [V*N][D] for the pose / linear head; defaults to taps4[3] upcast)
+        """taps4: 4 x bf16 [V*N][C_i] (+ final32 fp32 [V*N][D] for the pose / linear head; defaults to taps4[-1] upcast)
         -> raw dense fp32 [V*H*W][raw_ld] (head_out_dim used), pose_raw fp32 [V][7] (None without a pose head)."""
         if final32 is None:
-            final32 = taps4[3].float()
+            final32 = taps4[-1].float()
         N = hp * wp
         raw = self._empty(V * H * W, self.raw_ld, dtype=torch.float32)
         if self.head_type == "linear":

@@ -114,15 +114,30 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
         self.custom_positional_encoding = None
         cfg["module_args"]["input_embed_dim"] = self.encoder.enc_embed_dim
         cfg["module_args"]["custom_positional_encoding"] = None
-        if (self.info_sharing_return_type != "intermediate_features"
-                or self.info_sharing_type not in ("alternating_attention", "global_attention")):
+        if self.info_sharing_type == "cross_attention":
             raise ValueError(
-                f"mapanything_b200 implements info_sharing model_type 'alternating_attention' / 'global_attention' with "
-                f"model_return_type='intermediate_features' (got {self.info_sharing_type!r}, {self.info_sharing_return_type!r}); "
-                f"'cross_attention' is the two-view DUSt3R decoder of other model configs"
+                "info_sharing model_type 'cross_attention' (the two-view CroCo / DUSt3R decoder) is not implemented: the only "
+                "reference YAML that selects it (configs/model/info_sharing/cat_ifr_dust3r.yaml) sets a string "
+                "custom_positional_encoding, which the reference's MapAnything class rejects as well (model.py:244-250)")
+        if self.info_sharing_type not in ("alternating_attention", "global_attention"):
+            raise ValueError(
+                f"Invalid info_sharing_type: {self.info_sharing_type}. Valid options: ['cross_attention', 'global_attention', 'alternating_attention']"
+            )
+        if self.info_sharing_return_type not in ("no_intermediate_features", "intermediate_features"):
+            raise ValueError(
+                f"Invalid info_sharing_return_type: {self.info_sharing_return_type}. Valid options: ['no_intermediate_features', 'intermediate_features']"
             )
         if self.info_sharing_type == "global_attention":   # reference model.py:271-284, gat_ifr_24_layers.yaml
             cfg["module_args"].setdefault("attention_pattern", "global")
+        if self.info_sharing_return_type == "no_intermediate_features":
+            # reference model.py:266-285: only the normalised last-layer features come back, which only the linear head can
+            # consume (the DPT branches of forward read intermediate features the module does not return)
+            if self.pred_head_type != "linear":
+                raise ValueError("model_return_type 'no_intermediate_features' feeds pred_head_type 'linear' only "
+                                 "(the DPT heads need the intermediate features)")
+            cfg["module_args"].pop("indices", None)
+            self.info_sharing = P.AlternatingAttentionIFR(indices=(), **cfg["module_args"])
+            return
         self.info_sharing = P.AlternatingAttentionIFR(**cfg["module_args"])
         # reference model.py:304-313: 2 taps -> the DPT also takes the (fused) encoder features; 3 taps -> it does not
         if len(self.info_sharing.indices) == 2:
@@ -491,7 +506,10 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
                     self._fuse_geometric_inputs(eng, feat, views, b, N, plan, comm, gates)
                 fused = eng.fuse_norm(feat)                   # bf16 [V*N][C]   fusion LayerNorm (DPT tap 0)
                 taps, final, final32 = eng.info_sharing(fused, num_views, N, plan=plan, comm=comm)
-                dpt_in = [fused, taps[0], taps[1], final] if self.use_encoder_features_for_dpt else [*taps, final]
+                if self.pred_head_type == "linear":   # reference model.py:1541-1545: the final features only
+                    dpt_in = [final]
+                else:
+                    dpt_in = [fused, taps[0], taps[1], final] if self.use_encoder_features_for_dpt else [*taps, final]
                 raw, pose_raw = eng.dpt_and_pose(dpt_in, num_views, hp, wp, height, width, final32=final32[:num_views * N])
                 if plan is None:
                     scale_raw = eng.scale_head(final32[num_views * N:])

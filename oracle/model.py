@@ -54,7 +54,7 @@ class MapAnythingOracle(nn.Module):
         self.info_sharing_return_type = info_sharing_config["model_return_type"]
         self.pred_head_type = pred_head_config["type"]
         assert self.info_sharing_type in ("alternating_attention", "global_attention")
-        assert self.info_sharing_return_type == "intermediate_features"
+        assert self.info_sharing_return_type in ("intermediate_features", "no_intermediate_features")
         if self.info_sharing_type == "global_attention":   # reference model.py:271-284 (gat_ifr_24_layers.yaml)
             info_sharing_config["module_args"].setdefault("attention_pattern", "global")
         assert self.pred_head_type in ("linear", "dpt", "dpt+pose")  # reference model.py:339-372
@@ -85,9 +85,15 @@ class MapAnythingOracle(nn.Module):
 
         info_sharing_config["module_args"]["input_embed_dim"] = c
         info_sharing_config["module_args"]["custom_positional_encoding"] = None
-        self.info_sharing = U.MultiViewAlternatingAttentionTransformerIFR(**info_sharing_config["module_args"])
-        assert len(self.info_sharing.indices) in (2, 3)  # reference model.py:304-313
-        self.use_encoder_features_for_dpt = len(self.info_sharing.indices) == 2
+        if self.info_sharing_return_type == "no_intermediate_features":  # reference model.py:266-285: final features only
+            assert self.pred_head_type == "linear"
+            info_sharing_config["module_args"].pop("indices", None)
+            self.info_sharing = U.MultiViewAlternatingAttentionTransformerIFR(indices=(), **info_sharing_config["module_args"])
+            self.use_encoder_features_for_dpt = False
+        else:
+            self.info_sharing = U.MultiViewAlternatingAttentionTransformerIFR(**info_sharing_config["module_args"])
+            assert len(self.info_sharing.indices) in (2, 3)  # reference model.py:304-313
+            self.use_encoder_features_for_dpt = len(self.info_sharing.indices) == 2
 
         d = self.info_sharing.dim
         ph = pred_head_config
@@ -242,7 +248,9 @@ class MapAnythingOracle(nn.Module):
         final_feats = [f.float() for f in final_feats]
         final_extra = final_extra.float()
         inter = [([f.float() for f in fs], ex) for fs, ex in inter]
-        if self.use_encoder_features_for_dpt:  # reference model.py:1549-1572
+        if self.pred_head_type == "linear":    # reference model.py:1541-1545
+            dpt_in = [torch.cat(final_feats, 0)] * 4
+        elif self.use_encoder_features_for_dpt:  # reference model.py:1549-1572
             dpt_in = [torch.cat(fused, 0), torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(final_feats, 0)]
         else:
             dpt_in = [torch.cat(inter[0][0], 0), torch.cat(inter[1][0], 0), torch.cat(inter[2][0], 0), torch.cat(final_feats, 0)]

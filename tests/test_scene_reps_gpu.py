@@ -179,6 +179,24 @@ def test_linear_head_matches_oracle():
     _check_model(_tiny_with_head(adaptor_config="pointmap_confidence_mask_scale", head_type="linear"), "linear head + pointmap")
 
 
+def test_linear_head_without_intermediate_features():
+    """model_return_type "no_intermediate_features" (reference model.py:266-285): the transformer returns its final features
+    only, which the linear head consumes; the DPT heads cannot be built on it."""
+    from mapanything_b200 import MapAnything
+
+    cfg = _tiny_with_head(adaptor_config="pointmap_confidence_mask_scale", head_type="linear")
+    cfg["info_sharing_config"]["model_return_type"] = "no_intermediate_features"
+    _check_model(cfg, "linear head, no intermediate features")
+    cfg = _tiny_with_head(adaptor_config="pointmap_confidence_mask_scale")
+    cfg["info_sharing_config"]["model_return_type"] = "no_intermediate_features"
+    with pytest.raises(ValueError):
+        MapAnything(**cfg)
+    cfg = _tiny_with_head(adaptor_config="pointmap_confidence_mask_scale")
+    cfg["info_sharing_config"]["model_type"] = "cross_attention"
+    with pytest.raises(ValueError):
+        MapAnything(**cfg)
+
+
 def test_raymap_depth_model_matches_oracle():
     """No YAML of the reference selects raymap+depth; the model class accepts it (model.py:423-441)."""
     from oracle.config import tiny_config
