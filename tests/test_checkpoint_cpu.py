@@ -61,3 +61,69 @@ def test_verify_checkpoint_tool(tmp_path):
     r = subprocess.run([sys.executable, str(ROOT / "tools" / "verify_checkpoint.py"), str(tmp_path / "other.pth")],
                        capture_output=True, text=True)
     assert r.returncode == 0 and "DIFFERS" in r.stdout and "[128, 32]" in r.stdout, r.stdout[-2000:]
+
+
+def _tiny_variant(**kw):
+    from mapanything_b200 import MapAnything, pred_head_variant_config, tiny_config
+
+    cfg = tiny_config()
+    cfg["pred_head_config"] = pred_head_variant_config(**kw)
+    torch.manual_seed(0)
+    return MapAnything(**cfg), cfg
+
+
+def test_other_heads_and_scene_representations_construct_on_cpu():
+    """pred_head_type linear / dpt / dpt+pose and the adaptor YAMLs of the reference (model.py:320-588): module trees, key
+    prefixes and the config mutations the reference constructor performs; invalid combinations raise like the reference."""
+    import pytest
+
+    from mapanything_b200 import MapAnything, pred_head_variant_config, tiny_config
+    from mapanything_b200.config import ADAPTOR_CONFIGS
+
+    for name, ac in ADAPTOR_CONFIGS.items():
+        m, cfg = _tiny_variant(adaptor_config=name)
+        keys = set(m.state_dict())
+        posed = "pose" in ac["scene_rep_type"]
+        assert any(k.startswith("pose_head.") for k in keys) == posed, name
+        assert m.pred_head_type == ("dpt+pose" if posed else "dpt") and m.scene_rep_type == ac["type"]
+        assert m.state_dict()["dpt_regressor_head.conv2.2.weight"].shape[0] == ac["input_dim"]
+        assert any(k.startswith("dense_head.1.") for k in keys) and any(k.startswith("scale_head.") for k in keys)
+        # the constructor wrote the dependent sizes into the caller's dict (reference model.py:338-352)
+        assert m.pred_head_config["regressor_head"]["input_feature_dim"] == 256
+        assert m.pred_head_config["scale_head"]["input_feature_dim"] == m.info_sharing.dim
+    m, _ = _tiny_variant(adaptor_config="pointmap_confidence_mask_scale", head_type="linear")
+    assert m.state_dict()["dense_head.proj.weight"].shape == (5 * 14 * 14, m.info_sharing.dim, 1, 1)
+    assert not any(k.startswith(("dpt_", "pose_head.")) for k in m.state_dict())
+    assert m.pred_head_config["feature_head"]["input_feature_dim"] == m.info_sharing.dim
+    # all twenty adaptor types parse; the channel count must match the head
+    for rep, ch in (("pointmap", 3), ("raymap+depth", 7)):
+        for suffix, extra in (("", 0), ("+confidence", 1), ("+mask", 1), ("+confidence+mask", 2)):
+            cfg = tiny_config()
+            cfg["pred_head_config"].update({"type": "dpt", "adaptor_type": rep + suffix, "adaptor": {"name": rep + suffix}})
+            cfg["pred_head_config"]["regressor_head"]["output_dim"] = ch + extra
+            assert MapAnything(**cfg).scene_rep_type == rep + suffix
+    cfg = tiny_config()
+    cfg["pred_head_config"]["adaptor_type"] = "voxels"
+    with pytest.raises(ValueError, match="Invalid adaptor_type"):
+        MapAnything(**cfg)
+    cfg = tiny_config()
+    cfg["pred_head_config"] = pred_head_variant_config("campointmap_pose_confidence_mask_scale", head_type="dpt")
+    with pytest.raises(AssertionError, match="dpt \\+ pose head"):
+        MapAnything(**cfg)
+    cfg = tiny_config()
+    cfg["pred_head_config"]["dpt_adaptor"]["depth_mode"] = "square"   # not a value the fused decode implements
+    with pytest.raises(ValueError, match="fused decode"):
+        MapAnything(**cfg)
+
+
+def test_verify_checkpoint_tool_other_heads(tmp_path):
+    """Without config.json the tool infers the head type and an adaptor type that fits the channel count."""
+    for i, kw in enumerate((dict(adaptor_config="pointmap_confidence_mask_scale", head_type="linear"),
+                            dict(adaptor_config="pointmap_confidence_mask_scale"),
+                            dict(adaptor_config="pointmap_raydirs_depth_pose_confidence_mask_scale"))):
+        m, _ = _tiny_variant(**kw)
+        path = tmp_path / f"v{i}.pth"
+        torch.save({"model": m.state_dict()}, path)
+        r = subprocess.run([sys.executable, str(ROOT / "tools" / "verify_checkpoint.py"), str(path)], capture_output=True, text=True)
+        assert r.returncode == 0 and "strict load OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+        assert f"head.type                          {m.pred_head_type}" in r.stdout, r.stdout[-3000:]

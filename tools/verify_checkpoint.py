@@ -109,7 +109,33 @@ def infer(shapes):
         idx = sorted({int(k.split(".")[2]) for k in shapes if re.match(rf"{enc}\.encoder\.\d+\.weight", k)})
         f[f"{enc}.dims"] = [g(f"{enc}.encoder.{i}.weight", (0,))[0] for i in idx]
     f["dense_head_aliases"] = any(k.startswith("dense_head.") for k in shapes)
+    # prediction head type (reference model.py:339-388) and the adaptor types its channel count admits (model.py:407-587)
+    linear = "dense_head.proj.weight" in shapes
+    posed = any(k.startswith("pose_head.") for k in shapes)
+    f["head.type"] = "linear" if linear else ("dpt+pose" if posed else "dpt")
+    if linear:
+        p2 = max(1, f["encoder.patch_size"]) ** 2
+        f["head.output_dim"] = g("dense_head.proj.weight", (0,))[0] // p2
+    else:
+        f["head.output_dim"] = f["regressor.output_dim"]
+    f["head.adaptor_candidates"] = adaptor_candidates(f["head.output_dim"], posed)
     return f
+
+
+REP_CHANNELS = {"pointmap": 3, "raymap+depth": 7, "raydirs+depth+pose": 4, "campointmap+pose": 3, "pointmap+raydirs+depth+pose": 7}
+
+
+def adaptor_candidates(channels, posed):
+    """adaptor types whose channel count (representation + confidence + mask) equals the dense head's output width; the posed
+    representations need the pose head.  The released type first."""
+    out = []
+    for rep, c in REP_CHANNELS.items():
+        if ("pose" in rep) != posed:
+            continue
+        for suffix, extra in (("+confidence+mask", 2), ("+confidence", 1), ("+mask", 1), ("", 0)):
+            if c + extra == channels:
+                out.append(rep + suffix)
+    return sorted(out, key=lambda t: t != "raydirs+depth+pose+confidence+mask")
 
 
 def config_from(facts, cfg_json):
@@ -128,8 +154,26 @@ def config_from(facts, cfg_json):
     cfg["encoder_config"]["vit_kwargs"] = {"embed_dim": facts["encoder.embed_dim"], "depth": facts["encoder.depth"],
                                            "num_heads": facts["encoder.embed_dim"] // 64,
                                            "img_size": int(round((facts["encoder.pos_embed_tokens"] - 1) ** 0.5)) * facts["encoder.patch_size"]}
-    cfg["pred_head_config"]["regressor_head"]["hidden_dims"] = facts["regressor.hidden_dims"]
-    cfg["pred_head_config"]["pose_head"]["num_resconv_block"] = facts["pose.num_resconv_block"]
+    cand = facts["head.adaptor_candidates"]
+    if facts["head.type"] != "dpt+pose" or (cand and cand[0] != "raydirs+depth+pose+confidence+mask"):
+        # another head / scene representation: the first adaptor type the channel count admits (tensors cannot tell e.g.
+        # "+confidence" from "+mask"; both build the same module tree)
+        from mapanything_b200.config import ADAPTOR_CONFIGS, pred_head_variant_config
+
+        if not cand:
+            raise SystemExit(f"no adaptor type consumes {facts['head.output_dim']} channels with head {facts['head.type']}")
+        rep = cand[0].replace("+confidence", "").replace("+mask", "")
+        yaml = next(k for k, v in ADAPTOR_CONFIGS.items() if v["scene_rep_type"] == rep) if rep != "raymap+depth" else None
+        if yaml is not None:
+            cfg["pred_head_config"] = pred_head_variant_config(yaml, head_type=facts["head.type"], adaptor_type=cand[0])
+        else:
+            ph = cfg["pred_head_config"]
+            ph.update({"type": facts["head.type"], "adaptor_type": cand[0], "adaptor": {"name": cand[0]}})
+            ph["regressor_head"]["output_dim"] = facts["head.output_dim"]
+    if facts["head.type"] != "linear":
+        cfg["pred_head_config"]["regressor_head"]["hidden_dims"] = facts["regressor.hidden_dims"]
+    if facts["head.type"] == "dpt+pose":
+        cfg["pred_head_config"]["pose_head"]["num_resconv_block"] = facts["pose.num_resconv_block"]
     n_lin = len(facts["scale.linear_indices"])
     if n_lin:
         cfg["pred_head_config"]["scale_head"].update({"num_mlp_layers": n_lin - 1, "hidden_dim": facts["scale.widths"][0][0]})
@@ -141,7 +185,7 @@ ASSUMED = {
     "info.qk_norm": False, "info.qkv_bias": True, "info.persistent_view_pe": [], "info.other_block_types": [],
     "dpt.feature_dim": 256, "dpt.layer_dims": [96, 192, 384, 768], "dpt.layer_rn_bias": False, "dpt.refinenet4_has_rcu1": True,
     "regressor.hidden_dims": [128, 128], "regressor.output_dim": 6, "pose.num_resconv_block": 2, "pose.skip_projection": False,
-    "pose.more_mlps_linears": 2, "pose.rot_dim": 4, "ray_dirs_encoder.dims": [768, 1024], "depth_encoder.dims": [768, 1024],
+    "pose.more_mlps_linears": 2, "pose.rot_dim": 4, "head.type": "dpt+pose", "ray_dirs_encoder.dims": [768, 1024], "depth_encoder.dims": [768, 1024],
 }
 
 UNDECIDABLE = [
@@ -150,6 +194,8 @@ UNDECIDABLE = [
     ("ResConvBlock: relu(skip + conv3) vs skip + relu(conv3)", "pose_head final_relu_after_skip (default True)"),
     ("MLPHead activation", "scale_head activation (default 'relu')"),
     ("depth adaptor exp vs expm1, confidence 1 + exp", "adaptor config: depth_mode / confidence_type (only 'exp' implemented)"),
+    ("which of head.adaptor_candidates the model was trained with", "pred_head_config adaptor_type (config.json carries it)"),
+    ("point activation of pointmap / campointmap representations", "adaptor pointmap_mode: 'exp' | 'z_exp' | 'linear'"),
     ("entropy-scaling constant", "entropy_scaling_ref_len (only used when use_entropy_scaling)"),
     ("GELU (erf) in MLPs, LayerNorm eps 1e-6", "fixed; DINOv2 / timm convention"),
 ]
