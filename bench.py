@@ -563,7 +563,7 @@ def run_ours(args):
         strong = strong_scaling_record(model, dev, rank, world, timed, peak_tf)
         model.enable_view_sharding(views_per_rank=[V] * world)
     cpu = eager = None
-    if rank == 0 and world == 1:  # host + GPU-library baselines are reported at N = 1 only
+    if rank == 0 and world == 1 and not args.no_cpu:  # host + GPU-library baselines are reported at N = 1 only
         oracle_model = build_oracle()
         cpu = cpu_baseline(V, oracle_model, args.multimodal)
         if not args.no_eager:
@@ -650,6 +650,7 @@ def main():
     ap.add_argument("--multi", default="shard", choices=["shard", "replicas"],
                     help="N > 1: one scene of views*N views sharded by view (default) or N independent scenes")
     ap.add_argument("--no-eager", action="store_true", help="skip the GPU-eager (PyTorch library) baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="A/B runs only: skip the CPU baseline leg too (cpu_baseline: null)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the fixed 100-view strong-scaling record")
     ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")
     args = ap.parse_args()

@@ -11,12 +11,50 @@
 //   warp 1 (leader)    : MMA issuer; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
 //   warp 2 (both)      : TMEM allocator (cta_group::2)
 //   warps 4..11 (both) : epilogue for the CTA's own 128 rows; "accumulator drained" arrives on the leader's barrier
+//
+// Stream-K tail (in-place fp32 residual GEMMs, i.e. the reduce-add epilogue, K >= 2048): the tiles of the last, partially
+// filled wave are not handed out whole.  Their K blocks form one flattened range that is cut into equal contiguous pieces,
+// one per cluster, so every cluster works until (nearly) the same K block: 10960 x 1024 x 4096 on 74 clusters is 172 tiles =
+// 2 full waves + 24 tiles; whole tiles cost 3 x 64 K blocks per cluster, stream-K 2 x 64 + 21.  A piece that covers part of
+// a tile's K range is an ordinary work unit (tile, k0, k1): its partial product leaves through the same bulk tensor
+// REDUCE-ADD as a whole tile (x += gamma * acc; the unit that holds K block 0 also adds gamma * bias), so no workspace and
+// no fix-up pass exist.  The fp32 adds of one element's two or three partial products reach the L2 in arbitrary order: such
+// a GEMM is reproducible to fp32 rounding of the sum (~1e-7 relative), not bit for bit (ma_set_stream_k(0) restores that).
 #include "gemm_common.cuh"
 
 namespace ma {
 
+// Work units of one cluster: whole tiles t = cluster, cluster + W, ... below sk_lo, then the cluster's piece of the
+// flattened (tile, K block) range of the tiles [sk_lo, total_tiles).  Every warp role walks the same sequence.
+struct UnitWalk {
+  int t, W, sk_lo, kblocks;
+  int pos, end;  // stream-K piece, in K blocks from the start of tile sk_lo
+  __device__ UnitWalk(int cluster, int W_, int total_tiles, int sk_lo_, int kblocks_) : t(cluster), W(W_), sk_lo(sk_lo_), kblocks(kblocks_) {
+    const int total = (total_tiles - sk_lo) * kblocks;
+    const int piece = (total + W - 1) / W;
+    pos = cluster * piece;
+    end = pos + piece < total ? pos + piece : total;
+  }
+  __device__ bool next(int& tile, int& k0, int& k1) {
+    if (t < sk_lo) {
+      tile = t; k0 = 0; k1 = kblocks;
+      t += W;
+      return true;
+    }
+    if (pos >= end) return false;
+    const int j = pos / kblocks;
+    tile = sk_lo + j;
+    k0 = pos - j * kblocks;
+    k1 = k0 + (end - pos) < kblocks ? k0 + (end - pos) : kblocks;
+    pos += k1 - k0;
+    return true;
+  }
+};
+
 constexpr int G2_THREADS = 384;
 constexpr int G2_EPI_WARPS = 8;
+constexpr int G2_SK_MIN_KBLOCKS = 32;  // stream-K only for K >= 2048 (fc2 of the transformer blocks)
+constexpr int G2_SK_MIN_PIECE = 8;     // ... and pieces of at least 8 K blocks
 
 template <int BN>
 struct Gemm2Cfg {
@@ -34,7 +72,7 @@ template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ CUtensorMap tmap_out, const ma_gemm_epilogue ep, const int M, const int N, const int K,
-                      const ConvGeom cg, const int epi_mode) {
+                      const ConvGeom cg, const int epi_mode, const int sk_lo) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -90,7 +128,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      UnitWalk walk(cluster_id, num_clusters, total_tiles, sk_lo, kblocks);
+      int t, k0, k1;
+      while (walk.next(t, k0, k1)) {
         int tm2, tn;
         raster_tile(t, tiles_n, num_clusters, tm2, tn);
         const int tm = tm2 * 2 + static_cast<int>(cta);  // this CTA's 128-row tile
@@ -113,7 +153,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           }
         } else {
           const int m0 = tm * GEMM_BM;
-          for (int kb = 0; kb < kblocks; ++kb) {
+          for (int kb = k0; kb < k1; ++kb) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
             if (cta == 0) mbar_arrive_expect_tx(&bar_full[stage], 2u * Cfg::STAGE_BYTES);
             tma_load_2d_2sm(sA + stage * Cfg::A_BYTES, &tmap_x, &bar_full[stage], kb * GEMM_BK, m0);
@@ -128,14 +168,15 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+      UnitWalk walk(cluster_id, num_clusters, total_tiles, sk_lo, kblocks);
+      int t, k0, k1;
+      for (int it = 0; walk.next(t, k0, k1); ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait_cluster(&bar_tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = k0; kb < k1; ++kb) {
           mbar_wait(&bar_full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
@@ -144,7 +185,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb != k0 || k != 0) ? 1u : 0u);
           }
           umma_commit_2sm(&bar_empty[stage], 0x3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -166,8 +207,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       for (int i = threadIdx.x - 128; i < 8 * BN; i += G2_EPI_WARPS * 32) hw[i] = __ldg(ep.head_w + i);
       named_bar_sync(1, G2_EPI_WARPS * 32);
     }
-    int it = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+    UnitWalk walk(cluster_id, num_clusters, total_tiles, sk_lo, kblocks);
+    int t, k0, k1;
+    for (int it = 0; walk.next(t, k0, k1); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       int tm2, tn;
@@ -200,7 +242,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (head) {
           epilogue_head_chunk(ep, v, col0, BN, hw, hsum);
         } else if (epi_mode) {  // warp-uniform: asynchronous bulk tensor store / reduce-add of the 32 x 32 chunk
-          if (col0 < N) epilogue_tma_chunk(&tmap_out, epi_mode, ep, v, tm * GEMM_BM + quarter * 32, col0, epi_stage, lane);
+          // a stream-K unit that does not hold K block 0 contributes gamma * partial product only (no bias)
+          if (col0 < N) epilogue_tma_chunk(&tmap_out, epi_mode, ep, v, tm * GEMM_BM + quarter * 32, col0, epi_stage, lane, k0 == 0);
         } else if (row_ok && col0 < N) {
           epilogue_store_chunk(ep, v, m, col0, N);
         }
@@ -251,9 +294,21 @@ static int launch_gemm2(const CUtensorMap& tx, const CUtensorMap& tw, const CUte
   const int rows_tiles = cg.mode ? (M / (cg.H * cg.W)) * cg.tiles_x * cg.tiles_y : (M + GEMM_BM - 1) / GEMM_BM;
   const int tiles = ((rows_tiles + 1) / 2) * ((N + BN - 1) / BN);
   const int max_clusters = device_sm_count() / 2;
-  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  int clusters = tiles < max_clusters ? tiles : max_clusters;
+  // stream-K over the last partial wave: only where a partial product can leave as a reduce-add (epi_mode 2, no activation)
+  // and the K range is long enough for a piece to amortise its own epilogue
+  int sk_lo = tiles;
+  const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+  if (stream_k_enabled() && epi_mode == 2 && !cg.mode && ep.act == MA_ACT_NONE && kblocks >= G2_SK_MIN_KBLOCKS &&
+      tiles % max_clusters != 0) {
+    const int tail = tiles % max_clusters;
+    if ((tail * kblocks + max_clusters - 1) / max_clusters >= G2_SK_MIN_PIECE) {
+      sk_lo = tiles - tail;
+      clusters = max_clusters;
+    }
+  }
   MA_CHECK_CUDA(launch_kernel(gemm_bf16_2cta_kernel<BN>, dim3(2 * clusters), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, pdl_enabled(), tx,
-                              tw, tout, ep, M, N, K, cg, epi_mode));
+                              tw, tout, ep, M, N, K, cg, epi_mode, sk_lo));
   return MA_OK;
 }
 

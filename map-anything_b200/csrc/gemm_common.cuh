@@ -230,11 +230,12 @@ __device__ __forceinline__ void epilogue_head_chunk(const ma_gemm_epilogue& ep, 
 constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;
 
 __device__ __forceinline__ void epilogue_tma_chunk(const CUtensorMap* tmap_out, int mode, const ma_gemm_epilogue& ep,
-                                                   const uint32_t (&acc)[32], int row0, int col0, uint8_t* stage, int lane) {
+                                                   const uint32_t (&acc)[32], int row0, int col0, uint8_t* stage, int lane,
+                                                   bool with_bias = true) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (ep.bias) {
+  if (ep.bias && with_bias) {
     const float4* b4 = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

@@ -94,6 +94,17 @@ bool pdl_enabled() {
   return mode != 0;
 }
 
+static int g_stream_k_mode = -1;
+
+bool stream_k_enabled() {
+  int& mode = g_stream_k_mode;
+  if (mode < 0) {
+    const char* e = getenv("MA_GEMM_STREAMK");
+    mode = e ? (e[0] != '0') : 1;
+  }
+  return mode != 0;
+}
+
 int current_device() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MA_MAX_DEVICES) return 0;
@@ -120,6 +131,12 @@ extern "C" int ma_abi_version(void) { return MA_ABI_VERSION; }
 extern "C" int ma_set_pdl(int enabled) {
   const int before = ma::pdl_enabled() ? 1 : 0;
   if (enabled >= 0) ma::g_pdl_mode = enabled ? 1 : 0;
+  return before;
+}
+
+extern "C" int ma_set_stream_k(int enabled) {
+  const int before = ma::stream_k_enabled() ? 1 : 0;
+  if (enabled >= 0) ma::g_stream_k_mode = enabled ? 1 : 0;
   return before;
 }
 

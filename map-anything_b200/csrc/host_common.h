@@ -48,6 +48,7 @@ int device_sm_count();
 
 // Programmatic dependent launch of the chained hot-path kernels (GEMM, attention, LayerNorm): MA_PDL=0/1, see ptx.cuh.
 bool pdl_enabled();
+bool stream_k_enabled();
 
 // cudaLaunchKernelEx wrapper; with pdl = true the kernel may start before the previous kernel of the stream has
 // completed, and MUST execute pdl_wait() before its first global memory access.

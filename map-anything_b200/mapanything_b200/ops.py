@@ -73,6 +73,12 @@ def set_pdl(enabled: Optional[bool]) -> bool:
     return bool(_lib.load().ma_set_pdl(-1 if enabled is None else int(bool(enabled))))
 
 
+def set_stream_k(enabled: Optional[bool]) -> bool:
+    """Stream-K tail of the in-place fp32 residual GEMMs (include/mapanything_b200.h: ma_set_stream_k): faster, reproducible
+    to fp32 rounding instead of bit for bit.  None queries.  Returns the previous setting."""
+    return bool(_lib.load().ma_set_stream_k(-1 if enabled is None else int(bool(enabled))))
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return MA_BF16

@@ -74,6 +74,48 @@ def test_gemm_epilogues():
     _check(out2, torch.relu(ref), 1e-2, "relu twin output")
 
 
+@pytest.mark.parametrize("shape", [(10960, 1024, 4096), (10953, 768, 3072), (2740, 1024, 4096), (1370, 768, 3072),
+                                   (26 * 1369 + 1, 768, 3072), (10960, 1024, 2048 + 40)])
+def test_gemm_stream_k_residual(shape):
+    """In-place fp32 residual GEMMs with K >= 2048 (fc2 of the transformer blocks): the K blocks of the last partial wave of
+    tiles are split over all CTA pairs (stream-K) and joined by the reduce-add epilogue.  Same result as the whole-tile
+    schedule up to the fp32 rounding of the partial-product sum; bias added exactly once; the whole-tile schedule stays bit
+    reproducible.  Shapes: 2 waves + 24 tiles, 1 wave + 55, fewer tiles than CTA pairs, ragged M and K."""
+    from mapanything_b200 import ops
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) / K**0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = _ref(x, w, bias, 0, gamma, res)
+    before = ops.set_stream_k(None)
+    try:
+        outs = {}
+        for mode in (False, True):
+            ops.set_stream_k(mode)
+            runs = []
+            for _ in range(2):
+                y = res.clone()
+                ops.gemm(x, w, y, bias=bias, colscale=gamma, residual=y)
+                runs.append(y)
+            outs[mode] = runs
+            _check(runs[0], ref, 5e-4, f"stream_k={mode}")
+        assert torch.equal(outs[False][0], outs[False][1]), "the whole-tile schedule is bit reproducible"
+        _check(outs[True][0], outs[False][0].float(), 2e-6, "stream-K vs whole tiles")
+        _check(outs[True][1], outs[True][0].float(), 2e-6, "stream-K run to run")
+        # without bias / LayerScale (plain x += X W^T)
+        ops.set_stream_k(True)
+        y = res.clone()
+        ops.gemm(x, w, y, residual=y)
+        _check(y, _ref(x, w, None, 0, None, res), 5e-4, "stream-K, no bias")
+    finally:
+        ops.set_stream_k(before)
+
+
 def test_gemm_row_remap_and_strides():
     from mapanything_b200 import ops
 

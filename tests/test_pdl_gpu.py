@@ -11,8 +11,10 @@ def pdl_restore():
     from mapanything_b200 import ops
 
     before = ops.set_pdl(None)
+    sk_before = ops.set_stream_k(False)   # bitwise comparisons: the stream-K reduce-add order is not bit reproducible
     yield ops
     ops.set_pdl(before)
+    ops.set_stream_k(sk_before)
 
 
 def _chain(ops, x0, w1, w2, g, b, n_iter):
