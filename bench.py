@@ -323,11 +323,17 @@ def strong_scaling_record(model, dev, rank, world, timed, peak_tf, scene=100, st
     # end to end: infer() from pinned host images, every rank reads its views' point maps / masks / poses back
     host = [im.pin_memory() for im in imgs[lo:lo + counts[rank]]]
 
+    host_out = []   # pinned result buffers, allocated by the first call
+
     def e2e():
         preds = model.infer([{"img": im, "data_norm_type": ["dinov2"]} for im in host])
-        outs = [p[k].to("cpu", non_blocking=True) for p in preds for k in ("pts3d", "conf", "mask", "camera_poses", "intrinsics")]
+        srcs = [p[k] for p in preds for k in ("pts3d", "conf", "mask", "camera_poses", "intrinsics")]
+        if not host_out:
+            host_out.extend(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in srcs)
+        for dst, src in zip(host_out, srcs):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return outs
+        return host_out
 
     e2e()
     ms_e2e = timed(e2e, 2) / 2
@@ -477,12 +483,18 @@ def run_ours(args):
 
     d2h_keys = ("pts3d", "conf", "mask", "camera_poses", "intrinsics", "metric_scaling_factor")
 
+    host_out = []   # pinned result buffers, allocated on the first step and reused (what a serving loop does)
+
     def e2e_step():
         views = [{"img": im, "data_norm_type": ["dinov2"], **e} for im, e in zip(host_imgs, host_extra)]  # pinned HOST tensors
         preds = model.infer(views)
-        outs = [p[k].to("cpu", non_blocking=True) for p in preds for k in d2h_keys]
+        srcs = [p[k] for p in preds for k in d2h_keys]
+        if not host_out:
+            host_out.extend(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in srcs)
+        for dst, src in zip(host_out, srcs):
+            dst.copy_(src, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return outs
+        return host_out
 
     def timed(fn, steps):
         barrier()
