@@ -194,6 +194,10 @@ int ma_layernorm(const void* in, int in_dtype, int64_t ld_in, void* out, int out
                  int64_t in_group_stride, int64_t in_row_offset, int64_t out_group_stride, int64_t out_row_offset,
                  void* stream);
 
+/* dst[0:n] = value, fp32 (initial -inf maxima of the partial softmax states joined by ma_attention_merge; keeps the step free
+ * of library kernels).  No reference counterpart. */
+int ma_fill_f32(float* dst, int64_t n, float value, void* stream);
+
 /* dst[g*group_stride + row_offset][0:C] = a[0:C] + b[0:C] (b may be NULL) for g in [0, groups): cls token +
  * pos_embed[0] (reference vision_transformer.py:252-253), scale token row (model.py:1524-1535). fp32. */
 int ma_set_rows(float* dst, int64_t ld, int groups, int64_t group_stride, int64_t row_offset, const float* a,

@@ -167,6 +167,11 @@ __global__ void set_rows_kernel(float* __restrict__ dst, int64_t ld, int64_t gro
   for (int c = threadIdx.x; c < C; c += blockDim.x) d[c] = a[c] + (b ? b[c] : 0.f);
 }
 
+// fill_f32: dst[0:n] = value (the -inf maxima of unused partial softmax states in front of ma_attention_merge).
+__global__ void fill_f32_kernel(float* __restrict__ dst, int64_t n, float value) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = value;
+}
+
 // ----------------------------------------------------------------------------------------------
 // im2col for 3x3 / pad 1 / stride s convolutions over NHWC bf16: out[(i,yo,xo)][tap*C + c], tap = ky*3+kx.
 // One thread moves 8 channels (16 B); consecutive threads walk channels then taps -> coalesced both ways.
@@ -747,6 +752,13 @@ extern "C" int ma_set_rows(float* dst, int64_t ld, int groups, int64_t group_str
                            const float* b, int C, void* stream) {
   MA_REQUIRE(dst && a && groups > 0 && C > 0, "ma_set_rows: bad arguments");
   set_rows_kernel<<<groups, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, ld, group_stride, row_offset, a, b, C);
+  MA_CHECK_CUDA(cudaGetLastError());
+  return MA_OK;
+}
+
+extern "C" int ma_fill_f32(float* dst, int64_t n, float value, void* stream) {
+  MA_REQUIRE(dst && n > 0, "ma_fill_f32: bad arguments");
+  fill_f32_kernel<<<grid_for(n, 256, device_sm_count() * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, n, value);
   MA_CHECK_CUDA(cudaGetLastError());
   return MA_OK;
 }

@@ -92,6 +92,7 @@ SIGNATURES = {
     "ma_attention_merge": (_i, [_p, _i64, _i64, _p, _i64, _i, _i64, _i, _f, _p, _i64, _i, _p]),
     "ma_patchify": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ma_layernorm": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _p, _i, _i, _f, _i, _i64, _i64, _i64, _i64, _p]),
+    "ma_fill_f32": (_i, [_p, _i64, _f, _p]),
     "ma_set_rows": (_i, [_p, _i64, _i, _i64, _i64, _p, _p, _i, _p]),
     "ma_im2col3x3": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ma_pixel_shuffle": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),

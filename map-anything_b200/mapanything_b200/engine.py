@@ -396,7 +396,7 @@ class Engine:
             return ops.attention(q, k, v, out, **common)
         first, parts = pick
         so = self._empty(parts, q_len, heads * 64, dtype=torch.float32)
-        sm = torch.full((parts, q_len, heads), float("-inf"), device=self.device, dtype=torch.float32)
+        sm = ops.fill_f32(self._empty(parts, q_len, heads, dtype=torch.float32), float("-inf"))
         ops.attention(q, k, v, out, state=(so, sm), kv_split=parts, kv_split_from=first, **common)
         return ops.attention_merge((so, sm), out, num_heads=heads, first_slot=first)
 
@@ -454,7 +454,7 @@ class Engine:
                 so = self._empty(s_l + s_r, rows, dim, dtype=torch.float32)
                 sm = self._empty(s_l + s_r, rows, heads, dtype=torch.float32)
                 bufs["state"] = (so, sm)
-            sm.fill_(float("-inf"))                          # unused partial slots are skipped by the merge
+            ops.fill_f32(sm, float("-inf"))                  # unused partial slots are skipped by the merge
             ops.attention(q, K, Vv, None, kv_len=rows, kv_segments=plan.local_segment(), state=(so[:s_l], sm[:s_l]),
                           state_out=True, kv_split=s_l, kv_split_from=f_l, **common)
             if self.ag_wait_events is not None:

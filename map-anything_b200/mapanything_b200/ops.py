@@ -402,6 +402,14 @@ def im2col3x3(x: torch.Tensor, out: torch.Tensor, stride: int = 1) -> torch.Tens
     return out
 
 
+def fill_f32(x: torch.Tensor, value: float) -> torch.Tensor:
+    """x[...] = value (contiguous fp32; ma_fill_f32)."""
+    _req(x, torch.float32, "x")
+    with launch("fill"):
+        check(_lib.load().ma_fill_f32(x.data_ptr(), x.numel(), float(value), _stream()), "ma_fill_f32")
+    return x
+
+
 def pixel_shuffle(x: torch.Tensor, out: torch.Tensor, n: int, h: int, w: int, C_: int, s: int) -> torch.Tensor:
     _req(x, torch.bfloat16, "x")
     _req(out, torch.bfloat16, "out")
