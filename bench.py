@@ -463,6 +463,8 @@ def run_ours(args):
         model.geometric_input_config.update({"overall_prob": 1.0, "dropout_prob": 0.0, "ray_dirs_prob": 1.0, "depth_prob": 1.0,
                                              "cam_prob": 1.0})
     model.engine()
+    if args.cuda_graph and world == 1:
+        model.enable_cuda_graphs()
     sharded_rel = None
     if shard:
         sharded_rel = sharded_vs_single(model, dev, rank, world, V)   # leaves view sharding enabled
@@ -530,11 +532,13 @@ def run_ours(args):
         # per-launch event times would count the time spent waiting for SMs)
         eng = model.engine()
         n_streams, eng.encoder_streams = eng.encoder_streams, 1
+        graphs, model._graphs = model._graphs, None   # the instrumented pass launches kernel by kernel
         ops.PROFILE = []
         barrier()
         fwd_step()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
+        model._graphs = graphs
         eng.encoder_streams = n_streams
         for _ in range(2):
             e2e_step()
@@ -609,6 +613,7 @@ def run_ours(args):
                     "ms_per_step": e2e_ms_step},
             "gpu_launches": launches,
             "clocks": clocks.summary(),
+            "cuda_graph": bool(args.cuda_graph and world == 1),
         }
         emit(line)
     if world > 1:
@@ -663,6 +668,8 @@ def main():
                     help="N > 1: one scene of views*N views sharded by view (default) or N independent scenes")
     ap.add_argument("--no-eager", action="store_true", help="skip the GPU-eager (PyTorch library) baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="A/B runs only: skip the CPU baseline leg too (cpu_baseline: null)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="N = 1: replay the step as one captured CUDA graph (model.enable_cuda_graphs(); small scenes are launch-bound)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the fixed 100-view strong-scaling record")
     ap.add_argument("--profile-mode", action="store_true", help="1 warm-up + 1 step only, for ncu captures (prints no bench line)")
     args = ap.parse_args()

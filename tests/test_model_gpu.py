@@ -356,3 +356,45 @@ def test_infer_confidence_mask_removes_requested_fraction():
         assert torch.equal(c["mask"][0, ..., 0].cpu(), want)
         kept = (conf > thr).float().mean().item()
         assert 0.70 <= kept <= 0.76
+
+
+def test_cuda_graph_replay_matches_the_normal_path():
+    """enable_cuda_graphs(): forward / infer replayed as one captured graph per input signature give the same bits as the
+    kernel-by-kernel path (same kernels, same order), follow new inputs, return tensors the next call does not overwrite,
+    and leave ineligible calls (geometric inputs, memory_efficient_inference) on the normal path."""
+    from mapanything_b200 import ops
+    from oracle.config import tiny_config
+
+    _, model = _build(tiny_config, seed=0, init="ref")
+    va, vb = _views(3, 70, seed=5), _views(3, 70, seed=6)
+    cuda = lambda vs: [{**v, "img": v["img"].cuda()} for v in vs]  # noqa: E731
+    ref_a, ref_b = model(cuda(va)), model(cuda(vb))
+    ref_inf = model.infer([dict(v) for v in vb])
+    model.enable_cuda_graphs()
+    n0 = ops.LAUNCHES
+    got_a = model(cuda(va))            # captures
+    per_step = ops.LAUNCHES - n0
+    got_b = model(cuda(vb))            # replays with new inputs
+    assert len(model._graphs) == 1 and ops.LAUNCHES - n0 - per_step > 0
+    got_a2 = model(va)                 # host tensors are accepted too (copied into the static buffers)
+    for ref, got in ((ref_a, got_a), (ref_b, got_b), (ref_a, got_a2)):
+        for r, g in zip(ref, got):
+            assert set(r) == set(g)
+            for k in r:
+                assert torch.equal(r[k], g[k]), k
+    for r, g in zip(ref_a, got_a):     # the first result survived two more replays
+        assert torch.equal(r["pts3d"], g["pts3d"])
+    got_inf = model.infer([dict(v) for v in vb])
+    for r, g in zip(ref_inf, got_inf):
+        for k in r:
+            assert torch.equal(r[k], g[k]), k
+    # another signature -> a second graph; ineligible calls -> the normal path, no new graph
+    model(cuda(_views(2, 70, seed=7)))
+    assert len(model._graphs) == 2
+    model(cuda(va), memory_efficient_inference=True)
+    geo = [dict(v) for v in va]
+    geo[0]["intrinsics"] = torch.tensor([[[60.0, 0, 35], [0, 60.0, 35], [0, 0, 1]]])
+    model.infer(geo)
+    assert len(model._graphs) == 2
+    model.enable_cuda_graphs(False)
+    assert model._graphs is None
