@@ -45,6 +45,19 @@ def test_struct_layouts_match_header_sizes():
 
     assert ctypes.sizeof(_lib.GemmEpilogue) == 8 + 8 + 4 + 4 + 8 + 8 + 8 + 8 + 4 + 4 + 8 + 8 + 4 * 4 + 3 * 8
     assert ctypes.sizeof(_lib.AttnExt) == 4 + 4 + 64 + 64 + 8 + 8 + 8 + 4 + 4 + 8 + 8
+    assert ctypes.sizeof(_lib.DecodeSpec) == 5 * 4 + 4   # ma_decode_spec: five ints + conf_vmin
+    # the selector codes of the binding are the header's #defines
+    hdr = HEADER.read_text()
+    import re
+
+    for name, code in {"MA_REP_POINTMAP": _lib.MA_REP["pointmap"], "MA_REP_RAYMAP_DEPTH": _lib.MA_REP["raymap+depth"],
+                       "MA_REP_RAYDIRS_DEPTH_POSE": _lib.MA_REP["raydirs+depth+pose"],
+                       "MA_REP_CAMPOINTMAP_POSE": _lib.MA_REP["campointmap+pose"],
+                       "MA_REP_POINTMAP_RAYDIRS_DEPTH_POSE": _lib.MA_REP["pointmap+raydirs+depth+pose"],
+                       "MA_PTS_LINEAR": _lib.MA_PTS["linear"], "MA_PTS_EXP": _lib.MA_PTS["exp"],
+                       "MA_PTS_Z_EXP": _lib.MA_PTS["z_exp"]}.items():
+        m = re.search(rf"#define {name} (\d+)", hdr)
+        assert m and int(m.group(1)) == code, name
 
 
 def test_bad_arguments_return_status_not_crash():
@@ -60,6 +73,11 @@ def test_bad_arguments_return_status_not_crash():
     ep = _lib.GemmEpilogue()
     rc = lib.ma_gemm_bf16(None, 0, None, 0, 0, 0, 0, ctypes.byref(ep), 0, None)
     assert rc == -1
+    spec = _lib.DecodeSpec(rep=7)
+    rc = lib.ma_decode_scene(ctypes.byref(spec), None, 8, None, None, 1, 4, None, None, None, None, None, None, None, None, None,
+                             None, None, None)
+    assert rc == -1 and b"ma_decode_scene" in lib.ma_last_error()
+    assert lib.ma_set_stream_k(-1) in (0, 1)   # query only
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
