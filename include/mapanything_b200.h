@@ -47,10 +47,11 @@ int ma_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int ma_set_pdl(int enabled);
 /* Stream-K tail of the in-place fp32 residual GEMMs (ma_gemm_bf16 with residual == out, fp32, K >= 2048: fc2 of every
  * transformer block): the K blocks of the last, partially filled wave of tiles are split evenly over all CTA pairs and the
- * partial products are joined by the same bulk reduce-add that applies the residual.  Faster (172 tiles on 74 pairs: 149
- * instead of 192 K blocks per pair), but the fp32 sum of an element's partial products is formed in arrival order, so such
- * a GEMM is reproducible to fp32 rounding, not bit for bit.  enabled: 0 / 1, or -1 to query only.  Returns the previous
- * setting.  Initial value: environment variable MA_GEMM_STREAMK, else on. */
+ * partial products are joined by the same bulk reduce-add that applies the residual.  Shorter critical path (172 tiles on 74
+ * pairs: 149 instead of 192 K blocks per pair; -11 % for such a launch alone, +0.2 - 0.7 % on the 8-view step), but the fp32
+ * sum of an element's partial products is formed in arrival order, so such a GEMM is reproducible to fp32 rounding, not bit
+ * for bit.  enabled: 0 / 1, or -1 to query only.  Returns the previous setting.  Initial value: environment variable
+ * MA_GEMM_STREAMK, else on. */
 int ma_set_stream_k(int enabled);
 /* Which kernel the last ma_gemm_bf16 / ma_conv3x3_bf16 call of THIS thread launched, as a block_n code (64 / 128 / 256 = the
  * one-CTA kernel gemm_bf16_tcgen05_kernel<block_n>, 2128 / 2256 = the CTA-pair kernel gemm_bf16_2cta_kernel<block_n - 2000>);

@@ -296,8 +296,8 @@ class MapAnything(nn.Module, PyTorchModelHubMixin):
 
     def enable_cuda_graphs(self, enabled: bool = True) -> None:
         """Replay forward() / infer() as ONE captured CUDA graph per input signature (number of views, per-view batch, image
-        size) instead of ~400 kernel launches from Python.  The step of a small scene is launch-bound (2 views: 7.8 ms for
-        4.9 ms of tensor work); a graph removes the host from it.  Applies to image-only scenes on one GPU without
+        size) instead of ~400 kernel launches from Python.  The step of a small scene is partly launch-bound (2 views: 7.85 ms
+        kernel by kernel, 7.43 ms replayed); a graph removes the host from it.  Applies to image-only scenes on one GPU without
         memory_efficient_inference; every other call runs the normal path.  The first call of a signature runs the step
         eagerly once (lazy initialisation), captures it and keeps the captured activations alive (one private memory pool
         per signature); inputs are copied into the graph's static image buffers, outputs are copied out, so the returned
