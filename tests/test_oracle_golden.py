@@ -220,3 +220,43 @@ def test_small_vit_matches_huggingface_dinov2():
         ours = m.forward_patch_tokens(img)
         theirs = hf(pixel_values=img).last_hidden_state[:, 1:]
     assert torch.allclose(ours, theirs, atol=2e-5), (ours - theirs).abs().max()
+
+
+def test_adaptor_known_answers():
+    """Known-answer tests for the restated adaptor arithmetic of the other scene representations (the published DUSt3R /
+    MoGe forms the uniception adaptors wrap; oracle/uniception_modules.py): hand-computed values."""
+    import math
+
+    from oracle import uniception_modules as U
+
+    assert U.split_adaptor_type("pointmap+raydirs+depth+pose+confidence+mask") == ("pointmap+raydirs+depth+pose", True, True)
+    assert U.split_adaptor_type("raymap+depth+mask") == ("raymap+depth", False, True)
+    assert U.split_adaptor_type("campointmap+pose") == ("campointmap+pose", False, False)
+    with pytest.raises(ValueError):
+        U.split_adaptor_type("pointcloud+confidence")
+    x = torch.tensor([3.0, 0.0, 4.0]).view(1, 3, 1, 1)                       # norm 5
+    p = U.point_activation(x, "exp").flatten()
+    assert torch.allclose(p, torch.tensor([0.6, 0.0, 0.8]) * math.expm1(5.0), rtol=1e-6)
+    p = U.point_activation(torch.tensor([0.5, -2.0, math.log(3.0)]).view(1, 3, 1, 1), "z_exp").flatten()
+    assert torch.allclose(p, torch.tensor([1.5, -6.0, 3.0]), rtol=1e-6)
+    assert torch.equal(U.point_activation(x, "linear"), x)
+    # pointmap+confidence+mask: channels [xyz | confidence logit | mask logit]
+    raw = torch.tensor([0.0, 0.0, 2.0, math.log(2.0), -1.0]).view(1, 5, 1, 1)
+    value, conf, mask, logits = U.dense_adaptor(raw, "pointmap+confidence+mask", {"pointmap_mode": "exp", "confidence_vmin": 1})
+    assert torch.allclose(value.flatten(), torch.tensor([0.0, 0.0, math.expm1(2.0)]), rtol=1e-6)
+    assert abs(conf.item() - 3.0) < 1e-6 and abs(mask.item() - 1 / (1 + math.e)) < 1e-6 and logits.item() == -1.0
+    # raymap+depth: origin linear, direction normalised, depth = exp
+    raw = torch.tensor([1.0, 2.0, 3.0, 0.0, 3.0, 4.0, math.log(2.0)]).view(1, 7, 1, 1)
+    value, conf, mask, logits = U.dense_adaptor(raw, "raymap+depth", {})
+    assert conf is None and mask is None and logits is None
+    assert torch.allclose(value.flatten(), torch.tensor([1.0, 2.0, 3.0, 0.0, 0.6, 0.8, 2.0]), rtol=1e-6)
+    # the released adaptor through the generic entry = the dedicated function
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randn(2, 6, 3, 3, generator=g)
+    a = U.dense_adaptor(raw, "raydirs+depth+pose+confidence+mask", {"confidence_vmin": 1})
+    b = U.dense_adaptor_raydirs_depth_conf_mask(raw)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    # linear head: pixel shuffle of a 1x1 conv
+    head = U.LinearFeature(input_feature_dim=4, output_dim=2, patch_size=3)
+    out = head(torch.randn(1, 4, 2, 2, generator=g))
+    assert out.shape == (1, 2, 6, 6)
